@@ -1,0 +1,92 @@
+// Shared helpers for the dynaphopy_b200 CUDA kernels (sm_100a).
+#pragma once
+
+#ifdef DP_EMUL
+#include "dp_emul.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/dynaphopy_b200.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace dp {
+
+// ---- error plumbing ------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define DP_CUDA_OK(expr)                                            \
+    do {                                                            \
+        cudaError_t dp_e_ = (expr);                                 \
+        if (dp_e_ != cudaSuccess) return dp::cuda_fail(dp_e_, #expr); \
+    } while (0)
+
+#define DP_REQUIRE(cond, code, ...)          \
+    do {                                     \
+        if (!(cond)) {                       \
+            dp::set_error(__VA_ARGS__);      \
+            return (code);                   \
+        }                                    \
+    } while (0)
+
+// ---- launch / dynamic shared memory, identical source for nvcc and the test emulator ---
+#ifdef DP_EMUL
+#define DP_LAUNCH(kfn, grid, block, smem, stream, ...) \
+    dp_emul::launch((grid), (block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); })
+#define DP_DYNSMEM(type, name) type* name = reinterpret_cast<type*>(dp_emul::tls_worker()->dyn_smem)
+#define DP_SET_SMEM(kfn, bytes) cudaSuccess
+#else
+#define DP_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DP_DYNSMEM(type, name)                                   \
+    extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+    type* name = reinterpret_cast<type*>(name##_raw_)
+#define DP_SET_SMEM(kfn, bytes) \
+    cudaFuncSetAttribute((const void*)(kfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+
+// ---- small device helpers ---------------------------------------------------------------
+template <typename T> __host__ __device__ __forceinline__ T imin(T a, T b) { return a < b ? a : b; }
+template <typename T> __host__ __device__ __forceinline__ T imax(T a, T b) { return a > b ? a : b; }
+
+typedef double2 cplx;   // (re, im)
+
+__host__ __device__ __forceinline__ cplx cmake(double r, double i) { return make_double2(r, i); }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {   // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+__host__ __device__ __forceinline__ cplx cmul_i(cplx a) { return make_double2(-a.y, a.x); }      //  i*a
+__host__ __device__ __forceinline__ cplx cmul_mi(cplx a) { return make_double2(a.y, -a.x); }     // -i*a
+__host__ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+// exp(-2*pi*i * num/den), sign = -1 forward
+__device__ __forceinline__ cplx root_of_unity(long long num, long long den, int sign) {
+    double s, c;
+    long long r = num % den;
+    sincospi(2.0 * (double)r / (double)den, &s, &c);
+    return make_double2(c, sign < 0 ? -s : s);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+int sm_count();
+
+}  // namespace dp

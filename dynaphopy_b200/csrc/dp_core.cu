@@ -1,0 +1,53 @@
+// Error plumbing and device queries of the dynaphopy_b200 C ABI.
+#include <cstdarg>
+
+#include "dp_common.cuh"
+
+namespace dp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return DP_ERR_CUDA;
+}
+
+int sm_count() {
+#ifdef DP_EMUL
+    return 4;
+#else
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached = n;
+    return n;
+#endif
+}
+
+}  // namespace dp
+
+extern "C" {
+
+const char* dp_version(void) { return "dynaphopy_b200 0.1.0 (sm_100a)"; }
+
+const char* dp_last_error(void) { return dp::g_err; }
+
+int dp_sm_count(void) {
+    int n = dp::sm_count();
+    if (n <= 0) {
+        dp::set_error("no CUDA device available (dynaphopy_b200 has no CPU fallback)");
+        return DP_ERR_CUDA;
+    }
+    return n;
+}
+
+}  // extern "C"

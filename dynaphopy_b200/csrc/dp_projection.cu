@@ -1,0 +1,230 @@
+// A2 (dense form) and A3: wave-vector projection for arbitrary q lists and the eigenvector
+// contraction.  Reference: dynaphopy/projection.py:4-40 and :43-54.
+//
+// Dense projection = real(3T x N) x complex(N x Q) contraction per primitive type; the
+// phases exp(-i q.r_i) * sqrt(m_i) / sqrt(N/n_p) are tabulated once per call (Q x N), the
+// main kernel stages frame and phase tiles in shared memory and keeps 3 complex
+// accumulators per (frame, q) in registers.  Bound: fp64 FMA (12 flop per atom-frame-q).
+// The commensurate fast path (3-D DFT, HBM-bound) lives in dp_projection_fft.cu.
+#include <algorithm>
+#include <vector>
+
+#include "dp_common.cuh"
+
+namespace dp {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ph[q][a] for atoms in type-sorted order a -> atom_list[a]
+__global__ void __launch_bounds__(256)
+phase_table_kernel(const double* __restrict__ q_cart, const double* __restrict__ pos0,
+                   const int* __restrict__ atom_list, const double* __restrict__ sqrt_mass, int N, int Q,
+                   double norm, cplx* __restrict__ ph) {
+    int64_t total = (int64_t)Q * N;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        int q = (int)(idx / N), a = (int)(idx % N);
+        int i = atom_list[a];
+        double x = q_cart[q * 3 + 0] * pos0[i * 3 + 0] + q_cart[q * 3 + 1] * pos0[i * 3 + 1] +
+                   q_cart[q * 3 + 2] * pos0[i * 3 + 2];
+        double s, c;
+        sincos(x, &s, &c);
+        double w = norm * (sqrt_mass ? sqrt_mass[i] : 1.0);
+        ph[idx] = make_double2(c * w, -s * w);
+    }
+}
+
+constexpr int PJ_TQ = 32;   // q per CTA (threadIdx.x)
+constexpr int PJ_TT = 8;    // frames per CTA (threadIdx.y)
+constexpr int PJ_AC = 32;   // atoms per shared-memory chunk
+
+template <int NC>   // 1: real velocities, 2: complex128 velocities
+__global__ void __launch_bounds__(PJ_TQ* PJ_TT)
+project_dense_kernel(const double* __restrict__ v, const cplx* __restrict__ ph,
+                     const int* __restrict__ atom_list, const int* __restrict__ type_off, int N,
+                     int n_prim, int64_t T, int Q, int p_first, int p_last, cplx* __restrict__ out) {
+    __shared__ double vs[PJ_TT][PJ_AC][3 * NC];
+    __shared__ cplx phs[PJ_AC][PJ_TQ + 1];
+    const int tq = threadIdx.x, tt = threadIdx.y;
+    const int lin = tt * PJ_TQ + tq;
+    const int64_t t0 = (int64_t)blockIdx.x * PJ_TT;
+    const int q0 = blockIdx.y * PJ_TQ;
+    const int64_t t = t0 + tt;
+    const int q = q0 + tq;
+    for (int p = p_first; p <= p_last; p++) {
+        cplx acc[3];
+        acc[0] = acc[1] = acc[2] = make_double2(0.0, 0.0);
+        const int a_begin = type_off[p], a_end = type_off[p + 1];
+        for (int a0 = a_begin; a0 < a_end; a0 += PJ_AC) {
+            const int na = imin(PJ_AC, a_end - a0);
+            __syncthreads();
+            for (int e = lin; e < PJ_TT * PJ_AC * 3 * NC; e += PJ_TQ * PJ_TT) {
+                int ft = e / (PJ_AC * 3 * NC), rem = e % (PJ_AC * 3 * NC);
+                int aa = rem / (3 * NC), kk = rem % (3 * NC);
+                double val = 0.0;
+                if (aa < na && t0 + ft < T) {
+                    int i = atom_list[a0 + aa];
+                    val = __ldg(v + ((t0 + ft) * N + i) * (3 * NC) + kk);
+                }
+                vs[ft][aa][kk] = val;
+            }
+            for (int e = lin; e < PJ_AC * PJ_TQ; e += PJ_TQ * PJ_TT) {
+                int fq = e / PJ_AC, aa = e % PJ_AC;
+                cplx w = make_double2(0.0, 0.0);
+                if (aa < na && q0 + fq < Q) w = ph[(int64_t)(q0 + fq) * N + a0 + aa];
+                phs[aa][fq] = w;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int aa = 0; aa < PJ_AC; aa++) {
+                cplx w = phs[aa][tq];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (NC == 1) {
+                        double x = vs[tt][aa][k];
+                        acc[k].x = fma(x, w.x, acc[k].x);
+                        acc[k].y = fma(x, w.y, acc[k].y);
+                    } else {
+                        double xr = vs[tt][aa][2 * k], xi = vs[tt][aa][2 * k + 1];
+                        acc[k].x = fma(xr, w.x, fma(-xi, w.y, acc[k].x));
+                        acc[k].y = fma(xr, w.y, fma(xi, w.x, acc[k].y));
+                    }
+                }
+            }
+        }
+        if (t < T && q < Q) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) out[((t * Q + q) * n_prim + p) * 3 + k] = acc[k];
+        }
+    }
+}
+
+// vq[t,q,s] = sum_p ( sum_k vc[t,q,p,k] conj(e[q,s,p,k]) ): CTA = one q, PH_TF frames.
+constexpr int PH_TF = 64;
+
+__global__ void __launch_bounds__(256)
+project_phonon_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig, int64_t T, int Q, int M,
+                      cplx* __restrict__ vq) {
+    DP_DYNSMEM(cplx, sm);
+    cplx* es = sm;                      // [M][M]   e[q][s][j]
+    cplx* vs = sm + (size_t)M * M;      // [PH_TF][M]
+    const int q = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * PH_TF;
+    const int nthreads = blockDim.x;
+    for (int e = threadIdx.x; e < M * M; e += nthreads) es[e] = eig[(int64_t)q * M * M + e];
+    for (int e = threadIdx.x; e < PH_TF * M; e += nthreads) {
+        int f = e / M, j = e % M;
+        cplx val = make_double2(0.0, 0.0);
+        if (t0 + f < T) val = vc[((t0 + f) * Q + q) * M + j];
+        vs[e] = val;
+    }
+    __syncthreads();
+    const int np = M / 3;
+    for (int e = threadIdx.x; e < PH_TF * M; e += nthreads) {
+        int f = e / M, s = e % M;
+        if (t0 + f >= T) continue;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int p = 0; p < np; p++) {
+            cplx part = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                cplx a = vs[f * M + p * 3 + k], b = es[s * M + p * 3 + k];
+                part = cadd(part, cmulc(a, b));
+            }
+            acc = cadd(acc, part);
+        }
+        vq[((t0 + f) * Q + q) * M + s] = acc;
+    }
+}
+
+}  // namespace dp
+
+extern "C" {
+
+size_t dp_project_wave_vector_workspace_bytes(int N, int Q) {
+    if (N <= 0 || Q <= 0) return 0;
+    return dp::align_up((size_t)Q * 3 * sizeof(double), 256) + dp::align_up((size_t)N * sizeof(int), 256) +
+           dp::align_up(1024 * sizeof(int), 256) + dp::align_up((size_t)Q * N * sizeof(dp::cplx), 256);
+}
+
+int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt_mass,
+                           const double* pos0, const int* type_idx, int N, int n_prim, int64_t T,
+                           const double* q_cart, int Q, int project_on_atom, double* out_vc,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(v && pos0 && type_idx && q_cart && out_vc && workspace, DP_ERR_INVALID,
+               "dp_project_wave_vector: null pointer");
+    DP_REQUIRE(N > 0 && n_prim > 0 && n_prim < 1024 && T >= 0 && Q > 0, DP_ERR_INVALID,
+               "dp_project_wave_vector: bad sizes N=%d n_prim=%d T=%lld Q=%d", N, n_prim, (long long)T, Q);
+    DP_REQUIRE(project_on_atom < n_prim, DP_ERR_INVALID, "dp_project_wave_vector: project_on_atom=%d >= n_prim=%d",
+               project_on_atom, n_prim);
+    DP_REQUIRE(workspace_bytes >= dp_project_wave_vector_workspace_bytes(N, Q), DP_ERR_WORKSPACE,
+               "dp_project_wave_vector: workspace too small");
+    if (T == 0) return DP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // type-sorted atom list (stable: reference order inside a type is preserved)
+    std::vector<int> list(N), off(n_prim + 1, 0);
+    for (int i = 0; i < N; i++) {
+        DP_REQUIRE(type_idx[i] >= 0 && type_idx[i] < n_prim, DP_ERR_INVALID,
+                   "dp_project_wave_vector: type_idx[%d]=%d out of range", i, type_idx[i]);
+        off[type_idx[i] + 1]++;
+    }
+    for (int p = 0; p < n_prim; p++) off[p + 1] += off[p];
+    {
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (int i = 0; i < N; i++) list[cur[type_idx[i]]++] = i;
+    }
+    char* ws = (char*)workspace;
+    double* d_q = (double*)ws;            ws += dp::align_up((size_t)Q * 3 * sizeof(double), 256);
+    int* d_list = (int*)ws;               ws += dp::align_up((size_t)N * sizeof(int), 256);
+    int* d_off = (int*)ws;                ws += dp::align_up(1024 * sizeof(int), 256);
+    dp::cplx* d_ph = (dp::cplx*)ws;
+    DP_CUDA_OK(cudaMemcpyAsync(d_q, q_cart, (size_t)Q * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(d_list, list.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(d_off, off.data(), (size_t)(n_prim + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+#ifndef DP_EMUL
+    DP_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope below
+#endif
+    double norm = 1.0 / sqrt((double)N / (double)n_prim);
+    {
+        int64_t total = (int64_t)Q * N;
+        int grid = (int)dp::imin<int64_t>((total + 255) / 256, (int64_t)dp::imax(dp::sm_count(), 1) * 16);
+        auto k = dp::phase_table_kernel;
+        DP_LAUNCH(k, dim3(grid), dim3(256), 0, st, d_q, pos0, d_list, sqrt_mass, N, Q, norm, d_ph);
+        DP_CUDA_OK(cudaGetLastError());
+    }
+    int p_first = 0, p_last = n_prim - 1;
+    if (project_on_atom > -1) {
+        DP_CUDA_OK(cudaMemsetAsync(out_vc, 0, (size_t)T * Q * n_prim * 3 * sizeof(dp::cplx), st));
+        p_first = p_last = project_on_atom;
+    }
+    dim3 grid((unsigned)((T + dp::PJ_TT - 1) / dp::PJ_TT), (unsigned)((Q + dp::PJ_TQ - 1) / dp::PJ_TQ));
+    dim3 block(dp::PJ_TQ, dp::PJ_TT);
+    DP_REQUIRE(grid.y <= 65535, DP_ERR_UNSUPPORTED, "dp_project_wave_vector: Q=%d too large for one launch", Q);
+    if (v_is_complex) {
+        auto k = dp::project_dense_kernel<2>;
+        DP_LAUNCH(k, grid, block, 0, st, v, d_ph, d_list, d_off, N, n_prim, T, Q, p_first, p_last, (dp::cplx*)out_vc);
+    } else {
+        auto k = dp::project_dense_kernel<1>;
+        DP_LAUNCH(k, grid, block, 0, st, v, d_ph, d_list, d_off, N, n_prim, T, Q, p_first, p_last, (dp::cplx*)out_vc);
+    }
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+int dp_project_phonon(const double* vc, const double* eig, int64_t T, int Q, int M, double* vq, void* stream) {
+    DP_REQUIRE(vc && eig && vq, DP_ERR_INVALID, "dp_project_phonon: null pointer");
+    DP_REQUIRE(T >= 0 && Q > 0 && M > 0 && M % 3 == 0, DP_ERR_INVALID, "dp_project_phonon: bad sizes (M must be 3*n_prim)");
+    DP_REQUIRE(Q <= 65535, DP_ERR_UNSUPPORTED, "dp_project_phonon: Q=%d too large for one launch", Q);
+    if (T == 0) return DP_OK;
+    size_t smem = ((size_t)M * M + (size_t)dp::PH_TF * M) * sizeof(dp::cplx);
+    DP_REQUIRE(smem <= 200 * 1024, DP_ERR_UNSUPPORTED, "dp_project_phonon: M=%d too large", M);
+    auto k = dp::project_phonon_kernel;
+    DP_CUDA_OK(DP_SET_SMEM(k, smem));
+    dim3 grid((unsigned)((T + dp::PH_TF - 1) / dp::PH_TF), (unsigned)Q);
+    DP_LAUNCH(k, grid, dim3(256), smem, (cudaStream_t)stream, (const dp::cplx*)vc, (const dp::cplx*)eig, T, Q, M,
+              (dp::cplx*)vq);
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+}  // extern "C"

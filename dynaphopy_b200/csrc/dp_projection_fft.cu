@@ -1,0 +1,333 @@
+// A2, commensurate form: wave-vector projection of the whole q list as a batched 3-D DFT.
+// Reference semantics: dynaphopy/projection.py:4-40 with the supercell atom order of
+// dynaphopy/atoms.py:139-156 (i = u*Nc + x + Nx*(y + Ny*z)).
+//
+// For q commensurate with the (diagonal) supercell, exp(-i q.R_cell) = exp(-2 pi i m.n/dims), so
+//   vc[t,q,p,k] = sum_{u in p} twiddle[q,u] * DFT3_{cells}( v[t, u, cell, k] )[ m(q) ]
+// and one frame is read from HBM exactly once for all Q wave vectors (24 B per atom-frame in,
+// 16*3*n_prim*Q B per frame out) instead of once per q.
+//
+// Work unit = (frame, job).  A job packs TWO real sequences into one complex 3-D transform
+// c = a + i b (e.g. the x and y components of one unit-cell atom, or the z components of two
+// atoms) and separates them in the epilogue with A[m] = (C[m] + conj C[-m]) / 2,
+// B[m] = (C[m] - conj C[-m]) / 2i.  The transform runs in shared memory (Nc*16 B, row pitch
+// padded to an odd number of elements): three axis passes, each thread owning whole pencils in
+// registers and using compile-time unrolled mixed-radix codelets (radix 4/2/3/5, generic odd
+// primes) whose twiddles are immediate constants.  Persistent grid, one CTA per work unit,
+// sized as a multiple of the SM count.
+#include <algorithm>
+#include <vector>
+
+#include "dp_common.cuh"
+#include "dp_fft.cuh"
+
+#ifdef DP_EMUL
+#define DP_ROOTS_QUALIFIER static const
+#else
+#define DP_ROOTS_QUALIFIER static __device__ __constant__
+#endif
+#include "dp_roots.h"
+
+namespace dp {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------- compile-time pencil DFT codelets ---------------------------------------------
+__host__ __device__ constexpr int pencil_radix(int n) {
+    if (n % 4 == 0) return 4;
+    for (int f = 2; f <= n; f++)
+        if (n % f == 0) return f;
+    return n;
+}
+
+__device__ __forceinline__ cplx root_const(int n, int j) {      // exp(-2 pi i j / n), forward
+    const int idx = n * (n - 1) / 2 + (j % n);
+    return make_double2(dp_roots_re[idx], dp_roots_im[idx]);
+}
+
+template <int R> __device__ __forceinline__ void pencil_bfly(cplx* t) {
+    if constexpr (R == 1) return;
+    else if constexpr (R == 2) bfly2<-1>(t);
+    else if constexpr (R == 3) bfly3<-1>(t);
+    else if constexpr (R == 4) bfly4<-1>(t);
+    else if constexpr (R == 5) bfly5<-1>(t);
+    else {                               // generic odd prime: O(R^2) with constant roots
+        cplx o[R];
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            cplx acc = t[0];
+#pragma unroll
+            for (int r = 1; r < R; r++) acc = cadd(acc, cmul(t[r], root_const(R, (r * u) % R)));
+            o[u] = acc;
+        }
+#pragma unroll
+        for (int u = 0; u < R; u++) t[u] = o[u];
+    }
+}
+
+// forward DFT of N points held in registers, natural order in and out (decimation in time):
+//   out[k + M u] = sum_r w_R^(r u) [ w_N^(r k) DFT_M(in[m R + r])[k] ]
+template <int N> struct PencilDft {
+    static constexpr int R = pencil_radix(N);
+    static constexpr int M = N / R;
+    __device__ __forceinline__ static void run(const cplx* in, cplx* out) {
+        cplx sub[R][M];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            cplx g[M];
+#pragma unroll
+            for (int mm = 0; mm < M; mm++) g[mm] = in[mm * R + r];
+            PencilDft<M>::run(g, sub[r]);
+        }
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            cplx t[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r == 0 || k == 0) t[r] = sub[r][k];
+                else t[r] = cmul(sub[r][k], root_const(N, r * k));
+            }
+            pencil_bfly<R>(t);
+#pragma unroll
+            for (int u = 0; u < R; u++) out[k + M * u] = t[u];
+        }
+    }
+};
+template <> struct PencilDft<1> {
+    __device__ __forceinline__ static void run(const cplx* in, cplx* out) { out[0] = in[0]; }
+};
+
+// pencil pc: base = (pc % A)*sa + (pc / A)*sb, elements at base + i*st
+template <int N>
+__device__ __noinline__ void axis_pass_n(cplx* W, int npencil, int A, int sa, int sb, int st, int tid, int nthreads) {
+    for (int pc = tid; pc < npencil; pc += nthreads) {
+        const int base = (pc % A) * sa + (pc / A) * sb;
+        cplx in[N], out[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) in[i] = W[base + i * st];
+        PencilDft<N>::run(in, out);
+#pragma unroll
+        for (int i = 0; i < N; i++) W[base + i * st] = out[i];
+    }
+}
+
+#define DP_AXIS_CASE(n) case n: axis_pass_n<n>(W, npencil, A, sa, sb, st, tid, nthreads); break;
+__device__ __forceinline__ void axis_pass(int n, cplx* W, int npencil, int A, int sa, int sb, int st, int tid,
+                                          int nthreads) {
+    switch (n) {
+        DP_AXIS_CASE(2) DP_AXIS_CASE(3) DP_AXIS_CASE(4) DP_AXIS_CASE(5) DP_AXIS_CASE(6) DP_AXIS_CASE(7)
+        DP_AXIS_CASE(8) DP_AXIS_CASE(9) DP_AXIS_CASE(10) DP_AXIS_CASE(11) DP_AXIS_CASE(12) DP_AXIS_CASE(13)
+        DP_AXIS_CASE(14) DP_AXIS_CASE(15) DP_AXIS_CASE(16) DP_AXIS_CASE(17) DP_AXIS_CASE(18) DP_AXIS_CASE(19)
+        DP_AXIS_CASE(20) DP_AXIS_CASE(21) DP_AXIS_CASE(22) DP_AXIS_CASE(23) DP_AXIS_CASE(24) DP_AXIS_CASE(25)
+        DP_AXIS_CASE(26) DP_AXIS_CASE(27) DP_AXIS_CASE(28) DP_AXIS_CASE(29) DP_AXIS_CASE(30) DP_AXIS_CASE(31)
+        DP_AXIS_CASE(32)
+        default: break;                      // n == 1: nothing to do
+    }
+}
+#undef DP_AXIS_CASE
+
+// ---------------- kernel ------------------------------------------------------------------------
+struct PfJob { int pA, kA, pB, kB, term0, nterms; };      // pB < 0: single sequence
+struct PfTerm { int uA, uB; };                              // uB < 0: none
+
+struct PfParams {
+    const double* v;
+    int Nx, Ny, Nz, Px, Nc, N, n_unit, n_prim, Q, njobs;
+    int64_t T;
+    const PfJob* jobs;
+    const PfTerm* terms;
+    const int2* qoff;        // (offset of bin m(q), offset of bin -m(q)) in the padded layout
+    const cplx* tw;          // [Q][n_unit]
+    cplx* out;               // [T][Q][n_prim][3]
+};
+
+__global__ void __launch_bounds__(256)
+qoffset_kernel(const int* __restrict__ qbin, int Q, int Nx, int Ny, int Nz, int Px, int2* __restrict__ qoff,
+               int* __restrict__ bad) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x) {
+        int mx = qbin[q * 3], my = qbin[q * 3 + 1], mz = qbin[q * 3 + 2];
+        if (mx < 0 || mx >= Nx || my < 0 || my >= Ny || mz < 0 || mz >= Nz) { atomicAdd(bad, 1); mx = my = mz = 0; }
+        int nx = (Nx - mx) % Nx, ny = (Ny - my) % Ny, nz = (Nz - mz) % Nz;
+        qoff[q] = make_int2((mz * Ny + my) * Px + mx, (nz * Ny + ny) * Px + nx);
+    }
+}
+
+__global__ void __launch_bounds__(512)
+project_fft_kernel(PfParams p) {
+    DP_DYNSMEM(cplx, W);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz, Px = p.Px, Nc = p.Nc;
+    const int64_t nunits = p.T * p.njobs;
+    for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int64_t t = unit / p.njobs;
+        const PfJob job = p.jobs[(int)(unit % p.njobs)];
+        const double* vt = p.v + t * (int64_t)p.N * 3;
+        cplx* outA = p.out + ((t * p.Q) * p.n_prim + job.pA) * 3 + job.kA;
+        cplx* outB = job.pB >= 0 ? p.out + ((t * p.Q) * p.n_prim + job.pB) * 3 + job.kB : nullptr;
+        const int64_t qstride = (int64_t)p.n_prim * 3;
+        for (int term = 0; term < job.nterms; term++) {
+            const PfTerm tm = p.terms[job.term0 + term];
+            const double* srcA = tm.uA >= 0 ? vt + (int64_t)tm.uA * Nc * 3 + job.kA : nullptr;
+            const double* srcB = (tm.uB >= 0 && job.pB >= 0) ? vt + (int64_t)tm.uB * Nc * 3 + job.kB : nullptr;
+            __syncthreads();
+            for (int c = tid; c < Nc; c += nthreads) {
+                const int x = c % Nx, yz = c / Nx;
+                double a = srcA ? __ldg(srcA + (int64_t)c * 3) : 0.0;
+                double b = srcB ? __ldg(srcB + (int64_t)c * 3) : 0.0;
+                W[yz * Px + x] = make_double2(a, b);
+            }
+            __syncthreads();
+            axis_pass(Nx, W, Ny * Nz, Ny * Nz, Px, 0, 1, tid, nthreads);
+            __syncthreads();
+            axis_pass(Ny, W, Nx * Nz, Nx, 1, Ny * Px, Px, tid, nthreads);
+            __syncthreads();
+            axis_pass(Nz, W, Nx * Ny, Nx, 1, Px, Ny * Px, tid, nthreads);
+            __syncthreads();
+            const cplx* twA = tm.uA >= 0 ? p.tw + tm.uA : nullptr;
+            const cplx* twB = srcB ? p.tw + tm.uB : nullptr;
+            for (int q = tid; q < p.Q; q += nthreads) {
+                const int2 o = __ldg(p.qoff + q);
+                const cplx C = W[o.x], D = W[o.y];
+                // A = (C + conj D)/2,  B = (C - conj D)/(2i)
+                if (twA) {
+                    cplx a = make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y));
+                    cplx r = cmul(a, __ldg(twA + (int64_t)q * p.n_unit));
+                    cplx* dst = outA + q * qstride;
+                    if (term) { cplx old = *dst; r = cadd(old, r); }
+                    *dst = r;
+                }
+                if (twB) {
+                    cplx b = make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x));
+                    cplx r = cmul(b, __ldg(twB + (int64_t)q * p.n_unit));
+                    cplx* dst = outB + q * qstride;
+                    if (term) { cplx old = *dst; r = cadd(old, r); }
+                    *dst = r;
+                }
+            }
+        }
+    }
+}
+
+struct PfLayout {
+    size_t off_jobs, off_terms, off_qoff, off_bad, total;
+};
+
+static PfLayout pf_layout(int n_unit, int n_prim, int Q) {
+    PfLayout l;
+    size_t o = 0;
+    l.off_jobs = o;  o += align_up((size_t)(2 * n_prim + 2) * sizeof(PfJob), 256);
+    l.off_terms = o; o += align_up((size_t)(3 * n_unit + 4) * sizeof(PfTerm), 256);
+    l.off_qoff = o;  o += align_up((size_t)Q * sizeof(int2), 256);
+    l.off_bad = o;   o += 256;
+    l.total = o;
+    return l;
+}
+
+static int pick_threads(int Nx, int Ny, int Nz, int Q) {
+    int best = 128;
+    long long best_cost = -1;
+    for (int th = 128; th <= 512; th += 32) {
+        auto rounds = [&](int n) { return (long long)((n + th - 1) / th); };
+        long long cost = (rounds(Ny * Nz) + rounds(Nx * Nz) + rounds(Nx * Ny)) * th * 8 + rounds(Nx * Ny * Nz) * th +
+                         rounds(Q) * th * 2;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = th; }
+    }
+    return best;
+}
+
+}  // namespace dp
+
+extern "C" {
+
+size_t dp_project_commensurate_workspace_bytes(const int* dims, int n_unit, int n_prim, int Q) {
+    if (!dims || n_unit <= 0 || n_prim <= 0 || Q <= 0) return 0;
+    return dp::pf_layout(n_unit, n_prim, Q).total;
+}
+
+int dp_project_commensurate(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
+                            int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
+                            double* out_vc, void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(v && dims && unit_type && qbin && twiddle && out_vc && workspace, DP_ERR_INVALID,
+               "dp_project_commensurate: null pointer");
+    DP_REQUIRE(n_unit > 0 && n_prim > 0 && T >= 0 && Q > 0 && project_on_atom < n_prim, DP_ERR_INVALID,
+               "dp_project_commensurate: bad sizes");
+    const int Nx = dims[0], Ny = dims[1], Nz = dims[2];
+    DP_REQUIRE(Nx >= 1 && Ny >= 1 && Nz >= 1, DP_ERR_INVALID, "dp_project_commensurate: bad dims");
+    DP_REQUIRE(Nx <= DP_ROOTS_NMAX && Ny <= DP_ROOTS_NMAX && Nz <= DP_ROOTS_NMAX, DP_ERR_UNSUPPORTED,
+               "dp_project_commensurate: supercell multiplicity > %d (use dp_project_wave_vector)", DP_ROOTS_NMAX);
+    const int Px = (Nx % 2 == 0) ? Nx + 1 : Nx;
+    const int64_t Nc64 = (int64_t)Nx * Ny * Nz;
+    const size_t smem = (size_t)Nz * Ny * Px * sizeof(dp::cplx);
+    DP_REQUIRE(smem <= 220 * 1024, DP_ERR_UNSUPPORTED,
+               "dp_project_commensurate: %lld cells need %zu B of shared memory (use dp_project_wave_vector)",
+               (long long)Nc64, smem);
+    dp::PfLayout lay = dp::pf_layout(n_unit, n_prim, Q);
+    DP_REQUIRE(workspace_bytes >= lay.total, DP_ERR_WORKSPACE, "dp_project_commensurate: workspace too small");
+    if (T == 0) return DP_OK;
+    const int Nc = (int)Nc64;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // jobs: (p,x)+(p,y) per type; z components of two types share a transform
+    std::vector<std::vector<int>> units(n_prim);
+    for (int u = 0; u < n_unit; u++) {
+        DP_REQUIRE(unit_type[u] >= 0 && unit_type[u] < n_prim, DP_ERR_INVALID, "dp_project_commensurate: unit_type[%d]=%d", u, unit_type[u]);
+        units[unit_type[u]].push_back(u);
+    }
+    std::vector<dp::PfJob> jobs;
+    std::vector<dp::PfTerm> terms;
+    std::vector<int> types;
+    for (int p = 0; p < n_prim; p++)
+        if (project_on_atom < 0 || project_on_atom == p) types.push_back(p);
+    auto add_job = [&](int pA, int kA, int pB, int kB) {
+        dp::PfJob j{pA, kA, pB, kB, (int)terms.size(), 0};
+        size_t na = units[pA].size(), nb = pB >= 0 ? units[pB].size() : 0;
+        size_t n = std::max(na, nb);
+        for (size_t i = 0; i < n; i++) terms.push_back(dp::PfTerm{i < na ? units[pA][i] : -1, i < nb ? units[pB][i] : -1});
+        j.nterms = (int)n;
+        if (n) jobs.push_back(j);
+    };
+    for (int p : types) add_job(p, 0, p, 1);
+    for (size_t i = 0; i < types.size(); i += 2) add_job(types[i], 2, i + 1 < types.size() ? types[i + 1] : -1, 2);
+    // a slot whose type has fewer unit atoms than its partner still needs its first term to STORE:
+    // terms are ordered so that index 0 always carries both sequences when both exist.
+    bool need_zero = project_on_atom >= 0;
+    for (int p : types) if (units[p].empty()) need_zero = true;
+    for (const auto& j : jobs)
+        if (j.pB >= 0 && units[j.pA].size() != units[j.pB].size()) need_zero = true;
+    if (need_zero) DP_CUDA_OK(cudaMemsetAsync(out_vc, 0, (size_t)T * Q * n_prim * 3 * sizeof(dp::cplx), st));
+    if (jobs.empty()) return DP_OK;
+
+    char* ws = (char*)workspace;
+    dp::PfJob* d_jobs = (dp::PfJob*)(ws + lay.off_jobs);
+    dp::PfTerm* d_terms = (dp::PfTerm*)(ws + lay.off_terms);
+    int2* d_qoff = (int2*)(ws + lay.off_qoff);
+    int* d_bad = (int*)(ws + lay.off_bad);
+    DP_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(dp::PfJob), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(d_terms, terms.data(), terms.size() * sizeof(dp::PfTerm), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    {
+        auto k = dp::qoffset_kernel;
+        DP_LAUNCH(k, dim3((unsigned)dp::imin((Q + 255) / 256, 1024)), dim3(256), 0, st, qbin, Q, Nx, Ny, Nz, Px, d_qoff, d_bad);
+        DP_CUDA_OK(cudaGetLastError());
+    }
+    int bad = 0;
+    DP_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DP_CUDA_OK(cudaStreamSynchronize(st));      // also keeps the host job vectors alive long enough
+    DP_REQUIRE(bad == 0, DP_ERR_INVALID, "dp_project_commensurate: %d q bins outside the supercell grid", bad);
+
+    dp::PfParams p;
+    p.v = v; p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Px = Px; p.Nc = Nc; p.N = n_unit * Nc;
+    p.n_unit = n_unit; p.n_prim = n_prim; p.Q = Q; p.njobs = (int)jobs.size(); p.T = T;
+    p.jobs = d_jobs; p.terms = d_terms; p.qoff = d_qoff; p.tw = (const dp::cplx*)twiddle; p.out = (dp::cplx*)out_vc;
+    const int threads = dp::pick_threads(Nx, Ny, Nz, Q);
+    auto k = dp::project_fft_kernel;
+    DP_CUDA_OK(DP_SET_SMEM(k, smem));
+    int per_sm = (int)dp::imin<size_t>(4, dp::imax<size_t>(1, (size_t)(224 * 1024) / (smem + 1024)));
+    int64_t nunits = T * (int64_t)jobs.size();
+    int grid = (int)dp::imin<int64_t>(nunits, (int64_t)dp::imax(dp::sm_count(), 1) * per_sm);
+    DP_LAUNCH(k, dim3(grid), dim3(threads), smem, st, p);
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+}  // extern "C"

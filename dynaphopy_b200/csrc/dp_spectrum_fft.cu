@@ -1,0 +1,430 @@
+// A7: FFT power spectrum (selector keys 2/3) -- reference
+// dynaphopy/power_spectrum/__init__.py:226-270 (_numpy_power, get_fft_numpy_spectra) and :33-51
+// (_division_of_data).
+//
+// Per window ("piece") of length L and per series the reference evaluates
+//     a = np.correlate(x, x, 'same') / L          O(L^2)
+//     S = |FFT_L(a)| * dt ; mean over windows ; np.interp onto the requested grid.
+// Here one persistent CTA owns one (series, window) item and runs, with the hand-written
+// engine of dp_fft.cuh,
+//     X = FFT_P(x zero-padded to P >= L + L//2) ; |X|^2 ; IFFT_P      (linear autocorrelation)
+//     gather lags [-L//2, L - L//2) ; FFT_L ; |.| * dt
+// through a private scratch slab (P + L complex) that stays L2-resident; |X|^2 and the inverse
+// row transforms are fused in shared memory.  A second kernel averages the windows in the
+// reference's order and applies np.interp's exact arithmetic.
+#include <cmath>
+#include <algorithm>
+#include <vector>
+
+#include "dp_common.cuh"
+#include "dp_fft.cuh"
+
+namespace dp {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------- host planning ---------------------------------------------------------------
+struct SpecHostPlan {
+    int L = 0, P = 0, half = 0;
+    std::vector<int> starts;          // distinct windows actually transformed
+    int n_avg = 0;                    // number of windows the reference averages (npieces + 1)
+    bool duplicate_single = false;    // reference list is [[0,T],[0,T]]
+    FftSplit sp, sl;
+    int lo = 0, nkeep = 0;
+    std::vector<int> idx0, mode;      // np.interp bracket (sorted-frequency index), 1 = copy fp[idx0]
+    std::vector<double> dx, den;
+};
+
+// _division_of_data (power_spectrum/__init__.py:33-51), same floating-point expressions.
+static int plan_pieces(int64_t T, double dt, double resolution, int* piece_len, std::vector<int>* starts,
+                       bool* duplicate_single) {
+    double inv = 1.0 / (dt * resolution);
+    if (!(inv > 0.0) || !std::isfinite(inv) || inv > 2.0e9) {
+        set_error("power_fft: bad resolution %g / time step %g", resolution, dt);
+        return DP_ERR_INVALID;
+    }
+    long long piece = (long long)std::nearbyint(inv);      // Python round(): half to even
+    if (piece < 1) { set_error("power_fft: window length rounds to 0"); return DP_ERR_INVALID; }
+    long long npieces = (long long)((double)(T - 1) / (double)piece);
+    double interval;
+    *duplicate_single = false;
+    if (npieces > 0) {
+        interval = (double)(T - piece) / (double)npieces;
+    } else {
+        interval = 0.0;
+        npieces = 1;
+        piece = T;
+        *duplicate_single = true;
+    }
+    starts->clear();
+    for (long long i = 0; i <= npieces; i++) {
+        double mid = (double)piece / 2.0 + (double)i * interval;
+        long long ini = (long long)(mid - (double)piece / 2.0);
+        long long fin = (long long)(mid + (double)piece / 2.0);
+        if (fin - ini != piece || ini < 0 || fin > T) {
+            set_error("power_fft: ragged window [%lld,%lld) for length %lld (the reference fails here too)",
+                      ini, fin, piece);
+            return DP_ERR_UNSUPPORTED;
+        }
+        starts->push_back((int)ini);
+    }
+    *piece_len = (int)piece;
+    return DP_OK;
+}
+
+static int make_spec_plan(int64_t T, double dt, const double* freq, int F, SpecHostPlan* pl) {
+    if (T < 2 || F < 2 || !(dt > 0)) { set_error("power_fft: need T >= 2, F >= 2, dt > 0"); return DP_ERR_INVALID; }
+    if (T > (1 << 22)) { set_error("power_fft: T=%lld exceeds the supported 2^22", (long long)T); return DP_ERR_UNSUPPORTED; }
+    int rc = plan_pieces(T, dt, freq[1] - freq[0], &pl->L, &pl->starts, &pl->duplicate_single);
+    if (rc) return rc;
+    pl->n_avg = (int)pl->starts.size();
+    if (pl->duplicate_single) pl->starts.resize(1);     // (a + a) / 2 == a exactly
+    const int L = pl->L;
+    pl->half = L / 2;
+    if (!make_fft_split(L, &pl->sl)) {
+        set_error("power_fft: window length %d has a prime factor > %d or no usable split", L, FFT_MAX_RADIX);
+        return DP_ERR_UNSUPPORTED;
+    }
+    pl->P = next_fast_length(L + L / 2);
+    if (!make_fft_split(pl->P, &pl->sp)) { set_error("power_fft: internal: no split for P=%d", pl->P); return DP_ERR_UNSUPPORTED; }
+    // np.interp plan on the sorted fftfreq axis xp[i] = (i - half) * val, val = 1/(L*dt)
+    const double val = 1.0 / ((double)L * dt);
+    auto xp = [&](long long i) { return (double)(i - pl->half) * val; };
+    pl->idx0.resize(F); pl->mode.resize(F); pl->dx.resize(F); pl->den.resize(F);
+    long long lo = L, hi = -1;
+    for (int f = 0; f < F; f++) {
+        double x = freq[f];
+        long long j;
+        if (std::isnan(x)) { set_error("power_fft: NaN in frequency grid"); return DP_ERR_INVALID; }
+        if (x < xp(0)) j = -1;
+        else if (x >= xp(L - 1)) j = L - 1;
+        else {
+            double g = std::floor(x / val) + (double)pl->half;
+            j = (long long)g;
+            if (j < 0) j = 0;
+            if (j > L - 2) j = L - 2;
+            while (j > 0 && xp(j) > x) j--;
+            while (j < L - 2 && xp(j + 1) <= x) j++;
+        }
+        int mode = 0; long long i0 = j;
+        if (j == -1) { i0 = 0; mode = 1; }
+        else if (j >= L - 1) { i0 = L - 1; mode = 1; }
+        else if (xp(j) == x) mode = 1;
+        pl->idx0[f] = (int)i0; pl->mode[f] = mode;
+        pl->dx[f] = mode ? 0.0 : x - xp(j);
+        pl->den[f] = mode ? 1.0 : xp(j + 1) - xp(j);
+        lo = std::min(lo, i0);
+        hi = std::max(hi, mode ? i0 : i0 + 1);
+    }
+    pl->lo = (int)lo;
+    pl->nkeep = (int)(hi - lo + 1);
+    return DP_OK;
+}
+
+// ---------------- device side -------------------------------------------------------------------
+struct SpecParams {
+    const cplx* series; int64_t ld; int S;
+    int L, P, half, npieces;
+    const int* starts;
+    FftSplit sp, sl;
+    const cplx *twP1, *twP2, *twPN, *twL1, *twL2, *twLN;
+    cplx* scratch;            // gridDim.x slabs of (P + L)
+    double* spec;             // [S][npieces][nkeep]
+    int lo, nkeep;
+    double dt, acf_scale;     // acf_scale = 1 / (P * L)
+};
+
+// |X|^2 then inverse transform of the same rows, all in shared memory
+struct MidPowerInverse {
+    const FftPlan* plan;
+    const cplx* tw;
+    int n2;
+    __device__ __forceinline__ cplx* operator()(cplx* r, cplx* other, int nr, int tid, int nthreads) const {
+        for (int e = tid; e < n2 * nr; e += nthreads) {
+            cplx v = r[e];
+            r[e] = make_double2(v.x * v.x + v.y * v.y, 0.0);
+        }
+        __syncthreads();
+        return stockham<+1>(r, other, *plan, nr, tw, tid, nthreads);
+    }
+};
+
+__global__ void __launch_bounds__(FFT_THREADS)
+spectrum_items_kernel(SpecParams p) {
+    DP_DYNSMEM(cplx, smem);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    cplx* A = p.scratch + (size_t)blockIdx.x * ((size_t)p.P + p.L);
+    cplx* B = A + p.P;
+    const int64_t nitems = (int64_t)p.S * p.npieces;
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int pc = (int)(item / p.S), s = (int)(item % p.S);
+        const cplx* x0 = p.series + (int64_t)p.starts[pc] * p.ld + s;
+        const int64_t ld = p.ld;
+        const int L = p.L, P = p.P, half = p.half;
+        auto load_x = [=](int idx) -> cplx {
+            return idx < L ? __ldg(x0 + (int64_t)idx * ld) : make_double2(0.0, 0.0);
+        };
+        MidPowerInverse mid{&p.sp.p2, p.twP2, p.sp.n2};
+        // ---- linear autocorrelation through FFT_P ----
+        if (p.sp.n1 > 1) {
+            const int n2 = p.sp.n2;
+            fft_column_pass<-1, false>(p.sp, p.twP1, p.twPN, smem, load_x,
+                                       [=](int k1, int c, cplx v) { A[(size_t)k1 * n2 + c] = v; }, tid, nthreads);
+            __syncthreads();
+            fft_row_pass<-1>(p.sp, p.twP2, smem, [=](int row, int j2) { return A[(size_t)row * n2 + j2]; },
+                             [=](int row, int k2, cplx v) { A[(size_t)row * n2 + k2] = v; }, mid, tid, nthreads);
+            __syncthreads();
+            fft_column_pass<+1, true>(p.sp, p.twP1, p.twPN, smem, [=](int idx) { return A[idx]; },
+                                      [=](int j1, int c, cplx v) { A[(size_t)j1 * n2 + c] = v; }, tid, nthreads);
+        } else {
+            fft_row_pass<-1>(p.sp, p.twP2, smem, [=](int, int j2) { return load_x(j2); },
+                             [=](int, int k2, cplx v) { A[k2] = v; }, mid, tid, nthreads);
+        }
+        __syncthreads();
+        // ---- FFT_L of the gathered lags, |.| * dt into the kept sorted-frequency range ----
+        const double sc = p.acf_scale;
+        auto load_acf = [=](int m) -> cplx {
+            int k = m - half;
+            if (k < 0) k += P;
+            cplx v = A[k];
+            return make_double2(v.x * sc, v.y * sc);
+        };
+        double* spec = p.spec + ((size_t)s * p.npieces + pc) * p.nkeep;
+        const int n1L = p.sl.n1, lo = p.lo, nkeep = p.nkeep;
+        const double dt = p.dt;
+        auto store_bin = [=](int k1, int k2, cplx v) {
+            int bin = k1 + n1L * k2;
+            int i = bin + half;
+            if (i >= L) i -= L;
+            i -= lo;
+            if (i >= 0 && i < nkeep) spec[i] = __dmul_rn(hypot(v.x, v.y), dt);
+        };
+        if (p.sl.n1 > 1) {
+            const int n2 = p.sl.n2;
+            fft_column_pass<-1, false>(p.sl, p.twL1, p.twLN, smem, load_acf,
+                                       [=](int k1, int c, cplx v) { B[(size_t)k1 * n2 + c] = v; }, tid, nthreads);
+            __syncthreads();
+            fft_row_pass<-1>(p.sl, p.twL2, smem, [=](int row, int j2) { return B[(size_t)row * n2 + j2]; },
+                             store_bin, MidIdentity(), tid, nthreads);
+        } else {
+            fft_row_pass<-1>(p.sl, p.twL2, smem, [=](int, int j2) { return load_acf(j2); }, store_bin,
+                             MidIdentity(), tid, nthreads);
+        }
+        __syncthreads();
+    }
+}
+
+// mean over windows (sequential, np.add.reduce order) + np.interp arithmetic + unit scale
+__global__ void __launch_bounds__(256)
+spectrum_finalize_kernel(const double* __restrict__ spec, int S, int npieces, int n_avg, int nkeep, int lo,
+                         const int* __restrict__ idx0, const int* __restrict__ mode,
+                         const double* __restrict__ dx, const double* __restrict__ den, int F, double scale,
+                         double* __restrict__ out) {
+    int64_t total = (int64_t)F * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        int f = (int)(e / S), s = (int)(e % S);
+        const double* base = spec + (size_t)s * npieces * nkeep;
+        int i = idx0[f] - lo;
+        auto mean_at = [&](int ii) {
+            double acc = base[ii];
+            if (n_avg != npieces) {                 // duplicated single window: (a + a) / 2
+                acc = __dadd_rn(acc, acc);
+            } else {
+                for (int pc = 1; pc < npieces; pc++) acc = __dadd_rn(acc, base[(size_t)pc * nkeep + ii]);
+            }
+            return __ddiv_rn(acc, (double)n_avg);
+        };
+        double f0 = mean_at(i), res;
+        if (mode[f]) res = f0;
+        else {
+            double f1 = mean_at(i + 1);
+            double slope = __ddiv_rn(__dsub_rn(f1, f0), den[f]);
+            res = __dadd_rn(__dmul_rn(slope, dx[f]), f0);
+        }
+        out[e] = __dmul_rn(res, scale);
+    }
+}
+
+struct SpecLayout {
+    size_t off_tw[6], off_starts, off_idx0, off_mode, off_dx, off_den, off_spec, off_scratch, total;
+    int nslots;
+};
+
+static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
+    SpecLayout l;
+    size_t o = 0;
+    int lens[6] = {pl.sp.n1, pl.sp.n2, pl.P, pl.sl.n1, pl.sl.n2, pl.L};
+    for (int i = 0; i < 6; i++) { l.off_tw[i] = o; o += align_up((size_t)lens[i] * sizeof(cplx), 256); }
+    l.off_starts = o; o += align_up(pl.starts.size() * sizeof(int), 256);
+    l.off_idx0 = o;   o += align_up((size_t)F * sizeof(int), 256);
+    l.off_mode = o;   o += align_up((size_t)F * sizeof(int), 256);
+    l.off_dx = o;     o += align_up((size_t)F * sizeof(double), 256);
+    l.off_den = o;    o += align_up((size_t)F * sizeof(double), 256);
+    l.off_spec = o;   o += align_up((size_t)S * pl.starts.size() * pl.nkeep * sizeof(double), 256);
+    int64_t items = (int64_t)S * (int64_t)pl.starts.size();
+    l.nslots = (int)imin<int64_t>(items, (int64_t)imax(sm_count(), 1));
+    l.off_scratch = o; o += align_up((size_t)l.nslots * ((size_t)pl.P + pl.L) * sizeof(cplx), 256);
+    l.total = o;
+    return l;
+}
+
+static int launch_twiddles(cplx* tw, int n, cudaStream_t st) {
+    auto k = twiddle_table_kernel;
+    DP_LAUNCH(k, dim3((unsigned)imin((n + 255) / 256, 1024)), dim3(256), 0, st, tw, n);
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+}  // namespace dp
+
+extern "C" {
+
+size_t dp_power_fft_workspace_bytes(int64_t T, int S, double dt, const double* freq, int F) {
+    dp::SpecHostPlan pl;
+    if (!freq || S <= 0 || dp::make_spec_plan(T, dt, freq, F, &pl) != DP_OK) return 0;
+    return dp::spec_layout(pl, S, F).total;
+}
+
+int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* piece_len, int* n_pieces,
+                        int* starts, int max_pieces) {
+    DP_REQUIRE(freq && piece_len && n_pieces, DP_ERR_INVALID, "dp_power_fft_pieces: null pointer");
+    DP_REQUIRE(F >= 2, DP_ERR_INVALID, "dp_power_fft_pieces: need F >= 2");
+    std::vector<int> st;
+    bool dup;
+    int rc = dp::plan_pieces(T, dt, freq[1] - freq[0], piece_len, &st, &dup);
+    if (rc) return rc;
+    *n_pieces = (int)st.size();
+    for (int i = 0; i < (int)st.size() && i < max_pieces && starts; i++) starts[i] = st[i];
+    return DP_OK;
+}
+
+int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq, int F,
+                 double scale, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(series && freq && out && workspace, DP_ERR_INVALID, "dp_power_fft: null pointer");
+    DP_REQUIRE(S > 0 && ld >= S, DP_ERR_INVALID, "dp_power_fft: bad S=%d ld=%lld", S, (long long)ld);
+    dp::SpecHostPlan pl;
+    int rc = dp::make_spec_plan(T, dt, freq, F, &pl);
+    if (rc) return rc;
+    dp::SpecLayout lay = dp::spec_layout(pl, S, F);
+    DP_REQUIRE(workspace_bytes >= lay.total, DP_ERR_WORKSPACE, "dp_power_fft: workspace %zu < %zu", workspace_bytes, lay.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    dp::cplx* tw[6];
+    int lens[6] = {pl.sp.n1, pl.sp.n2, pl.P, pl.sl.n1, pl.sl.n2, pl.L};
+    for (int i = 0; i < 6; i++) {
+        tw[i] = (dp::cplx*)(ws + lay.off_tw[i]);
+        rc = dp::launch_twiddles(tw[i], lens[i], st);
+        if (rc) return rc;
+    }
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_starts, pl.starts.data(), pl.starts.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_idx0, pl.idx0.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_mode, pl.mode.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_dx, pl.dx.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_den, pl.den.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+#ifndef DP_EMUL
+    DP_CUDA_OK(cudaStreamSynchronize(st));   // plan vectors are host temporaries
+#endif
+    dp::SpecParams p;
+    p.series = (const dp::cplx*)series; p.ld = ld; p.S = S;
+    p.L = pl.L; p.P = pl.P; p.half = pl.half; p.npieces = (int)pl.starts.size();
+    p.starts = (const int*)(ws + lay.off_starts);
+    p.sp = pl.sp; p.sl = pl.sl;
+    p.twP1 = tw[0]; p.twP2 = tw[1]; p.twPN = tw[2]; p.twL1 = tw[3]; p.twL2 = tw[4]; p.twLN = tw[5];
+    p.scratch = (dp::cplx*)(ws + lay.off_scratch);
+    p.spec = (double*)(ws + lay.off_spec);
+    p.lo = pl.lo; p.nkeep = pl.nkeep;
+    p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
+    size_t smem = std::max(dp::fft_split_smem_elems(pl.sp), dp::fft_split_smem_elems(pl.sl)) * sizeof(dp::cplx);
+    auto k = dp::spectrum_items_kernel;
+    DP_CUDA_OK(DP_SET_SMEM(k, smem));
+    DP_LAUNCH(k, dim3(lay.nslots), dim3(dp::FFT_THREADS), smem, st, p);
+    DP_CUDA_OK(cudaGetLastError());
+    auto kf = dp::spectrum_finalize_kernel;
+    int64_t total = (int64_t)F * S;
+    DP_LAUNCH(kf, dim3((unsigned)dp::imin<int64_t>((total + 255) / 256, 4096)), dim3(256), 0, st,
+              (const double*)p.spec, S, p.npieces, pl.n_avg, pl.nkeep, pl.lo, (const int*)(ws + lay.off_idx0),
+              (const int*)(ws + lay.off_mode), (const double*)(ws + lay.off_dx), (const double*)(ws + lay.off_den), F,
+              scale, out);
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+}  // extern "C"
+
+// ---- plain batched transform through the same engine (validation / benchmarking) ---------------
+namespace dp {
+struct C2cParams {
+    const cplx* in; cplx* out; cplx* scratch;
+    FftSplit sp; const cplx *tw1, *tw2, *twN; int batch;
+};
+
+template <int DIR>
+__global__ void __launch_bounds__(FFT_THREADS) c2c_kernel(C2cParams p) {
+    DP_DYNSMEM(cplx, smem);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int N = p.sp.N, n1 = p.sp.n1, n2 = p.sp.n2;
+    for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+        const cplx* x = p.in + (size_t)b * N;
+        cplx* y = p.out + (size_t)b * N;
+        cplx* A = p.scratch + (size_t)blockIdx.x * N;
+        if (n1 > 1) {
+            fft_column_pass<DIR, false>(p.sp, p.tw1, p.twN, smem, [=](int idx) { return x[idx]; },
+                                        [=](int k1, int c, cplx v) { A[(size_t)k1 * n2 + c] = v; }, tid, nthreads);
+            __syncthreads();
+            fft_row_pass<DIR>(p.sp, p.tw2, smem, [=](int row, int j2) { return A[(size_t)row * n2 + j2]; },
+                              [=](int k1, int k2, cplx v) { y[k1 + (size_t)n1 * k2] = v; }, MidIdentity(), tid, nthreads);
+        } else {
+            fft_row_pass<DIR>(p.sp, p.tw2, smem, [=](int, int j2) { return x[j2]; },
+                              [=](int, int k2, cplx v) { y[k2] = v; }, MidIdentity(), tid, nthreads);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace dp
+
+extern "C" {
+
+size_t dp_fft_c2c_workspace_bytes(int n, int batch) {
+    dp::FftSplit sp;
+    if (n < 1 || batch < 1 || !dp::make_fft_split(n, &sp)) return 0;
+    size_t tw = dp::align_up((size_t)sp.n1 * 16, 256) + dp::align_up((size_t)sp.n2 * 16, 256) + dp::align_up((size_t)n * 16, 256);
+    int slots = dp::imin(batch, dp::imax(dp::sm_count(), 1));
+    return tw + dp::align_up((size_t)slots * n * 16, 256);
+}
+
+int dp_fft_c2c(const double* in, double* out, int n, int batch, int direction, void* workspace,
+               size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(in && out && workspace && in != out, DP_ERR_INVALID, "dp_fft_c2c: null or aliased pointer");
+    DP_REQUIRE(n >= 1 && batch >= 1 && (direction == 1 || direction == -1), DP_ERR_INVALID, "dp_fft_c2c: bad arguments");
+    dp::FftSplit sp;
+    DP_REQUIRE(dp::make_fft_split(n, &sp), DP_ERR_UNSUPPORTED, "dp_fft_c2c: length %d unsupported (prime factor > %d?)", n, dp::FFT_MAX_RADIX);
+    DP_REQUIRE(workspace_bytes >= dp_fft_c2c_workspace_bytes(n, batch), DP_ERR_WORKSPACE, "dp_fft_c2c: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    dp::C2cParams p;
+    p.in = (const dp::cplx*)in; p.out = (dp::cplx*)out; p.sp = sp; p.batch = batch;
+    dp::cplx* t1 = (dp::cplx*)ws; ws += dp::align_up((size_t)sp.n1 * 16, 256);
+    dp::cplx* t2 = (dp::cplx*)ws; ws += dp::align_up((size_t)sp.n2 * 16, 256);
+    dp::cplx* tN = (dp::cplx*)ws; ws += dp::align_up((size_t)n * 16, 256);
+    p.tw1 = t1; p.tw2 = t2; p.twN = tN; p.scratch = (dp::cplx*)ws;
+    int rc;
+    if ((rc = dp::launch_twiddles(t1, sp.n1, st))) return rc;
+    if ((rc = dp::launch_twiddles(t2, sp.n2, st))) return rc;
+    if ((rc = dp::launch_twiddles(tN, n, st))) return rc;
+    size_t smem = dp::fft_split_smem_elems(sp) * sizeof(dp::cplx);
+    int slots = dp::imin(batch, dp::imax(dp::sm_count(), 1));
+    if (direction < 0) {
+        auto k = dp::c2c_kernel<-1>;
+        DP_CUDA_OK(DP_SET_SMEM(k, smem));
+        DP_LAUNCH(k, dim3(slots), dim3(dp::FFT_THREADS), smem, st, p);
+    } else {
+        auto k = dp::c2c_kernel<+1>;
+        DP_CUDA_OK(DP_SET_SMEM(k, smem));
+        DP_LAUNCH(k, dim3(slots), dim3(dp::FFT_THREADS), smem, st, p);
+    }
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+}  // extern "C"

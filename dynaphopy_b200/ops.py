@@ -1,0 +1,234 @@
+"""Array-level operators over the C ABI (one method per entry point of include/dynaphopy_b200.h).
+
+``Ops`` is written against a tiny memory back-end so that the SAME marshalling code can be
+driven by the test-suite's host emulator (tests/emul.py supplies a numpy back-end together with
+the emulator build of the kernels).  The package itself only ever instantiates the CUDA
+back-end (``TorchCudaBackend``): device memory, streams and the current device come from
+PyTorch, the arithmetic from libdynaphopy_b200.so.  No CPU fallback exists here.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+UNIT_CONVERSION = 0.00010585723   # u * A^2 * THz -> eV*ps (dynaphopy/power_spectrum/__init__.py:9)
+
+
+class TorchCudaBackend:
+    """Device memory and streams from PyTorch (plumbing only)."""
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("dynaphopy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+
+    def _dtype(self, dtype):
+        t = self.torch
+        return {np.float64: t.float64, np.complex128: t.complex128, np.int32: t.int32, np.uint8: t.uint8}[dtype]
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(tuple(int(s) for s in shape), dtype=self._dtype(dtype), device=self.device)
+
+    def asarray(self, x, dtype):
+        t = self.torch
+        if isinstance(x, t.Tensor):
+            return x.to(device=self.device, dtype=self._dtype(dtype)).contiguous()
+        return t.as_tensor(np.ascontiguousarray(x, dtype=dtype), device=self.device)
+
+    def is_complex(self, x):
+        return x.is_complex() if isinstance(x, self.torch.Tensor) else np.iscomplexobj(x)
+
+    def ptr(self, x):
+        return ctypes.c_void_p(x.data_ptr()) if x is not None else None
+
+    def stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def shape(self, x):
+        return tuple(x.shape)
+
+
+def _host(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _hptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Ops:
+    def __init__(self, lib=None, backend=None):
+        self.lib = lib if lib is not None else _lib.load()
+        self.be = backend if backend is not None else TorchCudaBackend()
+
+    # ------------------------------------------------------------------ A8 / A9 / A1
+    def atomic_displacements(self, trajectory, positions, cell):
+        """(T,N,3) positions -> (T,N,3) real displacements (c/displacements.c:95-196 for all atoms)."""
+        be = self.be
+        cplx = be.is_complex(trajectory)
+        traj = be.asarray(trajectory, np.complex128 if cplx else np.float64)
+        T, N, _ = be.shape(traj)
+        pos = be.asarray(positions, np.float64)
+        cellh = _host(cell, np.float64)
+        out = be.empty((T, N, 3), np.float64)
+        self.lib.call("dp_atomic_displacements", be.ptr(traj), int(cplx), be.ptr(pos), _hptr(cellh), T, N,
+                      be.ptr(out), be.stream())
+        return out
+
+    def velocity_from_positions(self, trajectory, positions, cell, dt, sqrt_mass=None, prev_frame=None,
+                                next_frame=None, want_displacements=False):
+        """Fused displacements -> np.gradient -> sqrt(mass) (dynamics.py:158-179, 313-329, 143-156)."""
+        be = self.be
+        cplx = be.is_complex(trajectory)
+        dt_ = np.complex128 if cplx else np.float64
+        traj = be.asarray(trajectory, dt_)
+        T, N, _ = be.shape(traj)
+        pos = be.asarray(positions, np.float64)
+        cellh = _host(cell, np.float64)
+        sm = be.asarray(sqrt_mass, np.float64) if sqrt_mass is not None else None
+        pf = be.asarray(prev_frame, dt_) if prev_frame is not None else None
+        nf = be.asarray(next_frame, dt_) if next_frame is not None else None
+        out_u = be.empty((T, N, 3), np.float64) if want_displacements else None
+        out_v = be.empty((T, N, 3), np.float64)
+        self.lib.call("dp_velocity_from_positions", be.ptr(traj), int(cplx), be.ptr(pos), _hptr(cellh), be.ptr(sm),
+                      T, N, float(dt), be.ptr(pf), be.ptr(nf), be.ptr(out_u), be.ptr(out_v), be.stream())
+        return (out_u, out_v) if want_displacements else out_v
+
+    def mass_weight(self, velocity, sqrt_mass):
+        be = self.be
+        cplx = be.is_complex(velocity)
+        v = be.asarray(velocity, np.complex128 if cplx else np.float64)
+        T, N, _ = be.shape(v)
+        sm = be.asarray(sqrt_mass, np.float64)
+        out = be.empty((T, N, 3), np.complex128 if cplx else np.float64)
+        self.lib.call("dp_mass_weight", be.ptr(v), 2 if cplx else 1, be.ptr(sm), T, N, be.ptr(out), be.stream())
+        return out
+
+    # ------------------------------------------------------------------ A2 / A3
+    def project_wave_vector(self, velocity, sqrt_mass, positions, type_idx, n_prim, q_cart, project_on_atom=-1):
+        """Dense projection for a batch of Cartesian q: -> (T,Q,n_prim,3) complex128."""
+        be = self.be
+        cplx = be.is_complex(velocity)
+        v = be.asarray(velocity, np.complex128 if cplx else np.float64)
+        T, N, _ = be.shape(v)
+        q = _host(np.atleast_2d(q_cart), np.float64)
+        Q = q.shape[0]
+        typ = _host(type_idx, np.int32)
+        pos = be.asarray(positions, np.float64)
+        sm = be.asarray(sqrt_mass, np.float64) if sqrt_mass is not None else None
+        nbytes = self.lib.size("dp_project_wave_vector_workspace_bytes", N, Q)
+        ws = be.empty((nbytes,), np.uint8)
+        out = be.empty((T, Q, n_prim, 3), np.complex128)
+        self.lib.call("dp_project_wave_vector", be.ptr(v), int(cplx), be.ptr(sm), be.ptr(pos), _hptr(typ), N,
+                      int(n_prim), T, _hptr(q), Q, int(project_on_atom), be.ptr(out), be.ptr(ws), nbytes, be.stream())
+        return out
+
+    def project_commensurate(self, velocity, dims, unit_type, n_prim, qbin, twiddle, project_on_atom=-1):
+        """3-D DFT projection: real (T,N,3) -> (T,Q,n_prim,3) complex128 for commensurate q."""
+        be = self.be
+        v = be.asarray(velocity, np.float64)
+        T, N, _ = be.shape(v)
+        dims_h = _host(dims, np.int32)
+        ut = _host(unit_type, np.int32)
+        n_unit = ut.shape[0]
+        assert N == n_unit * int(np.prod(dims_h)), "atom count does not match dims * n_unit"
+        qb = be.asarray(qbin, np.int32)
+        Q = be.shape(qb)[0]
+        tw = be.asarray(twiddle, np.complex128)
+        nbytes = self.lib.size("dp_project_commensurate_workspace_bytes", _hptr(dims_h), n_unit, int(n_prim), Q)
+        ws = be.empty((nbytes,), np.uint8)
+        out = be.empty((T, Q, n_prim, 3), np.complex128)
+        self.lib.call("dp_project_commensurate", be.ptr(v), _hptr(dims_h), n_unit, _hptr(ut), int(n_prim), T,
+                      be.ptr(qb), be.ptr(tw), Q, int(project_on_atom), be.ptr(out), be.ptr(ws), nbytes, be.stream())
+        return out
+
+    def project_phonon(self, vc, eigenvectors):
+        """vc (T,Q,n_p,3) or (T,Q,M); eigenvectors (Q,M,n_p,3) or (Q,M,M) -> vq (T,Q,M)."""
+        be = self.be
+        vc = be.asarray(vc, np.complex128)
+        T, Q = be.shape(vc)[:2]
+        M = int(np.prod(be.shape(vc)[2:]))
+        e = be.asarray(eigenvectors, np.complex128)
+        assert be.shape(e)[0] == Q and int(np.prod(be.shape(e)[1:])) == M * M, "eigenvector shape mismatch"
+        out = be.empty((T, Q, M), np.complex128)
+        self.lib.call("dp_project_phonon", be.ptr(vc), be.ptr(e), T, Q, M, be.ptr(out), be.stream())
+        return out
+
+    # ------------------------------------------------------------------ A7 / A6 / A5
+    def _series(self, series):
+        s = self.be.asarray(series, np.complex128)
+        shp = self.be.shape(s)
+        assert len(shp) == 2, "series must be (T, S)"
+        return s, shp[0], shp[1]
+
+    def power_fft(self, series, dt, frequency_range, scale=UNIT_CONVERSION):
+        be = self.be
+        s, T, S = self._series(series)
+        f = _host(frequency_range, np.float64)
+        nbytes = self.lib.size("dp_power_fft_workspace_bytes", T, S, float(dt), _hptr(f), f.size)
+        if nbytes == 0:
+            # let the library explain (bad grid, unsupported window length, ...)
+            self.lib.call("dp_power_fft", be.ptr(s), T, S, S, float(dt), _hptr(f), f.size, float(scale), None, None, 0,
+                          be.stream())
+        ws = be.empty((nbytes,), np.uint8)
+        out = be.empty((f.size, S), np.float64)
+        self.lib.call("dp_power_fft", be.ptr(s), T, S, S, float(dt), _hptr(f), f.size, float(scale), be.ptr(out),
+                      be.ptr(ws), nbytes, be.stream())
+        return out
+
+    def power_mem(self, series, dt, frequency_range, coefficients, scale=UNIT_CONVERSION, nan_to_num=True):
+        be = self.be
+        s, T, S = self._series(series)
+        f = _host(frequency_range, np.float64)
+        nbytes = max(self.lib.size("dp_power_mem_workspace_bytes", T, S, f.size, int(coefficients)), 256)
+        ws = be.empty((nbytes,), np.uint8)
+        out = be.empty((f.size, S), np.float64)
+        self.lib.call("dp_power_mem", be.ptr(s), T, S, S, float(dt), _hptr(f), f.size, int(coefficients),
+                      float(scale), int(bool(nan_to_num)), be.ptr(out), be.ptr(ws), nbytes, be.stream())
+        return out
+
+    def power_correlation(self, series, dt, frequency_range, step=10, integration_method=1,
+                          weight=_lib.DP_CORR_WEIGHT_REFERENCE, scale=UNIT_CONVERSION):
+        be = self.be
+        s, T, S = self._series(series)
+        f = _host(frequency_range, np.float64)
+        nbytes = max(self.lib.size("dp_power_correlation_workspace_bytes", T, S, f.size, int(step)), 256)
+        ws = be.empty((nbytes,), np.uint8)
+        out = be.empty((f.size, S), np.float64)
+        self.lib.call("dp_power_correlation", be.ptr(s), T, S, S, float(dt), _hptr(f), f.size, int(step),
+                      int(integration_method), int(weight), float(scale), be.ptr(out), be.ptr(ws), nbytes, be.stream())
+        return out
+
+    def fft_pieces(self, T, dt, frequency_range, max_pieces=1 << 16):
+        """Window list of the FFT method (host query; power_spectrum/__init__.py:33-51)."""
+        f = _host(frequency_range, np.float64)
+        L = ctypes.c_int(0)
+        n = ctypes.c_int(0)
+        starts = np.zeros(max_pieces, dtype=np.int32)
+        self.lib.call("dp_power_fft_pieces", int(T), float(dt), _hptr(f), f.size, ctypes.byref(L), ctypes.byref(n),
+                      _hptr(starts), max_pieces)
+        return L.value, [[int(s), int(s) + L.value] for s in starts[:n.value]]
+
+    def fft_c2c(self, x, direction=-1):
+        be = self.be
+        x = be.asarray(x, np.complex128)
+        batch, n = be.shape(x)
+        nbytes = self.lib.size("dp_fft_c2c_workspace_bytes", n, batch)
+        out = be.empty((batch, n), np.complex128)
+        ws = be.empty((max(nbytes, 256),), np.uint8)
+        self.lib.call("dp_fft_c2c", be.ptr(x), be.ptr(out), n, batch, int(direction), be.ptr(ws), nbytes, be.stream())
+        return out
+
+
+_default = None
+
+
+def default_ops():
+    """Process-wide Ops on the current CUDA device."""
+    global _default
+    if _default is None:
+        _default = Ops()
+    return _default

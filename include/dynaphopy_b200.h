@@ -1,0 +1,195 @@
+/*
+ * dynaphopy_b200 -- C ABI of the B200-native normal-mode-decomposition hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy types.  Each
+ * entry point names the interface of the reference (abelcarreras/DynaPhoPy v1.19.0,
+ * paths relative to the reference tree) it replaces.  The reference's native interface
+ * is three CPython extension modules (c/correlation.c, c/mem.c, c/displacements.c) plus
+ * numpy code in dynaphopy/projection.py and dynaphopy/power_spectrum/__init__.py.
+ *
+ * Conventions
+ *   - Pointers marked [dev] are CUDA device pointers, [host] are host pointers.
+ *   - Complex numbers are interleaved (re, im) doubles (numpy complex128 layout).
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
+ *     asynchronous with respect to the host unless stated, re-entrant, and keep no
+ *     global state except the per-thread last-error string.
+ *   - No hidden device allocation: scratch memory is a caller-owned workspace whose
+ *     size is returned by the matching *_workspace_bytes function.
+ *   - Return value: 0 on success, negative DP_ERR_* on failure; dp_last_error() gives
+ *     the text.  There is no CPU fallback anywhere: without a CUDA device every compute
+ *     entry point fails with DP_ERR_CUDA.
+ */
+#ifndef DYNAPHOPY_B200_H
+#define DYNAPHOPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_OK 0
+#define DP_ERR_INVALID (-1)     /* bad argument                                          */
+#define DP_ERR_UNSUPPORTED (-2) /* valid request this build cannot serve (e.g. FFT length
+                                   with a prime factor > 61)                              */
+#define DP_ERR_WORKSPACE (-3)   /* workspace too small                                   */
+#define DP_ERR_CUDA (-4)        /* CUDA runtime error (includes "no device")             */
+
+/* weight_mode of dp_power_correlation */
+#define DP_CORR_WEIGHT_REFERENCE 0 /* as shipped: exp(w*tau + 1i)  (c/correlation.c:158) */
+#define DP_CORR_WEIGHT_INTENDED 1  /* exp(i*w*tau)  (comments at c/correlation.c:166-172) */
+
+const char* dp_version(void);
+const char* dp_last_error(void);
+/* Number of SMs of the current device (host query), or a negative error. */
+int dp_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * A8  minimum-image displacements.
+ * Replaces: displacements.atomic_displacements(trajectory, positions, cell)
+ *           (c/displacements.c:95-196), called once per atom by
+ *           Dynamics.get_relative_trajectory (dynaphopy/dynamics.py:158-179).
+ * Here all atoms are processed in one launch.
+ *   traj  [dev]  T x N x 3 positions; real doubles, or complex128 when traj_is_complex
+ *                (only the real part is used, as in the reference, :160,176)
+ *   pos0  [dev]  N x 3 lattice sites (Structure.get_positions(supercell))
+ *   cell  [host] 3 x 3, rows = supercell lattice vectors
+ *   out   [dev]  T x N x 3 real displacements (the reference returns complex with
+ *                imag == 0; the host shim widens when asked to)
+ * ------------------------------------------------------------------------------------ */
+int dp_atomic_displacements(const double* traj, int traj_is_complex, const double* pos0,
+                            const double* cell, int64_t T, int N, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * A8+A9+A1 fused: positions -> displacement -> np.gradient velocity -> sqrt(mass) weight.
+ * Replaces: Dynamics.get_relative_trajectory + Dynamics.velocity +
+ *           Dynamics.get_velocity_mass_average (dynaphopy/dynamics.py:158-179, 313-329,
+ *           143-156).
+ *   traj       [dev] Tl x N x 3 local block of frames (real or complex128)
+ *   prev_frame [dev] N x 3 positions of the frame before the block, or NULL when the
+ *                    block starts the trajectory (one-sided difference, np.gradient)
+ *   next_frame [dev] same for the frame after the block (time-sharded multi-GPU halo)
+ *   sqrt_mass  [dev] N, or NULL to skip mass weighting
+ *   out_u      [dev] Tl x N x 3 displacements, or NULL
+ *   out_v      [dev] Tl x N x 3 velocities (mass weighted when sqrt_mass != NULL)
+ * ------------------------------------------------------------------------------------ */
+int dp_velocity_from_positions(const double* traj, int traj_is_complex, const double* pos0,
+                               const double* cell, const double* sqrt_mass, int64_t Tl, int N,
+                               double dt, const double* prev_frame, const double* next_frame,
+                               double* out_u, double* out_v, void* stream);
+
+/* A1 stand-alone: out = v * sqrt_mass[atom]  (dynaphopy/dynamics.py:143-156).
+ * v/out: T x N x 3, real (ncomp = 1) or complex128 (ncomp = 2).                         */
+int dp_mass_weight(const double* v, int ncomp, const double* sqrt_mass, int64_t T, int N,
+                   double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * A2  wave-vector projection, dense form, batched over q (arbitrary q, arbitrary sites).
+ * Replaces: projection.project_onto_wave_vector(trajectory, q_vector, project_on_atom)
+ *           (dynaphopy/projection.py:4-40), one launch for Q wave vectors.
+ *   vc[t,q,p,k] = (N/n_prim)^-1/2 * sum_{i: type(i)=p} sqrt_mass[i] v[t,i,k] exp(-i q.r_i)
+ *   v         [dev]  T x N x 3, real or complex128 (v_is_complex)
+ *   sqrt_mass [dev]  N, or NULL when v is already mass weighted
+ *   pos0      [dev]  N x 3 equilibrium positions
+ *   type_idx  [host] N primitive-atom index of every supercell atom
+ *   q_cart    [host] Q x 3 Cartesian wave vectors (Quasiparticle.get_q_vector)
+ *   project_on_atom  -1, or a primitive atom index: other atoms are skipped while the
+ *                    normalisation is unchanged (projection.py:26-28,38-39)
+ *   out_vc    [dev]  T x Q x n_prim x 3 complex128
+ *   workspace [dev]  dp_project_wave_vector_workspace_bytes(N, Q) bytes
+ * ------------------------------------------------------------------------------------ */
+size_t dp_project_wave_vector_workspace_bytes(int N, int Q);
+int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt_mass,
+                           const double* pos0, const int* type_idx, int N, int n_prim, int64_t T,
+                           const double* q_cart, int Q, int project_on_atom, double* out_vc,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * A2  wave-vector projection, commensurate form: for q commensurate with a diagonal
+ * supercell the lattice sum is a 3-D DFT over unit-cell translations (atom order of
+ * dynaphopy/atoms.py:139-156: i = u*Nc + x + Nx*(y + Ny*z)), so every frame is read from
+ * HBM once for the whole q list.
+ *   v         [dev]  T x N x 3 real velocities, N = n_unit * dims[0]*dims[1]*dims[2]
+ *   dims      [host] 3 supercell multiplicities (Dynamics.get_supercell_matrix)
+ *   unit_type [host] n_unit primitive-atom index of every unit-cell atom
+ *   qbin      [dev]  Q x 3 int32 DFT bin of every q: round(q_unitcell * dims) mod dims
+ *   twiddle   [dev]  Q x n_unit complex128: (N/n_prim)^-1/2 sqrt(mass_u) exp(-i q.tau_u)
+ *   out_vc    [dev]  T x Q x n_prim x 3 complex128
+ * ------------------------------------------------------------------------------------ */
+size_t dp_project_commensurate_workspace_bytes(const int* dims, int n_unit, int n_prim, int Q);
+int dp_project_commensurate(const double* v, const int* dims, int n_unit, const int* unit_type,
+                            int n_prim, int64_t T, const int* qbin, const double* twiddle, int Q,
+                            int project_on_atom, double* out_vc, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * A3  eigenvector contraction, batched over q.
+ * Replaces: projection.project_onto_phonon(vc, eigenvectors) (dynaphopy/projection.py:43-54)
+ *   vq[t,q,s] = sum_{p,k} vc[t,q,p,k] * conj(e[q,s,p,k])
+ *   vc  [dev] T x Q x M complex128 (M = 3*n_prim, (p,k) flattened)
+ *   eig [dev] Q x M x M complex128, e[q][s][3p+k] (phonopy_link.py:189-192 arrangement)
+ *   vq  [dev] T x Q x M complex128 (may alias vc only if M*16 bytes rows are private: no)
+ * ------------------------------------------------------------------------------------ */
+int dp_project_phonon(const double* vc, const double* eig, int64_t T, int Q, int M, double* vq,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * A7  power spectrum, FFT method (selector keys 2 and 3).
+ * Replaces: get_fft_numpy_spectra / _numpy_power / _division_of_data
+ *           (dynaphopy/power_spectrum/__init__.py:226-270, 33-51), all columns at once.
+ *   series [dev]  T x ld complex128, column s of row t at series[(t*ld + s)*2]
+ *                 (the (T, M') array the reference passes; ld >= S)
+ *   freq   [host] F requested frequencies (parameters.frequency_range), F >= 2
+ *   scale         multiplied into the result (the reference's unit_conversion, :9)
+ *   out    [dev]  F x S doubles, row-major (the reference's (F, M') return layout)
+ * dp_power_fft_pieces reports the window list for inspection (host only).
+ * ------------------------------------------------------------------------------------ */
+size_t dp_power_fft_workspace_bytes(int64_t T, int S, double dt, const double* freq, int F);
+int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq,
+                 int F, double scale, double* out, void* workspace, size_t workspace_bytes,
+                 void* stream);
+int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* piece_len,
+                        int* n_pieces, int* starts, int max_pieces);
+
+/* ------------------------------------------------------------------------------------
+ * A6  power spectrum, maximum-entropy (Burg) method (selector key 1).
+ * Replaces: get_mem_power_spectra -> mem.mem(frequency, velocity, time_step, coefficients)
+ *           (dynaphopy/power_spectrum/__init__.py:81-103, c/mem.c:102-252) with the
+ *           canonical semantics Data[N] := 0 for the reference's out-of-bounds read.
+ *   nan_to_num != 0 applies np.nan_to_num (power_spectrum/__init__.py:101).
+ * ------------------------------------------------------------------------------------ */
+size_t dp_power_mem_workspace_bytes(int64_t T, int S, int F, int coefficients);
+int dp_power_mem(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq,
+                 int F, int coefficients, double scale, int nan_to_num, double* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * A5  power spectrum, direct correlation method (selector key 0).
+ * Replaces: get_fourier_direct_power_spectra -> correlation.correlation_par(frequency,
+ *           velocity, time_step, step, integration_method)
+ *           (dynaphopy/power_spectrum/__init__.py:57-75, c/correlation.c:101-178).
+ *   weight_mode DP_CORR_WEIGHT_REFERENCE reproduces the shipped real-exponential weights,
+ *   DP_CORR_WEIGHT_INTENDED uses exp(i w tau).  integration_method outside {0,1} fails
+ *   (the reference returns NULL without setting an exception, c/correlation.c:138-141).
+ * ------------------------------------------------------------------------------------ */
+size_t dp_power_correlation_workspace_bytes(int64_t T, int S, int F, int step);
+int dp_power_correlation(const double* series, int64_t T, int S, int64_t ld, double dt,
+                         const double* freq, int F, int step, int integration_method,
+                         int weight_mode, double scale, double* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Utility: batched complex FFT on device data with the library's own radix engine
+ * (the transform used inside dp_power_fft; exposed for validation and benchmarking).
+ *   in/out [dev] batch x n complex128 (contiguous rows), direction -1 forward, +1 inverse
+ *   (unnormalised).  n must factor into primes <= 61.
+ * ------------------------------------------------------------------------------------ */
+size_t dp_fft_c2c_workspace_bytes(int n, int batch);
+int dp_fft_c2c(const double* in, double* out, int n, int batch, int direction, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNAPHOPY_B200_H */
