@@ -187,9 +187,9 @@ extern "C" {
 
 int dp_atomic_displacements(const double* traj, int traj_is_complex, const double* pos0,
                             const double* cell, int64_t T, int N, double* out, void* stream) {
-    DP_REQUIRE(traj && pos0 && cell && out, DP_ERR_INVALID, "dp_atomic_displacements: null pointer");
     DP_REQUIRE(T >= 0 && N > 0, DP_ERR_INVALID, "dp_atomic_displacements: bad sizes T=%lld N=%d", (long long)T, N);
-    if (T == 0) return DP_OK;
+    if (T == 0) return DP_OK;      // empty trajectory: nothing to do (pointers may be null)
+    DP_REQUIRE(traj && pos0 && cell && out, DP_ERR_INVALID, "dp_atomic_displacements: null pointer");
     dp::CellMats m;
     dp::make_cell_mats(cell, &m);
     int64_t total = T * N;
@@ -238,9 +238,9 @@ int dp_velocity_from_positions(const double* traj, int traj_is_complex, const do
 
 int dp_mass_weight(const double* v, int ncomp, const double* sqrt_mass, int64_t T, int N, double* out,
                    void* stream) {
-    DP_REQUIRE(v && sqrt_mass && out, DP_ERR_INVALID, "dp_mass_weight: null pointer");
     DP_REQUIRE((ncomp == 1 || ncomp == 2) && T >= 0 && N > 0, DP_ERR_INVALID, "dp_mass_weight: bad sizes");
     if (T == 0) return DP_OK;
+    DP_REQUIRE(v && sqrt_mass && out, DP_ERR_INVALID, "dp_mass_weight: null pointer");
     int per_atom = 3 * ncomp;
     int64_t total = T * N * per_atom;
     auto k = dp::mass_weight_kernel;

@@ -151,7 +151,7 @@ int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt
                            const double* pos0, const int* type_idx, int N, int n_prim, int64_t T,
                            const double* q_cart, int Q, int project_on_atom, double* out_vc,
                            void* workspace, size_t workspace_bytes, void* stream) {
-    DP_REQUIRE(v && pos0 && type_idx && q_cart && out_vc && workspace, DP_ERR_INVALID,
+    DP_REQUIRE((T == 0 || (v && out_vc)) && pos0 && type_idx && q_cart && workspace, DP_ERR_INVALID,
                "dp_project_wave_vector: null pointer");
     DP_REQUIRE(N > 0 && n_prim > 0 && n_prim < 1024 && T >= 0 && Q > 0, DP_ERR_INVALID,
                "dp_project_wave_vector: bad sizes N=%d n_prim=%d T=%lld Q=%d", N, n_prim, (long long)T, Q);
@@ -212,7 +212,7 @@ int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt
 }
 
 int dp_project_phonon(const double* vc, const double* eig, int64_t T, int Q, int M, double* vq, void* stream) {
-    DP_REQUIRE(vc && eig && vq, DP_ERR_INVALID, "dp_project_phonon: null pointer");
+    DP_REQUIRE((T == 0 || (vc && vq)) && eig, DP_ERR_INVALID, "dp_project_phonon: null pointer");
     DP_REQUIRE(T >= 0 && Q > 0 && M > 0 && M % 3 == 0, DP_ERR_INVALID, "dp_project_phonon: bad sizes (M must be 3*n_prim)");
     DP_REQUIRE(Q <= 65535, DP_ERR_UNSUPPORTED, "dp_project_phonon: Q=%d too large for one launch", Q);
     if (T == 0) return DP_OK;

@@ -247,7 +247,7 @@ size_t dp_project_commensurate_workspace_bytes(const int* dims, int n_unit, int 
 int dp_project_commensurate(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
                             int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
                             double* out_vc, void* workspace, size_t workspace_bytes, void* stream) {
-    DP_REQUIRE(v && dims && unit_type && qbin && twiddle && out_vc && workspace, DP_ERR_INVALID,
+    DP_REQUIRE((T == 0 || (v && out_vc)) && dims && unit_type && qbin && twiddle && workspace, DP_ERR_INVALID,
                "dp_project_commensurate: null pointer");
     DP_REQUIRE(n_unit > 0 && n_prim > 0 && T >= 0 && Q > 0 && project_on_atom < n_prim, DP_ERR_INVALID,
                "dp_project_commensurate: bad sizes");

@@ -1,0 +1,356 @@
+"""Parity of the CUDA path with the reference, through the C ABI.
+
+Every test runs twice: on the host emulation of the kernel sources (CPU suite, `-m "not gpu"`)
+and on the real sm_100a library (`-m gpu`).  Expected values come from
+  * tests/golden/*.npz -- outputs of the REFERENCE ITSELF (oracle/gen_golden.py), and
+  * oracle.port        -- the CPU restatement pinned against the reference in
+                          tests/test_oracle_pinning.py,
+never from the code under test.  Tolerances: bit-exact for the displacement / velocity maps,
+1e-10 normwise relative (BASELINE.json north_star) for projections and spectra, exact argmax
+(peak-frequency bin) for spectra.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, relerr, to_np
+from oracle import port
+
+TOL = 1e-10
+
+
+def is_cuda(kops):
+    return type(kops.be).__name__ == "TorchCudaBackend"
+
+
+# ------------------------------------------------------------------------------- A8 / A9 / A1
+def test_displacements_bit_exact(kops):
+    g = golden("displacements_triclinic")
+    u = to_np(kops.atomic_displacements(g["trajectory"], g["positions"], g["supercell"]))
+    assert np.array_equal(u, g["relative"])
+    # complex128 input (the reference's native dtype): only the real part is used
+    uc = to_np(kops.atomic_displacements(g["trajectory"].astype(complex), g["positions"], g["supercell"]))
+    assert np.array_equal(uc, g["relative"])
+
+
+def test_velocity_pipeline_bit_exact(kops):
+    g = golden("displacements_triclinic")
+    dt = float(g["dt"])
+    u, vm = kops.velocity_from_positions(g["trajectory"], g["positions"], g["supercell"], dt,
+                                         sqrt_mass=np.sqrt(g["masses"]), want_displacements=True)
+    assert np.array_equal(to_np(u), g["relative"])
+    assert np.array_equal(to_np(vm), g["vm"])
+    v = to_np(kops.velocity_from_positions(g["trajectory"], g["positions"], g["supercell"], dt))
+    assert np.array_equal(v, g["velocity"])
+    assert np.array_equal(to_np(kops.mass_weight(g["velocity"], np.sqrt(g["masses"]))), g["vm"])
+
+
+@pytest.mark.parametrize("cut", [1, 7, 48, 95])
+def test_velocity_time_shard_halo(kops, cut):
+    """Time-sharded evaluation with a one-frame halo equals the single-block result."""
+    g = golden("displacements_triclinic")
+    dt = float(g["dt"])
+    tr = g["trajectory"]
+    a = to_np(kops.velocity_from_positions(tr[:cut], g["positions"], g["supercell"], dt, next_frame=tr[cut]))
+    b = to_np(kops.velocity_from_positions(tr[cut:], g["positions"], g["supercell"], dt, prev_frame=tr[cut - 1]))
+    assert np.array_equal(np.concatenate([a, b]), g["velocity"])
+
+
+@pytest.mark.parametrize("tag", ["xdatcar", "lammps"])
+def test_reading_test_known_answers(kops, tag):
+    """unittest/reading_test.py:23-102 -- the reference's only known-answer test on this path."""
+    g = golden("reading_test")
+    u = to_np(kops.atomic_displacements(g[tag + "_trajectory"], g[tag + "_positions"], g[tag + "_supercell"]))
+    assert np.array_equal(u, g[tag + "_relative"])
+    # Dynamics.get_mean_displacement_matrix (dynamics.py:207-239) on top of the kernel output
+    typ = g[tag + "_atom_type"]
+    ntypes = typ.max() + 1
+    mats = np.zeros((ntypes, 3, 3))
+    counts = np.bincount(typ)
+    for i in range(u.shape[1]):
+        mats[typ[i]] += u[:, i, :].T @ u[:, i, :] / counts[typ[i]]
+    mean = np.average(mats / u.shape[0], axis=0)
+    assert np.allclose(mean, g[tag + "_mean_matrix"], rtol=1e-12, atol=0)
+    assert np.allclose(mean, g[tag + "_mean_matrix_literal"], rtol=1e-3, atol=1e-6)
+
+
+def test_displacements_empty_and_errors(kops):
+    g = golden("displacements_triclinic")
+    out = kops.atomic_displacements(np.zeros((0, 24, 3)), g["positions"], g["supercell"])
+    assert tuple(out.shape) == (0, 24, 3)
+    from dynaphopy_b200._lib import DpError
+    with pytest.raises(DpError):      # np.gradient needs two frames
+        kops.velocity_from_positions(g["trajectory"][:1], g["positions"], g["supercell"], 0.002)
+
+
+# ------------------------------------------------------------------------------- A2 / A3
+def _commensurate_inputs(g, q_indices=None):
+    dims = g["dims"]
+    nc = int(np.prod(dims))
+    cell = g["unit_cell"]
+    n_prim = int(g["n_prim"])
+    unit_type = g["atom_type"][::nc]
+    tau = g["positions"][::nc]
+    keep, qb, tw = [], [], []
+    for i in (range(len(g["q_cart"])) if q_indices is None else q_indices):
+        m = g["q_cart"][i] @ cell.T / (2 * np.pi) * dims
+        if np.abs(m - np.round(m)).max() > 1e-6:
+            continue
+        keep.append(i)
+        qb.append(np.mod(np.round(m).astype(int), dims))
+        tw.append(np.sqrt(g["unit_masses"]) * np.exp(-1j * (tau @ g["q_cart"][i])) / np.sqrt(len(g["masses"]) / n_prim))
+    return dims, unit_type, n_prim, np.array(qb, dtype=np.int32), np.array(tw), keep
+
+
+@pytest.mark.parametrize("name", ["cubic2_232", "si_conv_222", "cubic2_222_complex"])
+def test_projection_dense_vs_reference(kops, name):
+    g = golden(name)
+    n_prim = int(g["n_prim"])
+    sm = np.sqrt(g["masses"])
+    vc = to_np(kops.project_wave_vector(g["velocity"], sm, g["positions"], g["atom_type"], n_prim, g["q_cart"]))
+    assert vc.shape == (g["velocity"].shape[0], len(g["q_cart"]), n_prim, 3)
+    assert relerr(vc.transpose(1, 0, 2, 3), g["vc"]) < TOL
+    # already mass-weighted input, one q at a time (the reference's calling pattern)
+    vc1 = to_np(kops.project_wave_vector(g["vm"], None, g["positions"], g["atom_type"], n_prim, g["q_cart"][2]))
+    assert relerr(vc1[:, 0], g["vc"][2]) < TOL
+    vca = to_np(kops.project_wave_vector(g["velocity"], sm, g["positions"], g["atom_type"], n_prim, g["q_cart"][1],
+                                         project_on_atom=0))
+    assert relerr(vca[:, 0], g["vc_atom0"]) < TOL
+    assert np.all(vca[:, 0, 1:] == 0)
+    vq = to_np(kops.project_phonon(vc, g["eigenvectors"]))
+    assert relerr(vq.transpose(1, 0, 2), g["vq"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["cubic2_232", "si_conv_222"])
+def test_projection_commensurate_vs_reference(kops, name):
+    g = golden(name)
+    dims, unit_type, n_prim, qb, tw, keep = _commensurate_inputs(g)
+    assert len(keep) >= 4
+    vc = to_np(kops.project_commensurate(g["velocity"], dims, unit_type, n_prim, qb, tw))
+    assert relerr(vc.transpose(1, 0, 2, 3), g["vc"][keep]) < TOL
+    dims, unit_type, n_prim, qb, tw, keep = _commensurate_inputs(g, [1])
+    vca = to_np(kops.project_commensurate(g["velocity"], dims, unit_type, n_prim, qb, tw, project_on_atom=0))
+    assert relerr(vca[:, 0], g["vc_atom0"]) < TOL
+    assert np.all(vca[:, 0, 1:] == 0)
+
+
+def _random_lattice_case(rng, dims, n_unit, n_prim, nt):
+    """Seeded synthetic structure (SURVEY 8d style) + oracle projection for every commensurate q."""
+    dims = np.array(dims)
+    nc = int(np.prod(dims))
+    cell = np.array([[4.0, 0.0, 0.0], [0.3, 4.2, 0.0], [-0.2, 0.5, 3.9]])
+    frac = rng.random((n_unit, 3))
+    unit_pos = frac @ cell
+    unit_type = np.arange(n_unit) % n_prim
+    unit_mass = 20.0 + 10.0 * unit_type
+    pos = port.supercell_positions(unit_pos, cell, dims)
+    typ = port.supercell_replicate(unit_type, dims).astype(np.int32)
+    mass = port.supercell_replicate(unit_mass, dims)
+    v = rng.normal(size=(nt, n_unit * nc, 3))
+    return dict(dims=dims, cell=cell, unit_pos=unit_pos, unit_type=unit_type.astype(np.int32), unit_mass=unit_mass,
+                pos=pos, typ=typ, mass=mass, v=v, n_prim=n_prim, nc=nc)
+
+
+@pytest.mark.parametrize("dims,n_unit,n_prim", [((1, 1, 1), 2, 2), ((2, 1, 3), 1, 1), ((3, 5, 2), 3, 3),
+                                                ((7, 2, 2), 4, 2), ((4, 6, 5), 2, 2), ((11, 1, 2), 2, 1),
+                                                ((16, 16, 20), 2, 2), ((13, 9, 8), 3, 3), ((32, 2, 1), 2, 2),
+                                                ((17, 3, 3), 1, 1), ((12, 10, 6), 5, 2)])
+def test_projection_commensurate_shapes(kops, dims, n_unit, n_prim):
+    """All pencil lengths / unit-cell layouts: FFT form == dense form == oracle on random q subsets."""
+    rng = np.random.default_rng(hash((dims, n_unit)) % (2 ** 31))
+    nt = 3 if not is_cuda(kops) else 17
+    c = _random_lattice_case(rng, dims, n_unit, n_prim, nt)
+    nq = min(c["nc"], 24)
+    m = np.stack([rng.integers(0, d, nq) for d in c["dims"]], axis=1)
+    m[0] = 0
+    shift = rng.integers(-1, 2, size=m.shape)                     # q outside the first cell too
+    q_unit = (m + shift * c["dims"]) / c["dims"]
+    q_cart = 2 * np.pi * q_unit @ np.linalg.inv(c["cell"]).T
+    tw = np.sqrt(c["unit_mass"])[None, :] * np.exp(-1j * q_cart @ c["unit_pos"].T) / np.sqrt(c["nc"] * n_unit / n_prim)
+    vc = to_np(kops.project_commensurate(c["v"], c["dims"], c["unit_type"], n_prim, m.astype(np.int32), tw))
+    vm = port.velocity_mass_average(c["v"], c["mass"])
+    ref = np.stack([port.project_onto_wave_vector(vm, c["pos"], c["typ"], n_prim, q) for q in q_cart], axis=1)
+    assert relerr(vc, ref) < TOL
+    dense = to_np(kops.project_wave_vector(c["v"], np.sqrt(c["mass"]), c["pos"], c["typ"], n_prim, q_cart))
+    assert relerr(dense, ref) < TOL
+
+
+def test_projection_ragged_and_empty(kops):
+    g = golden("cubic2_232")
+    n_prim = int(g["n_prim"])
+    sm = np.sqrt(g["masses"])
+    # T and Q not multiples of any tile size; 37 copies of 5 q
+    q = np.tile(g["q_cart"], (37, 1))[:181]
+    vc = to_np(kops.project_wave_vector(g["velocity"][:77], sm, g["positions"], g["atom_type"], n_prim, q))
+    assert relerr(vc[:, :5].transpose(1, 0, 2, 3), g["vc"][:, :77]) < TOL
+    assert np.array_equal(vc[:, 5:10], vc[:, :5])
+    out = kops.project_wave_vector(g["velocity"][:0], sm, g["positions"], g["atom_type"], n_prim, q)
+    assert tuple(out.shape) == (0, 181, n_prim, 3)
+    from dynaphopy_b200._lib import DpError
+    with pytest.raises(DpError):
+        kops.project_wave_vector(g["velocity"], sm, g["positions"], g["atom_type"], n_prim, q, project_on_atom=5)
+    with pytest.raises(DpError):      # DFT bin outside the grid
+        dims, unit_type, n_prim, qb, tw, _ = _commensurate_inputs(g)
+        kops.project_commensurate(g["velocity"], dims, unit_type, n_prim, qb + 7, tw)
+
+
+def test_project_phonon_wide(kops):
+    """M = 12 and 30 modes (GaN / larger cells), ragged frame count."""
+    rng = np.random.default_rng(5)
+    for n_prim, nt, nq in ((4, 131, 3), (10, 70, 2)):
+        m = 3 * n_prim
+        vc = rng.normal(size=(nt, nq, n_prim, 3)) + 1j * rng.normal(size=(nt, nq, n_prim, 3))
+        eig = rng.normal(size=(nq, m, n_prim, 3)) + 1j * rng.normal(size=(nq, m, n_prim, 3))
+        vq = to_np(kops.project_phonon(vc, eig))
+        ref = np.stack([port.project_onto_phonon(vc[:, q], eig[q]) for q in range(nq)], axis=1)
+        assert relerr(vq, ref) < TOL
+
+
+# ------------------------------------------------------------------------------- FFT engine
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7, 16, 30, 49, 121, 243, 300, 1000, 2500, 3000, 4096, 4100, 5000, 8192,
+                               20000, 32768, 2 * 61 * 61])
+def test_fft_engine(kops, n):
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(3, n)) + 1j * rng.normal(size=(3, n))
+    assert relerr(kops.fft_c2c(x, -1), np.fft.fft(x, axis=1)) < 1e-14
+    assert relerr(kops.fft_c2c(x, +1), np.fft.ifft(x, axis=1) * n) < 1e-14
+
+
+def test_fft_engine_linearity_and_unsupported(kops):
+    rng = np.random.default_rng(0)
+    n = 6000
+    x = rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))
+    y = to_np(kops.fft_c2c(x, -1))
+    back = to_np(kops.fft_c2c(y, +1)) / n
+    assert relerr(back, x) < 1e-14                                  # round trip
+    z = to_np(kops.fft_c2c(x[:1] * 2.0 - 1j * x[1:], -1))
+    assert relerr(z, 2.0 * y[:1] - 1j * y[1:]) < 1e-14               # linearity
+    from dynaphopy_b200._lib import DpError
+    with pytest.raises(DpError):
+        kops.fft_c2c(x[:, :4099], -1)                                # prime > 61
+
+
+# ------------------------------------------------------------------------------- A7 / A6 / A5
+@pytest.mark.parametrize("name", ["cubic2_232", "si_conv_222", "cubic2_222_complex"])
+def test_spectra_vs_reference_golden(kops, name):
+    g = golden(name)
+    vq = g["vq"][1]
+    dt = float(g["time_step_average"])
+    f = g["freq"]
+    L, pieces = kops.fft_pieces(vq.shape[0], dt, f)
+    assert pieces == port.division_of_data(f[1] - f[0], vq.shape[0], dt)
+    ps = to_np(kops.power_fft(vq, dt, f))
+    assert relerr(ps, g["ps_fft"]) < TOL
+    assert np.array_equal(ps.argmax(0), g["ps_fft"].argmax(0))
+    cols = g["vc"][1].swapaxes(1, 2).reshape(-1, vq.shape[1])          # dynaphopy/__init__.py:764 layout
+    assert relerr(kops.power_fft(cols, dt, f), g["ps_fft_wave_vector_cols"]) < TOL
+    pm = to_np(kops.power_mem(vq, dt, f, int(g["mem_order"])))
+    assert relerr(pm, g["ps_mem"]) < TOL
+    assert np.array_equal(pm.argmax(0), g["ps_mem"].argmax(0))
+    for method in (1, 0):
+        ref = g["ps_corr_m%d" % method]
+        pc = to_np(kops.power_correlation(vq, dt, f, 10, method, 0))
+        assert np.array_equal(np.isfinite(pc), np.isfinite(ref))        # non-finite where the reference is
+        assert relerr(pc, ref) < TOL
+        ref = g["ps_corr_intended_m%d" % method]
+        pc = to_np(kops.power_correlation(vq, dt, f, 10, method, 1, scale=1.0))
+        assert relerr(pc, ref) < TOL
+
+
+def _series(rng, nt, ns, dt):
+    t = np.arange(nt) * dt
+    x = rng.normal(size=(nt, ns)) + 1j * rng.normal(size=(nt, ns))
+    for f0, a0 in ((3.83, 3.0), (7.11, 2.0), (15.53, 1.5)):
+        x += a0 * np.exp(2j * np.pi * f0 * t[:, None] + 1j * rng.uniform(0, 2 * np.pi, size=(1, ns)))
+    return x
+
+
+@pytest.mark.parametrize("nt,dt,res,fmax", [(2500, 0.002, 0.05, 18.2),      # cfg 1/2: single window L = T
+                                            (3000, 0.001, 0.05, 25.0),      # cfg 4 (Ag2Cu2O4)
+                                            (1201, 0.002, 2.0, 40.0),       # L = 250, 5 windows, odd T
+                                            (700, 0.001, 3.0, 60.0),        # odd L = 333, grid beyond Nyquist? no: clamps
+                                            (640, 0.002, 1.7, 300.0)])      # grid far beyond +Nyquist (np.interp clamps)
+def test_power_fft_vs_oracle(kops, nt, dt, res, fmax):
+    rng = np.random.default_rng(nt)
+    ns = 3 if not is_cuda(kops) else 12
+    x = _series(rng, nt, ns, dt)
+    f = np.arange(0, fmax + res, res)
+    ps = to_np(kops.power_fft(x, dt, f))
+    ref = port.fft_spectra(x, dt, f)
+    assert ps.shape == ref.shape
+    assert relerr(ps, ref) < TOL
+    assert np.array_equal(ps.argmax(0), ref.argmax(0))
+
+
+def test_power_fft_negative_grid_and_ld(kops):
+    """Grid with negative frequencies and a strided (T, ld) parent array."""
+    rng = np.random.default_rng(3)
+    x = _series(rng, 900, 5, 0.002)
+    f = np.arange(-30.0, 30.0, 0.7)
+    ps = to_np(kops.power_fft(x[:, 1:4].copy(), 0.002, f))
+    ref = port.fft_spectra(x[:, 1:4], 0.002, f)
+    assert relerr(ps, ref) < TOL
+
+
+def test_power_fft_long_windows(kops):
+    """cfg-3/5 window geometry: L = 20000 (four-step, radix 5) with overlapping windows."""
+    nt = 50001 if is_cuda(kops) else 20011
+    rng = np.random.default_rng(7)
+    x = _series(rng, nt, 2 if not is_cuda(kops) else 6, 0.001)
+    f = np.arange(0, 31.3, 0.05)
+    L, pieces = kops.fft_pieces(nt, 0.001, f)
+    assert L == 20000 and pieces == port.division_of_data(0.05, nt, 0.001)
+    ps = to_np(kops.power_fft(x, 0.001, f))
+    ref = port.fft_spectra(x, 0.001, f, use_fft_correlate=True)      # FFT-based np.correlate restatement
+    assert relerr(ps, ref) < TOL
+    assert np.array_equal(ps.argmax(0), ref.argmax(0))
+
+
+def test_power_mem_vs_oracle(kops):
+    cuda = is_cuda(kops)
+    nt, m, ns = (2500, 1000, 6) if cuda else (900, 120, 2)          # cfg 2 on the GPU
+    rng = np.random.default_rng(11)
+    x = _series(rng, nt, ns, 0.002)
+    x[:, -1] = x[:, -1].real                                         # Im part all zero -> skipped part (xms == 0)
+    f = np.arange(0, 18.25, 0.05)
+    pm = to_np(kops.power_mem(x, 0.002, f, m))
+    ref = port.mem_spectra(x, 0.002, f, m)
+    assert relerr(pm, ref) < TOL
+    assert np.array_equal(pm.argmax(0), ref.argmax(0))
+    from dynaphopy_b200._lib import DpError
+    with pytest.raises(DpError, match="Number of coefficients"):    # power_spectrum/__init__.py:85-87
+        kops.power_mem(x[: m + 1], 0.002, f, m)
+
+
+def test_power_correlation_vs_oracle(kops):
+    cuda = is_cuda(kops)
+    nt, ns = (2500, 6) if cuda else (777, 2)
+    rng = np.random.default_rng(13)
+    x = _series(rng, nt, ns, 0.002)
+    f = np.arange(0, 40.05, 0.05 if cuda else 0.5)
+    for method in (1, 0):
+        for step in (10, 3):
+            ref = port.correlation_spectra(x, 0.002, f, step, method, "reference")
+            pc = to_np(kops.power_correlation(x, 0.002, f, step, method, 0))
+            fin_ref, fin = np.isfinite(ref), np.isfinite(pc)
+            # overflow boundary: the factored sum may cross DBL_MAX one grid point earlier/later
+            mismatch = fin_ref != fin
+            assert mismatch.sum() <= 2 * ns
+            ok = fin_ref & fin & (np.abs(ref) < 1e290)
+            assert ok.any()
+            assert np.abs(pc - ref)[ok].max() / np.abs(ref[ok]).max() < TOL
+            assert np.all(np.abs(pc[ok] - ref[ok]) <= 1e-9 * np.abs(ref[ok]) + 1e-300)   # element-wise: huge dynamic range
+            ref = port.correlation_spectra(x, 0.002, f, step, method, "intended")
+            pc = to_np(kops.power_correlation(x, 0.002, f, step, method, 1))
+            assert relerr(pc, ref) < TOL
+    from dynaphopy_b200._lib import DpError
+    with pytest.raises(DpError, match="Integration method"):         # c/correlation.c:138-141
+        kops.power_correlation(x, 0.002, f, 10, 2, 0)
+
+
+def test_spectra_single_column_and_two_frequencies(kops):
+    rng = np.random.default_rng(17)
+    x = _series(rng, 512, 1, 0.002)
+    f = np.array([1.0, 9.0])
+    assert relerr(kops.power_fft(x, 0.002, f), port.fft_spectra(x, 0.002, f)) < TOL
+    assert relerr(kops.power_mem(x, 0.002, f, 40), port.mem_spectra(x, 0.002, f, 40)) < TOL
+    assert relerr(kops.power_correlation(x, 0.002, f, 10, 1, 1), port.correlation_spectra(x, 0.002, f, 10, 1, "intended")) < TOL
