@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the normal-mode-decomposition hot path on BASELINE.json's headline workload.
+
+Workload (BASELINE.json configs[4], SURVEY.md section 8d "cfg 5-A"): synthetic 2-atom cubic cell,
+supercell 16x16x20 = 10 240 atoms, 2^17 = 131 072 frames (dt = 1 fs), the full commensurate q-mesh
+(5120 q, 6 modes each = 30 720 series), default frequency grid 0..40 THz step 0.05 (FFT windows of
+20 000 samples, 7 windows).  One step = wave-vector projection of every frame onto every q
+(A1+A2) -> eigenvector contraction (A3) -> [all-to-all when N > 1] -> FFT power spectra of every
+series (A7).  The total problem is fixed and the frames are sharded over the ranks by time block
+("scaling": "strong").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference [...]                         # reference arm (host CPU)
+
+metric/value: atom*frames per second through the whole step, all ranks together (inputs resident
+in HBM).  e2e: the same through MeshPipeline.run_from_host with the trajectory in pinned HOST
+memory (H2D of every frame and D2H of the spectra inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# ---- workload definition ------------------------------------------------------------
+DIMS = (16, 16, 20)
+A_LAT = 4.0
+UNIT_FRAC = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]])
+UNIT_MASS = np.array([28.0855, 69.723])
+DT = 0.001
+LINES = ((3.83, 1.0), (7.11, 0.7), (15.53, 0.4))
+KB = 0.831446            # u A^2 / ps^2 / K  (reference's k_B, iofile/__init__.py:348)
+TEMP = 400.0
+SEED = 20260101
+FREQ = np.arange(0, 40.05, 0.05)
+CHUNK = 1024             # frames generated / copied per chunk
+
+
+def workload(frames):
+    cell = np.eye(3) * A_LAT
+    nc = int(np.prod(DIMS))
+    unit_pos = UNIT_FRAC @ cell
+    grid = np.array([[x, y, z] for z in range(DIMS[2]) for y in range(DIMS[1]) for x in range(DIMS[0])], float) @ cell
+    pos = (unit_pos[:, None, :] + grid[None]).reshape(-1, 3)
+    typ = np.repeat(np.arange(2), nc).astype(np.int32)
+    mass = np.repeat(UNIT_MASS, nc)
+    m = np.array([[mx, my, mz] for mz in range(DIMS[2]) for my in range(DIMS[1]) for mx in range(DIMS[0])])
+    q_red = m / np.array(DIMS)                                 # identity primitive matrix
+    q_cart = q_red @ (2.0 * np.pi * np.linalg.inv(cell).T)     # Quasiparticle.get_q_vector
+    return dict(cell=cell, nc=nc, pos=pos, typ=typ, mass=mass, q_cart=q_cart, n_atoms=2 * nc, frames=frames,
+                n_prim=2, Q=len(q_cart), M=6)
+
+
+def gen_chunk_torch(torch, dev, wl, t0, t1):
+    """Frames [t0, t1) of the synthetic trajectory (white noise + three spectral lines); the random
+    stream depends only on the chunk index, so the data are the same for every rank count."""
+    assert t0 % CHUNK == 0
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + t0 // CHUNK)
+    n = wl["n_atoms"]
+    sigma = torch.as_tensor(np.sqrt(KB * TEMP / wl["mass"]), device=dev)[None, :, None]
+    v = torch.randn((t1 - t0, n, 3), dtype=torch.float64, device=dev, generator=g)
+    gp = torch.Generator(device=dev)
+    gp.manual_seed(SEED - 1)
+    t = (torch.arange(t0, t1, device=dev, dtype=torch.float64) * DT)[:, None, None]
+    for f0, a0 in LINES:
+        phi = torch.rand((1, n, 3), dtype=torch.float64, device=dev, generator=gp) * (2 * np.pi)
+        v += a0 * torch.cos(2 * np.pi * f0 * t + phi)
+    return v * sigma
+
+
+def random_unitary_eigenvectors(torch, dev, Q, M):
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + 7)
+    a = torch.randn((Q, M, M), dtype=torch.float64, device=dev, generator=g) + \
+        1j * torch.randn((Q, M, M), dtype=torch.float64, device=dev, generator=g)
+    qmat, _ = torch.linalg.qr(a)
+    return qmat.transpose(1, 2).contiguous()                   # e[q][s][j] = E[j][s]
+
+
+# ---- clocks ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except Exception:
+                continue
+            for nme, val in zip(names, parts[2:]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ---- CPU baseline: the reference's own algorithm (oracle port / compiled reference) on host cores ----
+def cpu_sample(wl, v_sub, eig_sub, q_idx, n_series, frames_total):
+    """Bounded sample of the same workload on the host: projection of v_sub (T_sub frames, all atoms)
+    onto len(q_idx) q, contraction, and FFT spectra of n_series full-length series; linear
+    extrapolation to the whole job (projection ~ T*Q, spectra ~ number of series)."""
+    from oracle import port
+    vm = port.velocity_mass_average(v_sub.astype(complex), wl["mass"])     # reference arrays are complex128
+    t0 = time.perf_counter()
+    vcs = [port.project_onto_wave_vector(vm, wl["pos"], wl["typ"], wl["n_prim"], wl["q_cart"][q]) for q in q_idx]
+    t_proj = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    vqs = [port.project_onto_phonon(vc, eig_sub[i].reshape(6, 2, 3)) for i, vc in enumerate(vcs)]
+    t_ph = time.perf_counter() - t0
+    rng = np.random.default_rng(SEED)
+    series = rng.normal(size=(frames_total, n_series)) + 1j * rng.normal(size=(frames_total, n_series))
+    t0 = time.perf_counter()
+    port.fft_spectra(series, DT, FREQ)                                      # np.correlate + np.fft, as the reference
+    t_fft = time.perf_counter() - t0
+    t_sub = v_sub.shape[0]
+    scale_proj = (frames_total / t_sub) * (wl["Q"] / len(q_idx))
+    t_full = (t_proj + t_ph) * scale_proj + t_fft * (wl["Q"] * wl["M"] / n_series)
+    return {"t_proj_sample_s": t_proj, "t_phonon_sample_s": t_ph, "t_fft_sample_s": t_fft,
+            "t_full_extrapolated_s": t_full, "value": wl["n_atoms"] * frames_total / t_full, "_vq0": vqs[0]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = args.frames
+    wl = workload(frames)
+    rng = np.random.default_rng(SEED)
+    t_sub = args.cpu_frames
+    sigma = np.sqrt(KB * TEMP / wl["mass"])[None, :, None]
+    v_sub = rng.normal(size=(t_sub, wl["n_atoms"], 3)) * sigma
+    q_idx = [0, 1237, 2560, 5119][: args.cpu_q]
+    eig = np.stack([np.linalg.qr(rng.normal(size=(6, 6)) + 1j * rng.normal(size=(6, 6)))[0].T for _ in q_idx])
+    times = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = cpu_sample(wl, v_sub, eig, q_idx, args.cpu_series, frames)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    value = res["value"]
+    sample = (f"projection of {t_sub} frames x {wl['n_atoms']} atoms onto {len(q_idx)} q + contraction, "
+              f"FFT spectra (np.correlate + np.fft) of {args.cpu_series} series of {frames} samples; "
+              "scaled linearly to 131072 frames x 5120 q and 30720 series")
+    line = {"impl": "reference", "metric": "atom_frames_per_s", "value": value, "unit": "atom*frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(wl, frames, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "atom*frames/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample, "host_cores": os.cpu_count(),
+                             "note": "Python-level loops serial as in the reference (SURVEY 0.1), numpy/BLAS threads at default "
+                                     "(all cores); each step = the bounded sample, value extrapolated",
+                             "full_job_extrapolated_s": res["t_full_extrapolated_s"]},
+            "e2e": {"value": value, "unit": "atom*frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(wl, frames, gpus):
+    return {"workload": "cfg5-A synthetic 2-atom cubic cell, 16x16x20 supercell (10240 atoms), "
+                        f"{frames} frames, full commensurate q-mesh (5120 q x 6 modes), "
+                        "projection + eigenvector contraction + FFT power spectra (801 frequencies, "
+                        "7 windows of 20000)",
+            "atoms": wl["n_atoms"], "frames": frames, "q_points": wl["Q"], "modes_per_q": wl["M"],
+            "series": wl["Q"] * wl["M"], "frequencies": len(FREQ), "dt_ps": DT,
+            "sharding": f"time-block x{gpus}" + (" + all-to-all (NCCL)" if gpus > 1 else ""),
+            "l2_policy": "inputs (32 GB velocities, 64 GB projected series) far exceed the 126 MB L2"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from dynaphopy_b200 import ops as dops, pipeline
+    ops = dops.Ops()
+    frames = args.frames
+    assert frames % (world * CHUNK) == 0, "frames must be a multiple of ranks * 1024"
+    wl = workload(frames)
+    tl = frames // world
+    t_lo = rank * tl
+    plan = pipeline.CommensuratePlan(wl["cell"], DIMS, wl["pos"], wl["mass"], wl["typ"], wl["n_prim"], wl["q_cart"])
+    assert plan.usable() and plan.commensurate.all()
+    eig = random_unitary_eigenvectors(torch, dev, wl["Q"], wl["M"])
+    pipe = pipeline.MeshPipeline(plan, eig, FREQ, DT, ops=ops, algorithm=2)
+
+    # ---- device-resident inputs -------------------------------------------------------------------
+    v = torch.empty((tl, wl["n_atoms"], 3), dtype=torch.float64, device=dev)
+    for t0 in range(0, tl, CHUNK):
+        v[t0:t0 + CHUNK] = gen_chunk_torch(torch, dev, wl, t_lo + t0, t_lo + t0 + CHUNK)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stage_ms = {"project": [], "contract": [], "exchange": [], "spectra": []}
+
+    def step(record):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        vc = pipe.project(v)
+        ev[1].record()
+        send = pipe.contract(vc)
+        del vc
+        ev[2].record()
+        series = pipe.exchange(send)
+        ev[3].record()
+        ps = pipe.spectra(series)
+        ev[4].record()
+        if record:
+            torch.cuda.synchronize()
+            for i, k in enumerate(("project", "contract", "exchange", "spectra")):
+                stage_ms[k].append(ev[i].elapsed_time(ev[i + 1]))
+        return ps
+
+    for _ in range(args.warmup):
+        ps = step(False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    l0 = ops.launch_count()
+    w0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ps = step(True)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    launches = ops.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = wl["n_atoms"] * frames / (ms_per_step * 1e-3)
+    peak_bin = int(torch.argmax(ps[:, 0]).item())
+    checksum = float(ps.sum().item())
+
+    # ---- end to end through the host-facing call (pinned host trajectory) -----------------------------
+    e2e = None
+    if not args.skip_e2e:
+        del v
+        torch.cuda.empty_cache()
+        vh = torch.empty((tl, wl["n_atoms"], 3), dtype=torch.float64, pin_memory=True)
+        for t0 in range(0, tl, CHUNK):
+            vh[t0:t0 + CHUNK].copy_(gen_chunk_torch(torch, dev, wl, t_lo + t0, t_lo + t0 + CHUNK))
+        torch.cuda.synchronize()
+        pipe.run_from_host(vh, chunk_frames=2048)                        # warm-up
+        barrier()
+        es = max(1, min(args.steps, 2))
+        t0 = time.perf_counter()
+        for _ in range(es):
+            ps_host = pipe.run_from_host(vh, chunk_frames=2048)
+        barrier()
+        dt_e2e = (time.perf_counter() - t0) / es
+        if world > 1:
+            tt = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt_e2e = float(tt.item())
+        e2e = {"value": wl["n_atoms"] * frames / dt_e2e, "unit": "atom*frames/s", "ms_per_step": dt_e2e * 1e3,
+               "h2d_bytes_per_step": int(vh.numel() * 8 * world), "d2h_bytes_per_step": int(ps_host.size * 8 * world),
+               "api": "dynaphopy_b200.pipeline.MeshPipeline.run_from_host (pinned host trajectory in, numpy spectra out)",
+               "peak_bin_matches_device_run": bool(int(np.argmax(ps_host[:, 0])) == peak_bin)}
+        del vh
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    mean = {k: (statistics.mean(x) if x else 0.0) for k, x in stage_ms.items()}
+    # algorithmic bytes per launch on ONE rank
+    L, npieces = 20000, 7
+    s_loc = wl["Q"] * wl["M"] // world
+    bytes_stage = {"project": (24.0 * wl["n_atoms"] + 16.0 * wl["M"] * wl["Q"]) * tl,
+                   "contract": 2 * 16.0 * wl["M"] * wl["Q"] * tl,
+                   "spectra": (16.0 * L * npieces + 8.0 * len(FREQ)) * s_loc}
+    kernels = {"project": "project_fft_kernel", "contract": "project_phonon_kernel", "spectra": "spectrum_items_kernel"}
+    stages = {}
+    for k in ("project", "contract", "spectra"):
+        ach = bytes_stage[k] / (mean[k] * 1e-3) / 1e9 if mean[k] > 0 else 0.0
+        stages[k] = {"kernel": kernels[k], "ms": mean[k], "achieved_GBps": ach, "frac_of_hbm": ach / hbm}
+    stages["exchange"] = {"kernel": "nccl all_to_all_single" if world > 1 else "none", "ms": mean["exchange"]}
+    dom = max(("project", "contract", "spectra"), key=lambda k: mean[k])
+    roofline = {"kernel": kernels[dom], "bound": "hbm", "achieved": stages[dom]["achieved_GBps"], "peak": hbm,
+                "unit": "GB/s", "frac": stages[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                "share_of_step": mean[dom] / max(sum(mean.values()), 1e-9),
+                "note": "algorithmic bytes per launch / CUDA-event duration of the stage on rank 0; "
+                        "the FFT-spectrum kernel is fp64-FMA limited before it is HBM limited (DESIGN.md)"}
+    line = {"metric": "atom_frames_per_s", "value": value, "unit": "atom*frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(wl, frames, world),
+            "mode_spectra_per_s": wl["Q"] * wl["M"] / (ms_per_step * 1e-3),
+            "stages": stages, "roofline": roofline, "gpu_launches": int(launches),
+            "result_check": {"peak_bin_series0": peak_bin, "peak_freq_THz": float(FREQ[peak_bin]), "checksum": checksum}}
+    if e2e:
+        line["e2e"] = e2e
+    if sampler:
+        line["clocks"] = sampler.window(w0, w1)
+        sampler.stop()
+    if world == 1 and not args.skip_cpu:
+        from oracle import port  # noqa: F401  (cpu_baseline leg: the oracle as the CPU baseline)
+        vsub = gen_chunk_torch(torch, dev, wl, 0, CHUNK)[: args.cpu_frames].cpu().numpy()
+        q_idx = [0, 1237, 2560, 5119][: args.cpu_q]
+        eig_sub = eig[q_idx].cpu().numpy()
+        res = cpu_sample(wl, vsub, eig_sub, q_idx, args.cpu_series, frames)
+        line["cpu_baseline"] = {
+            "value": res["value"], "unit": "atom*frames/s", "cores": os.cpu_count(), "kind": "port", "host_cores": os.cpu_count(),
+            "sample": f"projection of {args.cpu_frames} frames x {wl['n_atoms']} atoms onto {len(q_idx)} q "
+                      f"({res['t_proj_sample_s']:.2f} s) + contraction ({res['t_phonon_sample_s']:.3f} s) + FFT spectra of "
+                      f"{args.cpu_series} series of {frames} samples ({res['t_fft_sample_s']:.2f} s); scaled linearly "
+                      "to the full job (extrapolated)",
+            "full_job_extrapolated_s": res["t_full_extrapolated_s"],
+            "note": "oracle port = the reference's numpy projection / np.correlate+np.fft spectrum; Python-level loops are serial as in the reference, numpy/BLAS threading left at its default (all cores)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=131072, help="total frames (default: the full 2^17 workload)")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=1024)  # <= 1024 (one generator chunk)
+    ap.add_argument("--cpu-q", type=int, default=4)
+    ap.add_argument("--cpu-series", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,7 @@ SIGNATURES = {
     "dp_version": (_c.c_char_p, []),
     "dp_last_error": (_c.c_char_p, []),
     "dp_sm_count": (_I, []),
+    "dp_launch_count": (_c.c_longlong, []),
     "dp_atomic_displacements": (_I, [_P, _I, _P, _P, _L, _I, _P, _P]),
     "dp_velocity_from_positions": (_I, [_P, _I, _P, _P, _P, _L, _I, _D, _P, _P, _P, _P, _P]),
     "dp_mass_weight": (_I, [_P, _I, _P, _L, _I, _P, _P]),
@@ -27,6 +28,7 @@ SIGNATURES = {
     "dp_project_commensurate_workspace_bytes": (_Z, [_P, _I, _I, _I]),
     "dp_project_commensurate": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _I, _I, _P, _P, _Z, _P]),
     "dp_project_phonon": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    "dp_project_phonon_blocked": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
     "dp_power_fft_workspace_bytes": (_Z, [_L, _I, _D, _P, _I]),
     "dp_power_fft": (_I, [_P, _L, _I, _L, _D, _P, _I, _D, _P, _P, _Z, _P]),
     "dp_power_fft_pieces": (_I, [_L, _D, _P, _I, _P, _P, _P, _I]),

@@ -38,13 +38,18 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 // ---- launch / dynamic shared memory, identical source for nvcc and the test emulator ---
+// every kernel launch of the library is counted (dp_launch_count), so benchmarks can report how
+// many of OUR kernels ran inside a timed region
+void count_launch();
+
 #ifdef DP_EMUL
 #define DP_LAUNCH(kfn, grid, block, smem, stream, ...) \
-    dp_emul::launch((grid), (block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); })
+    (dp::count_launch(), dp_emul::launch((grid), (block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); }))
 #define DP_DYNSMEM(type, name) type* name = reinterpret_cast<type*>(dp_emul::tls_worker()->dyn_smem)
 #define DP_SET_SMEM(kfn, bytes) cudaSuccess
 #else
-#define DP_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DP_LAUNCH(kfn, grid, block, smem, stream, ...) \
+    (dp::count_launch(), kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define DP_DYNSMEM(type, name)                                   \
     extern __shared__ __align__(16) unsigned char name##_raw_[]; \
     type* name = reinterpret_cast<type*>(name##_raw_)

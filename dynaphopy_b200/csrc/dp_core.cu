@@ -1,9 +1,12 @@
 // Error plumbing and device queries of the dynaphopy_b200 C ABI.
+#include <atomic>
 #include <cstdarg>
 
 #include "dp_common.cuh"
 
 namespace dp {
+
+long long launches();
 
 static thread_local char g_err[512] = "";
 
@@ -18,6 +21,10 @@ int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return DP_ERR_CUDA;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
 #ifdef DP_EMUL
@@ -40,6 +47,8 @@ extern "C" {
 const char* dp_version(void) { return "dynaphopy_b200 0.1.0 (sm_100a)"; }
 
 const char* dp_last_error(void) { return dp::g_err; }
+
+long long dp_launch_count(void) { return dp::launches(); }
 
 int dp_sm_count(void) {
     int n = dp::sm_count();

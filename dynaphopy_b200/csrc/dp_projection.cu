@@ -103,8 +103,8 @@ project_dense_kernel(const double* __restrict__ v, const cplx* __restrict__ ph,
 constexpr int PH_TF = 64;
 
 __global__ void __launch_bounds__(256)
-project_phonon_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig, int64_t T, int Q, int M,
-                      cplx* __restrict__ vq) {
+project_phonon_kernel(const cplx* vc, const cplx* __restrict__ eig, int64_t T, int Q, int M, int q_block,
+                      cplx* vq) {
     DP_DYNSMEM(cplx, sm);
     cplx* es = sm;                      // [M][M]   e[q][s][j]
     cplx* vs = sm + (size_t)M * M;      // [PH_TF][M]
@@ -133,7 +133,8 @@ project_phonon_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig,
             }
             acc = cadd(acc, part);
         }
-        vq[((t0 + f) * Q + q) * M + s] = acc;
+        // [q / q_block][t][q % q_block][s]; q_block == Q gives the plain [t][q][s] layout
+        vq[(((int64_t)(q / q_block) * T + t0 + f) * q_block + (q % q_block)) * M + s] = acc;
     }
 }
 
@@ -212,7 +213,14 @@ int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt
 }
 
 int dp_project_phonon(const double* vc, const double* eig, int64_t T, int Q, int M, double* vq, void* stream) {
+    return dp_project_phonon_blocked(vc, eig, T, Q, M, Q, vq, stream);
+}
+
+int dp_project_phonon_blocked(const double* vc, const double* eig, int64_t T, int Q, int M, int q_block,
+                              double* vq, void* stream) {
     DP_REQUIRE((T == 0 || (vc && vq)) && eig, DP_ERR_INVALID, "dp_project_phonon: null pointer");
+    DP_REQUIRE(q_block > 0 && Q % q_block == 0, DP_ERR_INVALID, "dp_project_phonon: q_block=%d must divide Q=%d", q_block, Q);
+    DP_REQUIRE(vc != vq || q_block == Q, DP_ERR_INVALID, "dp_project_phonon: in-place needs q_block == Q");
     DP_REQUIRE(T >= 0 && Q > 0 && M > 0 && M % 3 == 0, DP_ERR_INVALID, "dp_project_phonon: bad sizes (M must be 3*n_prim)");
     DP_REQUIRE(Q <= 65535, DP_ERR_UNSUPPORTED, "dp_project_phonon: Q=%d too large for one launch", Q);
     if (T == 0) return DP_OK;
@@ -222,7 +230,7 @@ int dp_project_phonon(const double* vc, const double* eig, int64_t T, int Q, int
     DP_CUDA_OK(DP_SET_SMEM(k, smem));
     dim3 grid((unsigned)((T + dp::PH_TF - 1) / dp::PH_TF), (unsigned)Q);
     DP_LAUNCH(k, grid, dim3(256), smem, (cudaStream_t)stream, (const dp::cplx*)vc, (const dp::cplx*)eig, T, Q, M,
-              (dp::cplx*)vq);
+              q_block, (dp::cplx*)vq);
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
 }

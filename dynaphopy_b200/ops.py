@@ -126,8 +126,9 @@ class Ops:
                       int(n_prim), T, _hptr(q), Q, int(project_on_atom), be.ptr(out), be.ptr(ws), nbytes, be.stream())
         return out
 
-    def project_commensurate(self, velocity, dims, unit_type, n_prim, qbin, twiddle, project_on_atom=-1):
-        """3-D DFT projection: real (T,N,3) -> (T,Q,n_prim,3) complex128 for commensurate q."""
+    def project_commensurate(self, velocity, dims, unit_type, n_prim, qbin, twiddle, project_on_atom=-1, out=None):
+        """3-D DFT projection: real (T,N,3) -> (T,Q,n_prim,3) complex128 for commensurate q.
+        ``out``: optional preallocated contiguous (T,Q,n_prim,3) destination (e.g. a time slice)."""
         be = self.be
         v = be.asarray(velocity, np.float64)
         T, N, _ = be.shape(v)
@@ -140,22 +141,35 @@ class Ops:
         tw = be.asarray(twiddle, np.complex128)
         nbytes = self.lib.size("dp_project_commensurate_workspace_bytes", _hptr(dims_h), n_unit, int(n_prim), Q)
         ws = be.empty((nbytes,), np.uint8)
-        out = be.empty((T, Q, n_prim, 3), np.complex128)
+        if out is None:
+            out = be.empty((T, Q, n_prim, 3), np.complex128)
+        else:
+            assert be.shape(out) == (T, Q, int(n_prim), 3) and out.is_contiguous(), "bad `out` buffer"
         self.lib.call("dp_project_commensurate", be.ptr(v), _hptr(dims_h), n_unit, _hptr(ut), int(n_prim), T,
                       be.ptr(qb), be.ptr(tw), Q, int(project_on_atom), be.ptr(out), be.ptr(ws), nbytes, be.stream())
         return out
 
-    def project_phonon(self, vc, eigenvectors):
-        """vc (T,Q,n_p,3) or (T,Q,M); eigenvectors (Q,M,n_p,3) or (Q,M,M) -> vq (T,Q,M)."""
+    def project_phonon(self, vc, eigenvectors, q_block=None, out=None, inplace=False):
+        """vc (T,Q,n_p,3) or (T,Q,M); eigenvectors (Q,M,n_p,3) or (Q,M,M) -> vq (T,Q,M).
+
+        ``q_block``: write ``(Q/q_block, T, q_block, M)`` instead (all-to-all send layout);
+        ``inplace``: overwrite ``vc`` (plain layout only)."""
         be = self.be
         vc = be.asarray(vc, np.complex128)
         T, Q = be.shape(vc)[:2]
         M = int(np.prod(be.shape(vc)[2:]))
         e = be.asarray(eigenvectors, np.complex128)
         assert be.shape(e)[0] == Q and int(np.prod(be.shape(e)[1:])) == M * M, "eigenvector shape mismatch"
-        out = be.empty((T, Q, M), np.complex128)
-        self.lib.call("dp_project_phonon", be.ptr(vc), be.ptr(e), T, Q, M, be.ptr(out), be.stream())
-        return out
+        qb = Q if q_block is None else int(q_block)
+        if inplace:
+            out = vc
+        elif out is None:
+            out = be.empty((T, Q, M) if qb == Q else (Q // qb, T, qb, M), np.complex128)
+        self.lib.call("dp_project_phonon_blocked", be.ptr(vc), be.ptr(e), T, Q, M, qb, be.ptr(out), be.stream())
+        return out.reshape(T, Q, M) if (inplace and qb == Q) else out
+
+    def launch_count(self):
+        return int(self.lib.cdll.dp_launch_count())
 
     # ------------------------------------------------------------------ A7 / A6 / A5
     def _series(self, series):

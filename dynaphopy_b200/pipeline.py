@@ -1,0 +1,201 @@
+"""Batched normal-mode decomposition of a whole commensurate q-mesh (the callers' side of the
+hot path: what ``Quasiparticle.get_commensurate_points_data`` does one q at a time,
+dynaphopy/__init__.py:1130-1174, done here for all q in one pass).
+
+    velocities (T, N, 3)  --A1+A2-->  vc (T, Q, n_p, 3)  --A3-->  vq (T, Q*M)  --A4..A7-->  (F, Q*M)
+
+Multi-GPU: frames are sharded by contiguous time blocks -- projection and
+contraction are independent per frame -- then ONE all-to-all over NCCL/NVLink turns the
+time-sharded ``vq`` into series-sharded, time-major matrices and every rank computes the spectra
+of its own Q/G wave vectors.  The contraction kernel writes the send layout directly
+(``dp_project_phonon_blocked``), and the received blocks concatenate into the (T, S/G) matrix the
+spectrum kernels consume, so there is no pack or unpack pass.
+"""
+import numpy as np
+
+from . import ops as _ops
+
+
+class CommensuratePlan:
+    """Host-side description of a q list on a diagonal supercell: DFT bins + per-unit-atom twiddles.
+
+    positions follow dynaphopy/atoms.py:139-156 (i = u*Nc + x + Nx*(y + Ny*z)); a q is commensurate
+    when q.a_j * dims_j / 2pi is an integer for the three unit-cell vectors a_j."""
+
+    def __init__(self, unit_cell, dims, positions, masses, atom_type, n_prim, q_cart, tol=5e-13):
+        unit_cell = np.asarray(unit_cell, float)
+        self.dims = np.asarray(dims, dtype=np.int32)
+        self.nc = int(np.prod(self.dims))
+        positions = np.asarray(positions, float)
+        n = positions.shape[0]
+        if n % self.nc:
+            raise ValueError("atom count is not a multiple of the number of cells")
+        self.n_unit = n // self.nc
+        self.n_prim = int(n_prim)
+        self.unit_type = np.asarray(atom_type)[:: self.nc].astype(np.int32)
+        self.unit_mass = np.asarray(masses, float)[:: self.nc]
+        tau = positions[:: self.nc]
+        # the sites must be tau_u + R_cell in reference order, otherwise the DFT form does not apply
+        grid = np.array([[x, y, z] for z in range(self.dims[2]) for y in range(self.dims[1])
+                         for x in range(self.dims[0])], dtype=float) @ unit_cell
+        expect = (tau[:, None, :] + grid[None, :, :]).reshape(-1, 3)
+        self.lattice_ok = bool(np.allclose(expect, positions, rtol=0, atol=1e-8 * max(1.0, np.abs(unit_cell).max())))
+        self.lattice_ok = self.lattice_ok and bool(np.all(np.asarray(atom_type).reshape(self.n_unit, self.nc)
+                                                          == self.unit_type[:, None]))
+        q_cart = np.atleast_2d(np.asarray(q_cart, float))
+        m = q_cart @ unit_cell.T / (2.0 * np.pi) * self.dims
+        mr = np.round(m)
+        self.commensurate = np.abs(m - mr).max(axis=1) <= tol * np.maximum(1.0, np.abs(m).max(axis=1))
+        self.qbin = np.mod(mr.astype(np.int64), self.dims).astype(np.int32)
+        norm = 1.0 / np.sqrt(n / self.n_prim)
+        self.twiddle = norm * np.sqrt(self.unit_mass)[None, :] * np.exp(-1j * (q_cart @ tau.T))
+        self.twiddle_unweighted = norm * np.exp(-1j * (q_cart @ tau.T))
+        self.q_cart = q_cart
+
+    def usable(self):
+        return self.lattice_ok and bool(np.all(self.dims <= 32)) and self.nc * 17 // 16 * 16 <= 220 * 1024
+
+
+def project_q_list(ops, velocity, sqrt_mass, plan, positions, atom_type, project_on_atom=-1, method="auto",
+                   mass_weighted=False):
+    """vc (T, Q, n_prim, 3) for a list of Cartesian q; picks the 3-D DFT kernel for the commensurate
+    q when it pays (many q on a large supercell) and the dense kernel otherwise."""
+    be = ops.be
+    q_cart = plan.q_cart
+    nq = q_cart.shape[0]
+    comm = plan.commensurate if (plan.usable() and not be.is_complex(velocity)) else np.zeros(nq, dtype=bool)
+    use_fft = method == "fft" or (method == "auto" and comm.sum() >= 8 and plan.nc >= 64)
+    if method == "dense" or not use_fft:
+        comm = np.zeros(nq, dtype=bool)
+    sm = None if mass_weighted else sqrt_mass
+    if comm.all():
+        tw = plan.twiddle_unweighted if mass_weighted else plan.twiddle
+        return ops.project_commensurate(velocity, plan.dims, plan.unit_type, plan.n_prim, plan.qbin, tw, project_on_atom)
+    if not comm.any():
+        return ops.project_wave_vector(velocity, sm, positions, atom_type, plan.n_prim, q_cart, project_on_atom)
+    tw = (plan.twiddle_unweighted if mass_weighted else plan.twiddle)[comm]
+    a = ops.project_commensurate(velocity, plan.dims, plan.unit_type, plan.n_prim, plan.qbin[comm], tw, project_on_atom)
+    b = ops.project_wave_vector(velocity, sm, positions, atom_type, plan.n_prim, q_cart[~comm], project_on_atom)
+    out = be.empty((be.shape(a)[0], nq, plan.n_prim, 3), np.complex128)
+    out[:, np.nonzero(comm)[0]] = a
+    out[:, np.nonzero(~comm)[0]] = b
+    return out
+
+
+class MeshPipeline:
+    """All q of a mesh at once, optionally time-sharded over the ranks of a torch.distributed group."""
+
+    def __init__(self, plan, eigenvectors, frequency_range, dt, ops=None, group=None, algorithm=2,
+                 mem_coefficients=1000, correlation_step=10, integration_method=1, correlation_weight=0):
+        self.ops = ops if ops is not None else _ops.default_ops()
+        self.plan = plan
+        self.be = self.ops.be
+        self.freq = np.asarray(frequency_range, dtype=float)
+        self.dt = float(dt)
+        self.algorithm = algorithm
+        self.mem_coefficients = mem_coefficients
+        self.correlation_step = correlation_step
+        self.integration_method = integration_method
+        self.correlation_weight = correlation_weight
+        self.Q = plan.q_cart.shape[0]
+        self.M = 3 * plan.n_prim
+        self.group = group
+        self.world, self.rank = 1, 0
+        if group is not None or _dist_ready():
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+        if self.Q % self.world:
+            raise ValueError("number of q points must be divisible by the number of ranks")
+        self.q_block = self.Q // self.world
+        self.d_qbin = self.be.asarray(plan.qbin, np.int32)
+        self.d_tw = self.be.asarray(plan.twiddle, np.complex128)
+        self.d_eig = self.be.asarray(eigenvectors, np.complex128).reshape(self.Q, self.M, self.M)
+
+    # -- stages -----------------------------------------------------------------------------------
+    def project(self, velocity):
+        """Local frames (Tl, N, 3) real -> vc (Tl, Q, n_p, 3)."""
+        return self.ops.project_commensurate(velocity, self.plan.dims, self.plan.unit_type, self.plan.n_prim,
+                                             self.d_qbin, self.d_tw)
+
+    def contract(self, vc):
+        """vc -> vq; single rank: in place, (Tl, Q*M) time-major.  Multi rank: send layout
+        (G, Tl, Q/G, M)."""
+        if self.world == 1:
+            vq = self.ops.project_phonon(vc, self.d_eig, inplace=True)
+            return vq.reshape(self.be.shape(vq)[0], self.Q * self.M)
+        return self.ops.project_phonon(vc, self.d_eig, q_block=self.q_block)
+
+    def exchange(self, send):
+        """The one all-to-all: (G, Tl, Q/G, M) on every rank -> (G*Tl, (Q/G)*M) time-major."""
+        if self.world == 1:
+            return send
+        import torch
+        import torch.distributed as dist
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
+        g, tl = send.shape[0], send.shape[1]
+        return recv.reshape(g * tl, self.q_block * self.M)
+
+    def spectra(self, series):
+        """(T, S) time-major series -> (F, S) power spectra with the selected algorithm."""
+        a = self.algorithm
+        if a in (2, 3, 4, 5):
+            return self.ops.power_fft(series, self.dt, self.freq)
+        if a == 1:
+            return self.ops.power_mem(series, self.dt, self.freq, self.mem_coefficients)
+        if a == 0:
+            return self.ops.power_correlation(series, self.dt, self.freq, self.correlation_step,
+                                              self.integration_method, self.correlation_weight)
+        raise ValueError("Power spectrum algorithm number not found")
+
+    def run(self, velocity_local):
+        """Whole step on device-resident local frames; returns the (F, S_local) spectra of this rank."""
+        vc = self.project(velocity_local)
+        send = self.contract(vc)
+        del vc
+        series = self.exchange(send)
+        return self.spectra(series)
+
+    # -- host-resident trajectory: chunked H2D copies overlapped with the projection ------------------
+    def run_from_host(self, velocity_host, chunk_frames=2048):
+        """velocity_host: pinned (Tl, N, 3) float64 torch tensor on the host.  Frames are copied in
+        chunks on a side stream into a two-slot staging buffer while the previous chunk is being
+        projected; the spectra come back to the host as numpy."""
+        import torch
+        be = self.be
+        tl = velocity_host.shape[0]
+        n = velocity_host.shape[1]
+        out = be.empty((tl, self.Q, self.plan.n_prim, 3), np.complex128)
+        stage = [be.empty((min(chunk_frames, tl), n, 3), np.float64) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=be.device)
+        main = torch.cuda.current_stream(be.device)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        starts = list(range(0, tl, chunk_frames))
+        for i, t0 in enumerate(starts):
+            slot = i % 2
+            t1 = min(t0 + chunk_frames, tl)
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(freed[slot])
+                stage[slot][: t1 - t0].copy_(velocity_host[t0:t1], non_blocking=True)
+                ready[slot].record(copy_stream)
+            main.wait_event(ready[slot])
+            self.ops.project_commensurate(stage[slot][: t1 - t0], self.plan.dims, self.plan.unit_type,
+                                          self.plan.n_prim, self.d_qbin, self.d_tw, out=out[t0:t1])
+            freed[slot].record(main)
+        del stage
+        send = self.contract(out)
+        del out
+        series = self.exchange(send)
+        ps = self.spectra(series)
+        return ps.cpu().numpy()
+
+
+def _dist_ready():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+    except Exception:
+        return False

@@ -44,6 +44,8 @@ const char* dp_version(void);
 const char* dp_last_error(void);
 /* Number of SMs of the current device (host query), or a negative error. */
 int dp_sm_count(void);
+/* Number of kernels this library has launched in this process so far (monotonic counter). */
+long long dp_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * A8  minimum-image displacements.
@@ -133,6 +135,14 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
  * ------------------------------------------------------------------------------------ */
 int dp_project_phonon(const double* vc, const double* eig, int64_t T, int Q, int M, double* vq,
                       void* stream);
+/* Same contraction, output grouped by blocks of q_block wave vectors:
+ *   vq[(q / q_block)][t][q % q_block][s]   (q_block must divide Q; q_block == Q is the layout above).
+ * This is the send layout of the time-sharded -> series-sharded all-to-all: block g is the
+ * contiguous message for rank g, and concatenating the received blocks in rank order yields a
+ * time-major (T_total, q_block*M) series matrix on every rank.
+ * vq may alias vc when q_block == Q. */
+int dp_project_phonon_blocked(const double* vc, const double* eig, int64_t T, int Q, int M, int q_block,
+                              double* vq, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * A7  power spectrum, FFT method (selector keys 2 and 3).

@@ -1,0 +1,150 @@
+"""Whole-mesh pipeline (projection -> contraction -> [all-to-all] -> spectra) against the oracle,
+including the time-sharded multi-rank path: 2 gloo ranks on CPU drive the emulated kernels and the
+real torch.distributed all-to-all; on the GPU box the single-rank CUDA path is checked too."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import relerr, to_np
+from oracle import port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_case(nt=64, dims=(4, 2, 3), seed=5):
+    from dynaphopy_b200 import pipeline
+    rng = np.random.default_rng(seed)
+    cell = np.diag([4.0, 4.1, 3.9])
+    dims = np.array(dims)
+    nc = int(np.prod(dims))
+    unit_pos = np.array([[0, 0, 0], [0.5, 0.5, 0.5]]) @ cell
+    pos = port.supercell_positions(unit_pos, cell, dims)
+    typ = port.supercell_replicate([0, 1], dims).astype(np.int32)
+    mass = port.supercell_replicate([28.0855, 69.723], dims)
+    m = np.array([[x, y, z] for z in range(dims[2]) for y in range(dims[1]) for x in range(dims[0])])
+    q_cart = 2 * np.pi * (m / dims) @ np.linalg.inv(cell).T
+    t = np.arange(nt) * 0.002
+    v = rng.normal(size=(nt, 2 * nc, 3)) + 2.0 * np.cos(2 * np.pi * 7.3 * t)[:, None, None]
+    eig = np.stack([np.linalg.qr(rng.normal(size=(6, 6)) + 1j * rng.normal(size=(6, 6)))[0].T for _ in m])
+    freq = np.arange(0, 40.05, 2.0)
+    plan = pipeline.CommensuratePlan(cell, dims, pos, mass, typ, 2, q_cart)
+    vm = port.velocity_mass_average(v, mass)
+    ref_vq = np.stack([port.project_onto_phonon(port.project_onto_wave_vector(vm, pos, typ, 2, q), eig[i].reshape(6, 2, 3))
+                       for i, q in enumerate(q_cart)], axis=1)                        # (T, Q, M)
+    ref_ps = port.fft_spectra(ref_vq.reshape(nt, -1), 0.002, freq)
+    return dict(plan=plan, v=v, eig=eig, freq=freq, ref_vq=ref_vq, ref_ps=ref_ps, dt=0.002)
+
+
+def test_plan_classifies_q():
+    c = make_case()
+    assert c["plan"].usable() and c["plan"].commensurate.all()
+    from dynaphopy_b200 import pipeline
+    p = c["plan"]
+    q2 = np.vstack([p.q_cart[:3], p.q_cart[3] * 1.0001])
+    cell = np.diag([4.0, 4.1, 3.9])
+    pos = port.supercell_positions(np.array([[0, 0, 0], [0.5, 0.5, 0.5]]) @ cell, cell, p.dims)
+    plan2 = pipeline.CommensuratePlan(cell, p.dims, pos, np.ones(len(pos)), np.repeat([0, 1], p.nc), 2, q2)
+    assert list(plan2.commensurate) == [True, True, True, False]
+    # shuffled sites are not a lattice in reference order -> DFT form refused
+    plan3 = pipeline.CommensuratePlan(cell, p.dims, pos[::-1], np.ones(len(pos)), np.repeat([0, 1], p.nc), 2, q2)
+    assert not plan3.usable()
+
+
+def test_mesh_pipeline_single_rank(kops):
+    from dynaphopy_b200 import pipeline
+    c = make_case()
+    pipe = pipeline.MeshPipeline(c["plan"], c["eig"], c["freq"], c["dt"], ops=kops, algorithm=2)
+    vc = pipe.project(c["v"])
+    vq = pipe.contract(vc)
+    assert relerr(to_np(vq).reshape(c["ref_vq"].shape), c["ref_vq"]) < 1e-10
+    ps = to_np(pipe.run(c["v"]))
+    assert relerr(ps, c["ref_ps"]) < 1e-10
+    assert np.array_equal(ps.argmax(0), c["ref_ps"].argmax(0))
+    for alg, ref in ((1, port.mem_spectra(c["ref_vq"].reshape(64, -1)[:, :6], c["dt"], c["freq"], 10)),):
+        pipe1 = pipeline.MeshPipeline(c["plan"], c["eig"], c["freq"], c["dt"], ops=kops, algorithm=alg, mem_coefficients=10)
+        assert relerr(to_np(pipe1.spectra(to_np(vq)[:, :6])), ref) < 1e-10
+
+
+def test_project_q_list_mixed(kops):
+    """Commensurate and non-commensurate q in one list: DFT kernel + dense kernel, stitched."""
+    from dynaphopy_b200 import pipeline
+    c = make_case(nt=9, dims=(4, 4, 4))
+    p = c["plan"]
+    cell = np.diag([4.0, 4.1, 3.9])
+    pos = port.supercell_positions(np.array([[0, 0, 0], [0.5, 0.5, 0.5]]) @ cell, cell, p.dims)
+    typ = np.repeat([0, 1], p.nc).astype(np.int32)
+    mass = np.repeat([28.0855, 69.723], p.nc)
+    q = np.vstack([p.q_cart[:10], [[0.1, 0.2, 0.3]], p.q_cart[10:12]])
+    plan = pipeline.CommensuratePlan(cell, p.dims, pos, mass, typ, 2, q)
+    assert plan.commensurate.sum() == 12
+    v = c["v"]
+    vc = to_np(pipeline.project_q_list(kops, v, np.sqrt(mass), plan, pos, typ))
+    vm = port.velocity_mass_average(v, mass)
+    ref = np.stack([port.project_onto_wave_vector(vm, pos, typ, 2, qq) for qq in q], axis=1)
+    assert relerr(vc, ref) < 1e-10
+    for method in ("dense", "fft"):
+        plan_c = pipeline.CommensuratePlan(cell, p.dims, pos, mass, typ, 2, p.q_cart[:12])
+        out = to_np(pipeline.project_q_list(kops, v, np.sqrt(mass), plan_c, pos, typ, method=method))
+        assert relerr(out, ref[:, [*range(10), 11, 12]]) < 1e-10
+
+
+def _rank_main(rank, world, port_no, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["DP_EMUL_THREADS"] = "2"
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
+    from emul import emul_ops
+    from dynaphopy_b200 import pipeline
+    c = make_case()
+    pipe = pipeline.MeshPipeline(c["plan"], c["eig"], c["freq"], c["dt"], ops=emul_ops(), algorithm=2)
+    assert pipe.world == world and pipe.q_block == 24 // world
+    nt = c["v"].shape[0]
+    tl = nt // world
+    v_local = c["v"][rank * tl:(rank + 1) * tl]
+    send = pipe.contract(pipe.project(v_local))                       # numpy (G, Tl, Q/G, M)
+    series = pipe.exchange(torch.from_numpy(np.ascontiguousarray(send))).numpy()
+    ps = pipe.spectra(series)
+    np.save(os.path.join(out_dir, f"ps{rank}.npy"), ps)
+    np.save(os.path.join(out_dir, f"series{rank}.npy"), series)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_time_sharded_all_to_all_gloo(tmp_path, world):
+    """N ranks, time-sharded projection, one all-to-all, series-sharded spectra == oracle."""
+    import torch.multiprocessing as mp
+    port_no = 29600 + os.getpid() % 300 + world
+    mp.spawn(_rank_main, args=(world, port_no, str(tmp_path)), nprocs=world, join=True)
+    c = make_case()
+    nt = c["ref_vq"].shape[0]
+    qb = 24 // world
+    for r in range(world):
+        series = np.load(tmp_path / f"series{r}.npy")
+        ref_series = c["ref_vq"][:, r * qb:(r + 1) * qb].reshape(nt, -1)
+        assert relerr(series, ref_series) < 1e-10
+        ps = np.load(tmp_path / f"ps{r}.npy")
+        assert relerr(ps, c["ref_ps"][:, r * qb * 6:(r + 1) * qb * 6]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_run_from_host_streams(cuda_ops):
+    """Pinned-host trajectory, chunked H2D overlapped with projection == device-resident run."""
+    import torch
+    from dynaphopy_b200 import pipeline
+    c = make_case(nt=96)
+    pipe = pipeline.MeshPipeline(c["plan"], c["eig"], c["freq"], c["dt"], ops=cuda_ops, algorithm=2)
+    vh = torch.from_numpy(c["v"]).pin_memory()
+    ps = pipe.run_from_host(vh, chunk_frames=20)
+    ref = port.fft_spectra(np.stack([port.project_onto_phonon(
+        port.project_onto_wave_vector(port.velocity_mass_average(c["v"], np.repeat([28.0855, 69.723], 24)),
+                                      port.supercell_positions(np.array([[0, 0, 0], [0.5, 0.5, 0.5]]) @ np.diag([4.0, 4.1, 3.9]),
+                                                               np.diag([4.0, 4.1, 3.9]), c["plan"].dims),
+                                      np.repeat([0, 1], 24), 2, q), c["eig"][i].reshape(6, 2, 3))
+        for i, q in enumerate(c["plan"].q_cart)], axis=1).reshape(96, -1), c["dt"], c["freq"])
+    assert relerr(ps, ref) < 1e-10
+    assert relerr(ps, to_np(pipe.run(c["v"]))) < 1e-13
