@@ -16,86 +16,17 @@
 // primes) whose twiddles are immediate constants.  Persistent grid, one CTA per work unit,
 // sized as a multiple of the SM count.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "dp_common.cuh"
 #include "dp_fft.cuh"
 
-#ifdef DP_EMUL
-#define DP_ROOTS_QUALIFIER static const
-#else
-#define DP_ROOTS_QUALIFIER static __device__ __constant__
-#endif
-#include "dp_roots.h"
+#include "dp_pencil.cuh"
 
 namespace dp {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-// ---------------- compile-time pencil DFT codelets ---------------------------------------------
-__host__ __device__ constexpr int pencil_radix(int n) {
-    if (n % 4 == 0) return 4;
-    for (int f = 2; f <= n; f++)
-        if (n % f == 0) return f;
-    return n;
-}
-
-__device__ __forceinline__ cplx root_const(int n, int j) {      // exp(-2 pi i j / n), forward
-    const int idx = n * (n - 1) / 2 + (j % n);
-    return make_double2(dp_roots_re[idx], dp_roots_im[idx]);
-}
-
-template <int R> __device__ __forceinline__ void pencil_bfly(cplx* t) {
-    if constexpr (R == 1) return;
-    else if constexpr (R == 2) bfly2<-1>(t);
-    else if constexpr (R == 3) bfly3<-1>(t);
-    else if constexpr (R == 4) bfly4<-1>(t);
-    else if constexpr (R == 5) bfly5<-1>(t);
-    else {                               // generic odd prime: O(R^2) with constant roots
-        cplx o[R];
-#pragma unroll
-        for (int u = 0; u < R; u++) {
-            cplx acc = t[0];
-#pragma unroll
-            for (int r = 1; r < R; r++) acc = cadd(acc, cmul(t[r], root_const(R, (r * u) % R)));
-            o[u] = acc;
-        }
-#pragma unroll
-        for (int u = 0; u < R; u++) t[u] = o[u];
-    }
-}
-
-// forward DFT of N points held in registers, natural order in and out (decimation in time):
-//   out[k + M u] = sum_r w_R^(r u) [ w_N^(r k) DFT_M(in[m R + r])[k] ]
-template <int N> struct PencilDft {
-    static constexpr int R = pencil_radix(N);
-    static constexpr int M = N / R;
-    __device__ __forceinline__ static void run(const cplx* in, cplx* out) {
-        cplx sub[R][M];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            cplx g[M];
-#pragma unroll
-            for (int mm = 0; mm < M; mm++) g[mm] = in[mm * R + r];
-            PencilDft<M>::run(g, sub[r]);
-        }
-#pragma unroll
-        for (int k = 0; k < M; k++) {
-            cplx t[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (r == 0 || k == 0) t[r] = sub[r][k];
-                else t[r] = cmul(sub[r][k], root_const(N, r * k));
-            }
-            pencil_bfly<R>(t);
-#pragma unroll
-            for (int u = 0; u < R; u++) out[k + M * u] = t[u];
-        }
-    }
-};
-template <> struct PencilDft<1> {
-    __device__ __forceinline__ static void run(const cplx* in, cplx* out) { out[0] = in[0]; }
-};
 
 // pencil pc: base = (pc % A)*sa + (pc / A)*sb, elements at base + i*st
 template <int N>
@@ -152,29 +83,42 @@ qoffset_kernel(const int* __restrict__ qbin, int Q, int Nx, int Ny, int Nz, int 
     }
 }
 
-__global__ void __launch_bounds__(512)
+// MAXT / MINB: launch bounds (register budget): <=320 threads with 2 CTAs per SM, or <=512 with 1
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 project_fft_kernel(PfParams p) {
     DP_DYNSMEM(cplx, W);
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz, Px = p.Px, Nc = p.Nc;
+    const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz, Px = p.Px, Nc = p.Nc, Q = p.Q, n_unit = p.n_unit;
+    const int2* __restrict__ qoff = p.qoff;
+    const cplx* __restrict__ tw = p.tw;
     const int64_t nunits = p.T * p.njobs;
     for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
         const int64_t t = unit / p.njobs;
         const PfJob job = p.jobs[(int)(unit % p.njobs)];
-        const double* vt = p.v + t * (int64_t)p.N * 3;
-        cplx* outA = p.out + ((t * p.Q) * p.n_prim + job.pA) * 3 + job.kA;
-        cplx* outB = job.pB >= 0 ? p.out + ((t * p.Q) * p.n_prim + job.pB) * 3 + job.kB : nullptr;
+        const double* __restrict__ vt = p.v + t * (int64_t)p.N * 3;
+        cplx* __restrict__ outA = p.out + ((t * Q) * p.n_prim + job.pA) * 3 + job.kA;
+        cplx* __restrict__ outB = job.pB >= 0 ? p.out + ((t * Q) * p.n_prim + job.pB) * 3 + job.kB : nullptr;
         const int64_t qstride = (int64_t)p.n_prim * 3;
         for (int term = 0; term < job.nterms; term++) {
             const PfTerm tm = p.terms[job.term0 + term];
-            const double* srcA = tm.uA >= 0 ? vt + (int64_t)tm.uA * Nc * 3 + job.kA : nullptr;
-            const double* srcB = (tm.uB >= 0 && job.pB >= 0) ? vt + (int64_t)tm.uB * Nc * 3 + job.kB : nullptr;
+            const double* __restrict__ srcA = tm.uA >= 0 ? vt + (int64_t)tm.uA * Nc * 3 + job.kA : nullptr;
+            const double* __restrict__ srcB = (tm.uB >= 0 && job.pB >= 0) ? vt + (int64_t)tm.uB * Nc * 3 + job.kB : nullptr;
             __syncthreads();
-            for (int c = tid; c < Nc; c += nthreads) {
-                const int x = c % Nx, yz = c / Nx;
-                double a = srcA ? __ldg(srcA + (int64_t)c * 3) : 0.0;
-                double b = srcB ? __ldg(srcB + (int64_t)c * 3) : 0.0;
-                W[yz * Px + x] = make_double2(a, b);
+            // ---- load: two real sequences -> one complex array (4 independent loads in flight) ----
+            for (int c0 = tid; c0 < Nc; c0 += 4 * nthreads) {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int c = c0 + i * nthreads;
+                    a[i] = (srcA && c < Nc) ? __ldg(srcA + (int64_t)c * 3) : 0.0;
+                    b[i] = (srcB && c < Nc) ? __ldg(srcB + (int64_t)c * 3) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int c = c0 + i * nthreads;
+                    if (c < Nc) W[(c / Nx) * Px + (c % Nx)] = make_double2(a[i], b[i]);
+                }
             }
             __syncthreads();
             axis_pass(Nx, W, Ny * Nz, Ny * Nz, Px, 0, 1, tid, nthreads);
@@ -183,25 +127,43 @@ project_fft_kernel(PfParams p) {
             __syncthreads();
             axis_pass(Nz, W, Nx * Ny, Nx, 1, Px, Ny * Px, tid, nthreads);
             __syncthreads();
-            const cplx* twA = tm.uA >= 0 ? p.tw + tm.uA : nullptr;
-            const cplx* twB = srcB ? p.tw + tm.uB : nullptr;
-            for (int q = tid; q < p.Q; q += nthreads) {
-                const int2 o = __ldg(p.qoff + q);
-                const cplx C = W[o.x], D = W[o.y];
-                // A = (C + conj D)/2,  B = (C - conj D)/(2i)
-                if (twA) {
-                    cplx a = make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y));
-                    cplx r = cmul(a, __ldg(twA + (int64_t)q * p.n_unit));
-                    cplx* dst = outA + q * qstride;
-                    if (term) { cplx old = *dst; r = cadd(old, r); }
-                    *dst = r;
+            // ---- epilogue: separate the two sequences, twiddle, store (4 q in flight per thread) ----
+            const bool hasA = tm.uA >= 0, hasB = srcB != nullptr;
+            const cplx* __restrict__ twA = tw + (hasA ? tm.uA : 0);
+            const cplx* __restrict__ twB = tw + (hasB ? tm.uB : 0);
+            for (int q0 = tid; q0 < Q; q0 += 4 * nthreads) {
+                int2 o[4];
+                cplx wa[4], wb[4], olda[4], oldb[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int q = q0 + i * nthreads;
+                    if (q < Q) {
+                        o[i] = __ldg(qoff + q);
+                        if (hasA) wa[i] = __ldg(twA + (int64_t)q * n_unit);
+                        if (hasB) wb[i] = __ldg(twB + (int64_t)q * n_unit);
+                        if (term) {
+                            if (hasA) olda[i] = outA[q * qstride];
+                            if (hasB) oldb[i] = outB[q * qstride];
+                        }
+                    }
                 }
-                if (twB) {
-                    cplx b = make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x));
-                    cplx r = cmul(b, __ldg(twB + (int64_t)q * p.n_unit));
-                    cplx* dst = outB + q * qstride;
-                    if (term) { cplx old = *dst; r = cadd(old, r); }
-                    *dst = r;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int q = q0 + i * nthreads;
+                    if (q < Q) {
+                        const cplx C = W[o[i].x], D = W[o[i].y];
+                        // A = (C + conj D)/2,  B = (C - conj D)/(2i)
+                        if (hasA) {
+                            cplx r = cmul(make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y)), wa[i]);
+                            if (term) r = cadd(olda[i], r);
+                            outA[q * qstride] = r;
+                        }
+                        if (hasB) {
+                            cplx r = cmul(make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x)), wb[i]);
+                            if (term) r = cadd(oldb[i], r);
+                            outB[q * qstride] = r;
+                        }
+                    }
                 }
             }
         }
@@ -223,13 +185,18 @@ static PfLayout pf_layout(int n_unit, int n_prim, int Q) {
     return l;
 }
 
-static int pick_threads(int Nx, int Ny, int Nz, int Q) {
-    int best = 128;
-    long long best_cost = -1;
-    for (int th = 128; th <= 512; th += 32) {
-        auto rounds = [&](int n) { return (long long)((n + th - 1) / th); };
-        long long cost = (rounds(Ny * Nz) + rounds(Nx * Nz) + rounds(Nx * Ny)) * th * 8 + rounds(Nx * Ny * Nz) * th +
-                         rounds(Q) * th * 2;
+static int pick_threads(int Nx, int Ny, int Nz, int Q, int max_threads) {
+    // every pass should keep at least 8 warps busy and waste few thread slots in its last round
+    const char* env = getenv("DP_PF_THREADS");
+    if (env && atoi(env) >= 32 && atoi(env) <= max_threads) return atoi(env) / 32 * 32;
+    int best = 256;
+    double best_cost = -1;
+    for (int th = 256; th <= max_threads; th += 32) {
+        auto rounds = [&](int n) { return (double)((n + th - 1) / th); };
+        // time ~ rounds (latency bound); pencil passes weigh more than the element-wise phases
+        double cost = 4.0 * (rounds(Ny * Nz) + rounds(Nx * Nz) + rounds(Nx * Ny)) + rounds(Nx * Ny * Nz) / 4.0 +
+                      rounds(Q) / 4.0;
+        cost *= 1.0 + 0.1 * th / 512.0;       // mild preference for fewer threads (register budget)
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = th; }
     }
     return best;
@@ -319,13 +286,20 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
     p.v = v; p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Px = Px; p.Nc = Nc; p.N = n_unit * Nc;
     p.n_unit = n_unit; p.n_prim = n_prim; p.Q = Q; p.njobs = (int)jobs.size(); p.T = T;
     p.jobs = d_jobs; p.terms = d_terms; p.qoff = d_qoff; p.tw = (const dp::cplx*)twiddle; p.out = (dp::cplx*)out_vc;
-    const int threads = dp::pick_threads(Nx, Ny, Nz, Q);
-    auto k = dp::project_fft_kernel;
-    DP_CUDA_OK(DP_SET_SMEM(k, smem));
-    int per_sm = (int)dp::imin<size_t>(4, dp::imax<size_t>(1, (size_t)(224 * 1024) / (smem + 1024)));
+    int per_sm = (int)dp::imin<size_t>(2, dp::imax<size_t>(1, (size_t)(226 * 1024) / (smem + 1024)));
+    int threads = dp::pick_threads(Nx, Ny, Nz, Q, per_sm >= 2 ? 320 : 512);
+    if (threads > 320) per_sm = 1;
     int64_t nunits = T * (int64_t)jobs.size();
     int grid = (int)dp::imin<int64_t>(nunits, (int64_t)dp::imax(dp::sm_count(), 1) * per_sm);
-    DP_LAUNCH(k, dim3(grid), dim3(threads), smem, st, p);
+    if (per_sm >= 2) {
+        auto k = dp::project_fft_kernel<320, 2>;
+        DP_CUDA_OK(DP_SET_SMEM(k, smem));
+        DP_LAUNCH(k, dim3(grid), dim3(threads), smem, st, p);
+    } else {
+        auto k = dp::project_fft_kernel<512, 1>;
+        DP_CUDA_OK(DP_SET_SMEM(k, smem));
+        DP_LAUNCH(k, dim3(grid), dim3(threads), smem, st, p);
+    }
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
 }

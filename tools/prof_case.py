@@ -1,0 +1,51 @@
+"""One isolated call of a hot-path kernel at bench-relevant sizes, for `ncu --set full` captures.
+
+    python tools/prof_case.py fft5a|project|contract|mem|corr [reps]
+"""
+import itertools
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dynaphopy_b200 import ops as dops  # noqa: E402
+
+case = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ops = dops.Ops()
+dev = ops.be.device
+freq = np.arange(0, 40.05, 0.05)
+torch.manual_seed(0)
+
+if case == "fft5a":
+    S = int(os.environ.get("PC_S", 296))
+    x = torch.randn((131072, S), dtype=torch.complex128, device=dev)
+    for _ in range(reps):
+        out = ops.power_fft(x, 0.001, freq)
+elif case in ("project", "contract"):
+    dims = np.array([16, 16, 20]); nc = int(np.prod(dims)); T = int(os.environ.get("PC_T", 4096))
+    cell = np.diag([4.0] * 3); unit_pos = np.array([[0, 0, 0], [2.0, 2, 2]])
+    mm = np.array([[x, y, z] for z in range(20) for y in range(16) for x in range(16)], dtype=np.int32)
+    q_cart = 2 * np.pi * (mm / dims) @ np.linalg.inv(cell).T
+    tw = torch.as_tensor(np.sqrt([28.0855, 69.723])[None, :] * np.exp(-1j * q_cart @ unit_pos.T) / np.sqrt(nc), device=dev)
+    qb = torch.as_tensor(mm, device=dev)
+    v = torch.randn((T, 2 * nc, 3), dtype=torch.float64, device=dev)
+    eig = torch.randn((len(mm), 6, 6), dtype=torch.complex128, device=dev)
+    for _ in range(reps):
+        vc = ops.project_commensurate(v, dims, [0, 1], 2, qb, tw)
+        if case == "contract":
+            vq = ops.project_phonon(vc, eig, inplace=True)
+elif case == "mem":
+    T, S = (int(os.environ.get("PC_T", 2500)), int(os.environ.get("PC_S", 592)))
+    x = torch.randn((T, S), dtype=torch.complex128, device=dev)
+    for _ in range(reps):
+        out = ops.power_mem(x, 0.002, freq, 1000)
+elif case == "corr":
+    T, S = (int(os.environ.get("PC_T", 32768)), int(os.environ.get("PC_S", 64)))
+    x = torch.randn((T, S), dtype=torch.complex128, device=dev)
+    for _ in range(reps):
+        out = ops.power_correlation(x, 0.001, freq, 10, 1, 1)
+torch.cuda.synchronize()
+print("done", case)
