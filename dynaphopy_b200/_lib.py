@@ -31,6 +31,7 @@ SIGNATURES = {
     "dp_project_phonon_blocked": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
     "dp_power_fft_workspace_bytes": (_Z, [_L, _I, _D, _P, _I]),
     "dp_power_fft": (_I, [_P, _L, _I, _L, _D, _P, _I, _D, _P, _P, _Z, _P]),
+    "dp_power_fft_strided": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _D, _P, _P, _Z, _P]),
     "dp_power_fft_pieces": (_I, [_L, _D, _P, _I, _P, _P, _P, _I]),
     "dp_power_mem_workspace_bytes": (_Z, [_L, _I, _I, _I]),
     "dp_power_mem": (_I, [_P, _L, _I, _L, _D, _P, _I, _I, _D, _I, _P, _P, _Z, _P]),
@@ -73,7 +74,8 @@ class DpLib:
         return self.cdll.dp_version().decode()
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdynaphopy_b200.so")
+LIB_PATH = os.environ.get("DYNAPHOPY_B200_LIB",        # development override: an alternative build of the SAME library
+                          os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdynaphopy_b200.so"))
 _lib = None
 
 

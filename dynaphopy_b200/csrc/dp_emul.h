@@ -30,6 +30,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __shared__ static thread_local
 #define __align__(n) __attribute__((aligned(n)))
 
@@ -244,6 +245,10 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, 
     return dp_emul::shfl_any(v, lane - (int)d >= 0 ? lane - (int)d : lane);
 }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcs(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
+template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
+template <typename T> static inline void __stcg(T* p, T v) { *p = v; }
 
 static inline double atomicAdd(double* p, double v) {
     static std::mutex m; std::lock_guard<std::mutex> g(m);

@@ -13,11 +13,13 @@
 // row transforms are fused in shared memory.  A second kernel averages the windows in the
 // reference's order and applies np.interp's exact arithmetic.
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 #include <vector>
 
 #include "dp_common.cuh"
 #include "dp_fft.cuh"
+#include "dp_spectrum_fft2.cuh"
 
 namespace dp {
 
@@ -33,6 +35,8 @@ struct SpecHostPlan {
     int lo = 0, nkeep = 0;
     std::vector<int> idx0, mode;      // np.interp bracket (sorted-frequency index), 1 = copy fp[idx0]
     std::vector<double> dx, den;
+    bool use_v2 = false;              // register-codelet fast path (dp_spectrum_fft2.cuh)
+    S2Plan s2;
 };
 
 // _division_of_data (power_spectrum/__init__.py:33-51), same floating-point expressions.
@@ -81,12 +85,6 @@ static int make_spec_plan(int64_t T, double dt, const double* freq, int F, SpecH
     if (pl->duplicate_single) pl->starts.resize(1);     // (a + a) / 2 == a exactly
     const int L = pl->L;
     pl->half = L / 2;
-    if (!make_fft_split(L, &pl->sl)) {
-        set_error("power_fft: window length %d has a prime factor > %d or no usable split", L, FFT_MAX_RADIX);
-        return DP_ERR_UNSUPPORTED;
-    }
-    pl->P = next_fast_length(L + L / 2);
-    if (!make_fft_split(pl->P, &pl->sp)) { set_error("power_fft: internal: no split for P=%d", pl->P); return DP_ERR_UNSUPPORTED; }
     // np.interp plan on the sorted fftfreq axis xp[i] = (i - half) * val, val = 1/(L*dt)
     const double val = 1.0 / ((double)L * dt);
     auto xp = [&](long long i) { return (double)(i - pl->half) * val; };
@@ -118,12 +116,21 @@ static int make_spec_plan(int64_t T, double dt, const double* freq, int F, SpecH
     }
     pl->lo = (int)lo;
     pl->nkeep = (int)(hi - lo + 1);
+    const char* force = getenv("DP_SPECTRUM_ENGINE");      // "v1" forces the general engine (validation)
+    pl->use_v2 = !(force && force[0] == 'v' && force[1] == '1') && make_s2_plan(L, pl->nkeep, &pl->s2);
+    if (pl->use_v2) { pl->P = pl->s2.P; return DP_OK; }
+    if (!make_fft_split(L, &pl->sl)) {
+        set_error("power_fft: window length %d has a prime factor > %d or no usable split", L, FFT_MAX_RADIX);
+        return DP_ERR_UNSUPPORTED;
+    }
+    pl->P = next_fast_length(L + L / 2);
+    if (!make_fft_split(pl->P, &pl->sp)) { set_error("power_fft: internal: no split for P=%d", pl->P); return DP_ERR_UNSUPPORTED; }
     return DP_OK;
 }
 
 // ---------------- device side -------------------------------------------------------------------
 struct SpecParams {
-    const cplx* series; int64_t ld; int S;
+    const cplx* series; int64_t stride_s, stride_t; int tb_len; int64_t tb_stride; int S;
     int L, P, half, npieces;
     const int* starts;
     FftSplit sp, sl;
@@ -158,11 +165,17 @@ spectrum_items_kernel(SpecParams p) {
     const int64_t nitems = (int64_t)p.S * p.npieces;
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int pc = (int)(item / p.S), s = (int)(item % p.S);
-        const cplx* x0 = p.series + (int64_t)p.starts[pc] * p.ld + s;
-        const int64_t ld = p.ld;
+        const cplx* x0 = p.series + (int64_t)s * p.stride_s;
+        const int t0 = p.starts[pc];
+        const int64_t stride_t = p.stride_t, tb_stride = p.tb_stride;
+        const int tb_len = p.tb_len;
         const int L = p.L, P = p.P, half = p.half;
         auto load_x = [=](int idx) -> cplx {
-            return idx < L ? __ldg(x0 + (int64_t)idx * ld) : make_double2(0.0, 0.0);
+            if (idx >= L) return make_double2(0.0, 0.0);
+            const int t = t0 + idx;
+            if (tb_len == 0) return __ldg(x0 + (int64_t)t * stride_t);
+            const int b = t / tb_len;
+            return __ldg(x0 + (int64_t)b * tb_stride + (int64_t)(t - b * tb_len) * stride_t);
         };
         MidPowerInverse mid{&p.sp.p2, p.twP2, p.sp.n2};
         // ---- linear autocorrelation through FFT_P ----
@@ -248,13 +261,17 @@ spectrum_finalize_kernel(const double* __restrict__ spec, int S, int npieces, in
 
 struct SpecLayout {
     size_t off_tw[6], off_starts, off_idx0, off_mode, off_dx, off_den, off_spec, off_scratch, total;
+    size_t slab_elems;
     int nslots;
 };
 
 static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
     SpecLayout l;
     size_t o = 0;
-    int lens[6] = {pl.sp.n1, pl.sp.n2, pl.P, pl.sl.n1, pl.sl.n2, pl.L};
+    // v2: w256, wsub, fine, coarse (256 each), unused, w_L table
+    int lens_v1[6] = {pl.sp.n1, pl.sp.n2, pl.P, pl.sl.n1, pl.sl.n2, pl.L};
+    int lens_v2[6] = {6 * 256, 1, 1, 1, 1, pl.L};
+    const int* lens = pl.use_v2 ? lens_v2 : lens_v1;
     for (int i = 0; i < 6; i++) { l.off_tw[i] = o; o += align_up((size_t)lens[i] * sizeof(cplx), 256); }
     l.off_starts = o; o += align_up(pl.starts.size() * sizeof(int), 256);
     l.off_idx0 = o;   o += align_up((size_t)F * sizeof(int), 256);
@@ -264,7 +281,8 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
     l.off_spec = o;   o += align_up((size_t)S * pl.starts.size() * pl.nkeep * sizeof(double), 256);
     int64_t items = (int64_t)S * (int64_t)pl.starts.size();
     l.nslots = (int)imin<int64_t>(items, (int64_t)imax(sm_count(), 1));
-    l.off_scratch = o; o += align_up((size_t)l.nslots * ((size_t)pl.P + pl.L) * sizeof(cplx), 256);
+    l.slab_elems = pl.use_v2 ? (size_t)pl.P : (size_t)pl.P + pl.L;
+    l.off_scratch = o; o += align_up((size_t)l.nslots * l.slab_elems * sizeof(cplx), 256);
     l.total = o;
     return l;
 }
@@ -299,10 +317,13 @@ int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* pi
     return DP_OK;
 }
 
-int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq, int F,
-                 double scale, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                         int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, double scale,
+                         double* out, void* workspace, size_t workspace_bytes, void* stream) {
     DP_REQUIRE(series && freq && out && workspace, DP_ERR_INVALID, "dp_power_fft: null pointer");
-    DP_REQUIRE(S > 0 && ld >= S, DP_ERR_INVALID, "dp_power_fft: bad S=%d ld=%lld", S, (long long)ld);
+    DP_REQUIRE(S > 0 && stride_t != 0, DP_ERR_INVALID, "dp_power_fft: bad S=%d stride_t=%lld", S, (long long)stride_t);
+    DP_REQUIRE(tb_len >= 0 && tb_len < (1LL << 31), DP_ERR_INVALID, "dp_power_fft: bad time-block length %lld", (long long)tb_len);
+    if (tb_len >= T) tb_len = 0;
     dp::SpecHostPlan pl;
     int rc = dp::make_spec_plan(T, dt, freq, F, &pl);
     if (rc) return rc;
@@ -311,11 +332,22 @@ int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, 
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     dp::cplx* tw[6];
-    int lens[6] = {pl.sp.n1, pl.sp.n2, pl.P, pl.sl.n1, pl.sl.n2, pl.L};
-    for (int i = 0; i < 6; i++) {
-        tw[i] = (dp::cplx*)(ws + lay.off_tw[i]);
-        rc = dp::launch_twiddles(tw[i], lens[i], st);
+    for (int i = 0; i < 6; i++) tw[i] = (dp::cplx*)(ws + lay.off_tw[i]);
+    if (pl.use_v2) {
+        auto kt = dp::s2_tables_kernel;
+        int a1, a2, b1, b2;
+        dp::s2_radices(pl.s2.n1, &a1, &a2);
+        dp::s2_radices(pl.s2.n2, &b1, &b2);
+        DP_LAUNCH(kt, dim3(1), dim3(256), 0, st, tw[0], a1, a2, b1, b2, pl.s2.m1, pl.s2.m2, pl.s2.P);
+        DP_CUDA_OK(cudaGetLastError());
+        rc = dp::launch_twiddles(tw[5], pl.L, st);
         if (rc) return rc;
+    } else {
+        int lens[6] = {pl.sp.n1, pl.sp.n2, pl.P, pl.sl.n1, pl.sl.n2, pl.L};
+        for (int i = 0; i < 6; i++) {
+            rc = dp::launch_twiddles(tw[i], lens[i], st);
+            if (rc) return rc;
+        }
     }
     DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_starts, pl.starts.data(), pl.starts.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_idx0, pl.idx0.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -325,29 +357,55 @@ int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, 
 #ifndef DP_EMUL
     DP_CUDA_OK(cudaStreamSynchronize(st));   // plan vectors are host temporaries
 #endif
-    dp::SpecParams p;
-    p.series = (const dp::cplx*)series; p.ld = ld; p.S = S;
-    p.L = pl.L; p.P = pl.P; p.half = pl.half; p.npieces = (int)pl.starts.size();
-    p.starts = (const int*)(ws + lay.off_starts);
-    p.sp = pl.sp; p.sl = pl.sl;
-    p.twP1 = tw[0]; p.twP2 = tw[1]; p.twPN = tw[2]; p.twL1 = tw[3]; p.twL2 = tw[4]; p.twLN = tw[5];
-    p.scratch = (dp::cplx*)(ws + lay.off_scratch);
-    p.spec = (double*)(ws + lay.off_spec);
-    p.lo = pl.lo; p.nkeep = pl.nkeep;
-    p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
-    size_t smem = std::max(dp::fft_split_smem_elems(pl.sp), dp::fft_split_smem_elems(pl.sl)) * sizeof(dp::cplx);
-    auto k = dp::spectrum_items_kernel;
-    DP_CUDA_OK(DP_SET_SMEM(k, smem));
-    DP_LAUNCH(k, dim3(lay.nslots), dim3(dp::FFT_THREADS), smem, st, p);
-    DP_CUDA_OK(cudaGetLastError());
+    const int npieces = (int)pl.starts.size();
+    double* spec = (double*)(ws + lay.off_spec);
+    if (pl.use_v2) {
+        dp::S2Params p;
+        p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;
+        p.tb_len = (int)tb_len; p.tb_stride = tb_stride; p.S = S; p.npieces = npieces;
+        p.starts = (const int*)(ws + lay.off_starts);
+        p.pl = pl.s2;
+        p.g_tables = tw[0]; p.g_twL = tw[5];
+        p.scratch = (dp::cplx*)(ws + lay.off_scratch); p.slab_elems = lay.slab_elems;
+        p.spec = spec; p.lo = pl.lo; p.nkeep = pl.nkeep;
+        p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
+        p.skip_mask = getenv("DP_S2_SKIP") ? atoi(getenv("DP_S2_SKIP")) : 0;
+        auto k = dp::spectrum2_kernel;
+        DP_CUDA_OK(DP_SET_SMEM(k, dp::S2_SMEM_BYTES));
+        DP_LAUNCH(k, dim3(lay.nslots), dim3(dp::S2_THREADS), dp::S2_SMEM_BYTES, st, p);
+        DP_CUDA_OK(cudaGetLastError());
+    } else {
+        dp::SpecParams p;
+        p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;
+        p.tb_len = (int)tb_len; p.tb_stride = tb_stride; p.S = S;
+        p.L = pl.L; p.P = pl.P; p.half = pl.half; p.npieces = npieces;
+        p.starts = (const int*)(ws + lay.off_starts);
+        p.sp = pl.sp; p.sl = pl.sl;
+        p.twP1 = tw[0]; p.twP2 = tw[1]; p.twPN = tw[2]; p.twL1 = tw[3]; p.twL2 = tw[4]; p.twLN = tw[5];
+        p.scratch = (dp::cplx*)(ws + lay.off_scratch);
+        p.spec = spec;
+        p.lo = pl.lo; p.nkeep = pl.nkeep;
+        p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
+        size_t smem = std::max(dp::fft_split_smem_elems(pl.sp), dp::fft_split_smem_elems(pl.sl)) * sizeof(dp::cplx);
+        auto k = dp::spectrum_items_kernel;
+        DP_CUDA_OK(DP_SET_SMEM(k, smem));
+        DP_LAUNCH(k, dim3(lay.nslots), dim3(dp::FFT_THREADS), smem, st, p);
+        DP_CUDA_OK(cudaGetLastError());
+    }
     auto kf = dp::spectrum_finalize_kernel;
     int64_t total = (int64_t)F * S;
     DP_LAUNCH(kf, dim3((unsigned)dp::imin<int64_t>((total + 255) / 256, 4096)), dim3(256), 0, st,
-              (const double*)p.spec, S, p.npieces, pl.n_avg, pl.nkeep, pl.lo, (const int*)(ws + lay.off_idx0),
+              (const double*)spec, S, npieces, pl.n_avg, pl.nkeep, pl.lo, (const int*)(ws + lay.off_idx0),
               (const int*)(ws + lay.off_mode), (const double*)(ws + lay.off_dx), (const double*)(ws + lay.off_den), F,
               scale, out);
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
+}
+
+int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq, int F,
+                 double scale, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(S > 0 && ld >= S, DP_ERR_INVALID, "dp_power_fft: bad S=%d ld=%lld", S, (long long)ld);
+    return dp_power_fft_strided(series, T, S, 1, ld, 0, 0, dt, freq, F, scale, out, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -178,10 +178,28 @@ class Ops:
         assert len(shp) == 2, "series must be (T, S)"
         return s, shp[0], shp[1]
 
-    def power_fft(self, series, dt, frequency_range, scale=UNIT_CONVERSION):
+    def power_fft(self, series, dt, frequency_range, scale=UNIT_CONVERSION, series_major=False):
+        """FFT power spectrum of every series -> (F, S) float64.
+
+        ``series``: (T, S) complex128 as the reference passes it, or -- ``series_major=True`` --
+        (S, T) with the time axis contiguous (the layout the kernels stream at full bandwidth), or
+        (G, S, Tb) = G consecutive time blocks of Tb samples (what the time-sharded ->
+        series-sharded all-to-all delivers, T = G*Tb)."""
         be = self.be
-        s, T, S = self._series(series)
         f = _host(frequency_range, np.float64)
+        s = be.asarray(series, np.complex128)
+        shp = be.shape(s)
+        if not series_major:
+            assert len(shp) == 2, "series must be (T, S)"
+            T, S = shp
+            strides = (1, S, 0, 0)
+        elif len(shp) == 2:
+            S, T = shp
+            strides = (T, 1, 0, 0)
+        else:
+            G, S, Tb = shp
+            T = G * Tb
+            strides = (Tb, 1, Tb, S * Tb)
         nbytes = self.lib.size("dp_power_fft_workspace_bytes", T, S, float(dt), _hptr(f), f.size)
         if nbytes == 0:
             # let the library explain (bad grid, unsupported window length, ...)
@@ -189,8 +207,8 @@ class Ops:
                           be.stream())
         ws = be.empty((nbytes,), np.uint8)
         out = be.empty((f.size, S), np.float64)
-        self.lib.call("dp_power_fft", be.ptr(s), T, S, S, float(dt), _hptr(f), f.size, float(scale), be.ptr(out),
-                      be.ptr(ws), nbytes, be.stream())
+        self.lib.call("dp_power_fft_strided", be.ptr(s), T, S, strides[0], strides[1], strides[2], strides[3], float(dt),
+                      _hptr(f), f.size, float(scale), be.ptr(out), be.ptr(ws), nbytes, be.stream())
         return out
 
     def power_mem(self, series, dt, frequency_range, coefficients, scale=UNIT_CONVERSION, nan_to_num=True):

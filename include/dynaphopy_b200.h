@@ -159,6 +159,15 @@ size_t dp_power_fft_workspace_bytes(int64_t T, int S, double dt, const double* f
 int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq,
                  int F, double scale, double* out, void* workspace, size_t workspace_bytes,
                  void* stream);
+/* Same spectrum for series stored with arbitrary strides (in complex128 elements): sample t of series s
+ * is at  series[s*stride_s + (t / tb_len)*tb_stride + (t % tb_len)*stride_t]  when tb_len > 0 (the time axis
+ * arrives in blocks, e.g. one block per source rank after the time-sharded -> series-sharded all-to-all,
+ * SURVEY.md section 8e), or  series[s*stride_s + t*stride_t]  when tb_len == 0.  dp_power_fft is the
+ * case stride_s = 1, stride_t = ld.  The series-major layout (stride_t = 1) is the one the kernels stream
+ * at full HBM bandwidth. */
+int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                         int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, double scale,
+                         double* out, void* workspace, size_t workspace_bytes, void* stream);
 int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* piece_len,
                         int* n_pieces, int* starts, int max_pieces);
 

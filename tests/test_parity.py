@@ -354,3 +354,19 @@ def test_spectra_single_column_and_two_frequencies(kops):
     assert relerr(kops.power_fft(x, 0.002, f), port.fft_spectra(x, 0.002, f)) < TOL
     assert relerr(kops.power_mem(x, 0.002, f, 40), port.mem_spectra(x, 0.002, f, 40)) < TOL
     assert relerr(kops.power_correlation(x, 0.002, f, 10, 1, 1), port.correlation_spectra(x, 0.002, f, 10, 1, "intended")) < TOL
+
+
+def test_power_fft_series_major_and_time_blocks(kops):
+    """Series-major (S, T) input and the blocked time axis (G, S, Tb) the all-to-all delivers give the
+    same spectra as the reference's (T, S) layout."""
+    rng = np.random.default_rng(23)
+    nt, ns = 1200, 3
+    x = _series(rng, nt, ns, 0.002)
+    f = np.arange(0, 40.0, 2.0)
+    ref = port.fft_spectra(x, 0.002, f)
+    a = to_np(kops.power_fft(x, 0.002, f))
+    b = to_np(kops.power_fft(np.ascontiguousarray(x.T), 0.002, f, series_major=True))
+    blocks = np.ascontiguousarray(x.reshape(4, nt // 4, ns).transpose(0, 2, 1))       # (G, S, Tb)
+    c = to_np(kops.power_fft(blocks, 0.002, f, series_major=True))
+    assert relerr(a, ref) < TOL
+    assert np.array_equal(a, b) and np.array_equal(a, c)

@@ -99,7 +99,10 @@ if "fft" in which:
         t = timeit(lambda: ops.power_fft(x, dt, freq), reps=3, warm=1)
         L, pieces = ops.fft_pieces(Ts, dt, freq)
         report(f"power_fft T={Ts} S={S}", t, nbytes=16.0 * L * len(pieces) * S, extra=f"L={L} pieces={len(pieces)} series/s={S / t[0]:.1f}")
-        del x
+        xt = x.t().contiguous()
+        t = timeit(lambda: ops.power_fft(xt, dt, freq, series_major=True), reps=3, warm=1)
+        report(f"power_fft series-major T={Ts} S={S}", t, nbytes=16.0 * L * len(pieces) * S, extra=f"L={L} pieces={len(pieces)} series/s={S / t[0]:.1f}")
+        del x, xt
 if "mem" in which:
     for (Ts, S, m) in ((2500, 192, 1000), (131072, int(os.environ.get("KB_SM", 148)), 1000)):
         x = torch.randn((Ts, S), dtype=torch.complex128, device=dev)

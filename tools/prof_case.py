@@ -21,9 +21,9 @@ torch.manual_seed(0)
 
 if case == "fft5a":
     S = int(os.environ.get("PC_S", 296))
-    x = torch.randn((131072, S), dtype=torch.complex128, device=dev)
+    x = torch.randn((S, 131072), dtype=torch.complex128, device=dev)
     for _ in range(reps):
-        out = ops.power_fft(x, 0.001, freq)
+        out = ops.power_fft(x, 0.001, freq, series_major=True)
 elif case in ("project", "contract"):
     dims = np.array([16, 16, 20]); nc = int(np.prod(dims)); T = int(os.environ.get("PC_T", 4096))
     cell = np.diag([4.0] * 3); unit_pos = np.array([[0, 0, 0], [2.0, 2, 2]])
