@@ -29,6 +29,7 @@ SIGNATURES = {
     "dp_project_commensurate": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _I, _I, _P, _P, _Z, _P]),
     "dp_project_phonon": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "dp_project_phonon_blocked": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
+    "dp_project_phonon_series": (_I, [_P, _P, _L, _I, _I, _I, _L, _L, _P, _P]),
     "dp_power_fft_workspace_bytes": (_Z, [_L, _I, _D, _P, _I]),
     "dp_power_fft": (_I, [_P, _L, _I, _L, _D, _P, _I, _D, _P, _P, _Z, _P]),
     "dp_power_fft_strided": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _D, _P, _P, _Z, _P]),

@@ -51,9 +51,11 @@ template <int R> __device__ __forceinline__ void dft_inplace(cplx* v) {
     }
 }
 
-// tab[k1*R2 + j2] = w_N^(j2 k1) (forward roots): consecutive lanes read consecutive entries
+// tab[k1*R2 + j2] = w_N^(j2 k1) (forward roots): consecutive lanes read consecutive entries.
+// sub_dit_a: first butterflies + twiddles, values parked in the slab (the registers are free afterwards:
+// the place to issue the loads of the next tile); sub_dit_b: exchange + second butterflies.
 template <class C>
-__device__ __forceinline__ void sub_dit(cplx (&v)[16], cplx* __restrict__ E, const cplx* __restrict__ tab, int g) {
+__device__ __forceinline__ void sub_dit_a(cplx (&v)[16], cplx* __restrict__ E, const cplx* __restrict__ tab, int g) {
 #pragma unroll
     for (int i = 0; i < C::NB1; i++) {
         const int j2 = g + C::TG * i;
@@ -67,6 +69,9 @@ __device__ __forceinline__ void sub_dit(cplx (&v)[16], cplx* __restrict__ E, con
             }
         }
     }
+}
+template <class C>
+__device__ __forceinline__ void sub_dit_b(cplx (&v)[16], const cplx* __restrict__ E, int g) {
     if constexpr (C::R2 > 1) {
         __syncwarp();
 #pragma unroll
@@ -79,6 +84,11 @@ __device__ __forceinline__ void sub_dit(cplx (&v)[16], cplx* __restrict__ E, con
             }
         }
     }
+}
+template <class C>
+__device__ __forceinline__ void sub_dit(cplx (&v)[16], cplx* __restrict__ E, const cplx* __restrict__ tab, int g) {
+    sub_dit_a<C>(v, E, tab, g);
+    sub_dit_b<C>(v, E, g);
 }
 
 // tab[c*R1 + k1] = w_N^(k1 c)

@@ -138,6 +138,75 @@ project_phonon_kernel(const cplx* vc, const cplx* __restrict__ eig, int64_t T, i
     }
 }
 
+
+// Same contraction, series-major output for the spectrum kernels:
+//   out[((q / q_block) * q_block * M + (q % q_block) * M + s) * T_total + t_offset + t]
+// i.e. one contiguous time series per (q, s) (HBM-friendly for the time FFTs) and, for q_block < Q, one
+// contiguous block per destination rank of the all-to-all.  CTA = PS_TT frames x qt wave vectors:
+// the tile is read as PS_TT runs of qt*M contiguous values, contracted from shared memory (lane = frame,
+// so the eigenvector reads are broadcasts) and written as runs of PS_TT consecutive time samples.
+constexpr int PS_TT = 32;
+constexpr int PS_QT_MAX = 16;       // wave vectors per CTA (fewer for wide M: shared-memory budget)
+
+template <int MT>   // MT > 0: compile-time M (inputs kept in registers); 0: any M
+__global__ void __launch_bounds__(256)
+project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig, int64_t T, int Q, int Mdyn,
+                             int q_block, int qt, int64_t t_offset, int64_t T_total, cplx* __restrict__ out) {
+    DP_DYNSMEM(cplx, sm);
+    const int M = MT > 0 ? MT : Mdyn;
+    const int pitch = qt * M + 1;                   // odd: conflict-free column reads
+    cplx* in = sm;                                      // [PS_TT][pitch]
+    cplx* es = sm + (size_t)PS_TT * pitch;              // [qt][M*M]
+    const int64_t t0 = (int64_t)blockIdx.x * PS_TT;
+    const int q0 = blockIdx.y * qt;
+    const int nq = imin(qt, Q - q0);
+    const int nthreads = blockDim.x, tid = threadIdx.x;
+    for (int e = tid; e < PS_TT * nq * M; e += nthreads) {
+        const int f = e / (nq * M), j = e % (nq * M);
+        cplx val = make_double2(0.0, 0.0);
+        if (t0 + f < T) val = __ldcs(vc + ((t0 + f) * Q + q0) * M + j);
+        in[f * pitch + j] = val;
+    }
+    for (int e = tid; e < nq * M * M; e += nthreads) es[e] = __ldg(eig + (int64_t)q0 * M * M + e);
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int64_t t = t0 + lane;
+    const int np = M / 3;
+    for (int qq = warp; qq < nq; qq += nwarps) {
+        const int q = q0 + qq;
+        const cplx* row = in + lane * pitch + qq * M;
+        const cplx* e = es + qq * M * M;
+        cplx* dst = out + ((int64_t)(q / q_block) * q_block * M + (int64_t)(q % q_block) * M) * T_total + t_offset + t;
+        if (MT > 0) {
+            cplx a[MT > 0 ? MT : 1];
+#pragma unroll
+            for (int j = 0; j < MT; j++) a[j] = row[j];
+#pragma unroll
+            for (int s = 0; s < MT; s++) {
+                cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int p = 0; p < MT / 3; p++) {
+                    cplx part = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) part = cadd(part, cmulc(a[p * 3 + k], e[s * MT + p * 3 + k]));
+                    acc = cadd(acc, part);
+                }
+                if (t < T) __stcs(dst + (int64_t)s * T_total, acc);
+            }
+        } else {
+            for (int s = 0; s < M; s++) {
+                cplx acc = make_double2(0.0, 0.0);
+                for (int p = 0; p < np; p++) {
+                    cplx part = make_double2(0.0, 0.0);
+                    for (int k = 0; k < 3; k++) part = cadd(part, cmulc(row[p * 3 + k], e[s * M + p * 3 + k]));
+                    acc = cadd(acc, part);
+                }
+                if (t < T) __stcs(dst + (int64_t)s * T_total, acc);
+            }
+        }
+    }
+}
+
 }  // namespace dp
 
 extern "C" {
@@ -231,6 +300,38 @@ int dp_project_phonon_blocked(const double* vc, const double* eig, int64_t T, in
     dim3 grid((unsigned)((T + dp::PH_TF - 1) / dp::PH_TF), (unsigned)Q);
     DP_LAUNCH(k, grid, dim3(256), smem, (cudaStream_t)stream, (const dp::cplx*)vc, (const dp::cplx*)eig, T, Q, M,
               q_block, (dp::cplx*)vq);
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int Q, int M, int q_block,
+                             int64_t t_offset, int64_t T_total, double* out, void* stream) {
+    DP_REQUIRE((T == 0 || (vc && out)) && eig, DP_ERR_INVALID, "dp_project_phonon_series: null pointer");
+    DP_REQUIRE(vc != out, DP_ERR_INVALID, "dp_project_phonon_series: cannot run in place (the output is transposed)");
+    DP_REQUIRE(q_block > 0 && Q % q_block == 0, DP_ERR_INVALID, "dp_project_phonon_series: q_block=%d must divide Q=%d", q_block, Q);
+    DP_REQUIRE(T >= 0 && Q > 0 && M > 0 && M % 3 == 0, DP_ERR_INVALID, "dp_project_phonon_series: bad sizes (M must be 3*n_prim)");
+    DP_REQUIRE(t_offset >= 0 && t_offset + T <= T_total, DP_ERR_INVALID, "dp_project_phonon_series: frames [%lld, %lld) outside the series length %lld",
+               (long long)t_offset, (long long)(t_offset + T), (long long)T_total);
+    if (T == 0) return DP_OK;
+    const size_t per_q = ((size_t)dp::PS_TT * M + (size_t)M * M) * sizeof(dp::cplx);
+    const int qt = (int)dp::imax<size_t>(1, dp::imin<size_t>(dp::PS_QT_MAX, (size_t)(72 * 1024) / per_q));
+    const unsigned gy = (unsigned)((Q + qt - 1) / qt);
+    DP_REQUIRE(gy <= 65535, DP_ERR_UNSUPPORTED, "dp_project_phonon_series: Q=%d too large for one launch", Q);
+    size_t smem = ((size_t)dp::PS_TT * (qt * M + 1) + (size_t)qt * M * M) * sizeof(dp::cplx);
+    DP_REQUIRE(smem <= 200 * 1024, DP_ERR_UNSUPPORTED, "dp_project_phonon_series: M=%d too large", M);
+    dim3 grid((unsigned)((T + dp::PS_TT - 1) / dp::PS_TT), gy);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DP_PS_LAUNCH(MT)                                                                                          \
+    do {                                                                                                          \
+        auto k = dp::project_phonon_series_kernel<MT>;                                                            \
+        DP_CUDA_OK(DP_SET_SMEM(k, smem));                                                                         \
+        DP_LAUNCH(k, grid, dim3(256), smem, st, (const dp::cplx*)vc, (const dp::cplx*)eig, T, Q, M, q_block,     \
+                  qt, t_offset, T_total, (dp::cplx*)out);                                                             \
+    } while (0)
+    if (M == 6) DP_PS_LAUNCH(6);
+    else if (M == 12) DP_PS_LAUNCH(12);
+    else DP_PS_LAUNCH(0);
+#undef DP_PS_LAUNCH
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
 }

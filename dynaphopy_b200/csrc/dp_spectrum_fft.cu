@@ -281,6 +281,8 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
     l.off_spec = o;   o += align_up((size_t)S * pl.starts.size() * pl.nkeep * sizeof(double), 256);
     int64_t items = (int64_t)S * (int64_t)pl.starts.size();
     l.nslots = (int)imin<int64_t>(items, (int64_t)imax(sm_count(), 1));
+    if (getenv("DP_S2_GRID") && atoi(getenv("DP_S2_GRID")) > 0)      // development aid: fewer persistent CTAs
+        l.nslots = (int)imin<int64_t>(l.nslots, atoi(getenv("DP_S2_GRID")));
     l.slab_elems = pl.use_v2 ? (size_t)pl.P : (size_t)pl.P + pl.L;
     l.off_scratch = o; o += align_up((size_t)l.nslots * l.slab_elems * sizeof(cplx), 256);
     l.total = o;

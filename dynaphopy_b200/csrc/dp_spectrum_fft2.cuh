@@ -21,9 +21,9 @@
 namespace dp {
 
 #ifndef DP_S2_THREADS
-#define DP_S2_THREADS 384
+#define DP_S2_THREADS 256
 #endif
-constexpr int S2_THREADS = DP_S2_THREADS;          // 12 warps x <= 168 registers
+constexpr int S2_THREADS = DP_S2_THREADS;          // 8 warps x <= 255 registers
 constexpr int S2_WARPS = S2_THREADS / 32;
 constexpr int S2_BINSLOTS = 8;                    // bins per residue thread in pass 4
 constexpr int S2_TILE_COLS = S2_THREADS / 16;     // pass-4 column tile: 16 threads per column
@@ -111,9 +111,14 @@ __device__ __forceinline__ unsigned long long s2_slab_policy() {
     return pol;
 #endif
 }
+#ifndef DP_S2_LDMODE
+#define DP_S2_LDMODE 2
+#endif
 __device__ __forceinline__ cplx s2_ld_slab(const cplx* ptr, unsigned long long pol) {
-#ifdef DP_EMUL
+#if defined(DP_EMUL) || DP_S2_LDMODE == 0
     return *ptr;
+#elif DP_S2_LDMODE == 1
+    return __ldcg(ptr);
 #else
     cplx v;
     asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;\n" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol) : "memory");
@@ -121,8 +126,10 @@ __device__ __forceinline__ cplx s2_ld_slab(const cplx* ptr, unsigned long long p
 #endif
 }
 __device__ __forceinline__ void s2_st_slab(cplx* ptr, cplx v, unsigned long long pol) {
-#ifdef DP_EMUL
+#if defined(DP_EMUL) || DP_S2_LDMODE == 0
     *ptr = v;
+#elif DP_S2_LDMODE == 1
+    __stcg(ptr, v);
 #else
     asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;\n" ::"l"(ptr), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 #endif
@@ -138,16 +145,20 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
     const int seq = lane % C::NS, g = lane / C::NS;
     cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
-    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
+    auto load_tile = [&](int tile, cplx (&w)[16]) {
         const int col = tile * C::NS + seq;
-        cplx v[16];
 #pragma unroll
         for (int i = 0; i < C::NB1; i++)
 #pragma unroll
             for (int a = 0; a < C::R1; a++) {
                 const int idx = (a * C::R2 + g + C::TG * i) * n2 + col;
-                v[i * C::R1 + a] = idx < L ? __ldcs(x + s2_time_offset(p, t0 + idx)) : make_double2(0.0, 0.0);
+                w[i * C::R1 + a] = idx < L ? __ldcs(x + s2_time_offset(p, t0 + idx)) : make_double2(0.0, 0.0);
             }
+    };
+    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
+        const int col = tile * C::NS + seq;
+        cplx v[16];
+        load_tile(tile, v);
         sub_dit<C>(v, E, sm.T1, g);
         // four-step twiddle w_P^(col*kk), kk = k1 + R1*k2: geometric in k2
         const cplx ratio = tw2level(sm.fine, sm.coarse, col * C::R1);
@@ -174,14 +185,18 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, i
     const int seq = lane % C::NS, g = lane / C::NS;
     cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int ntiles = n1 / C::NS;
+    auto load_tile = [&](int tile, cplx (&w)[16]) {
+        const cplx* Ar = A + (size_t)(tile * C::NS + seq) * n2;
+#pragma unroll
+        for (int i = 0; i < C::NB1; i++)
+#pragma unroll
+            for (int a = 0; a < C::R1; a++) w[i * C::R1 + a] = s2_ld_slab(Ar + a * C::R2 + g + C::TG * i, pol);
+    };
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int row = tile * C::NS + seq;
         cplx* __restrict__ Ar = A + (size_t)row * n2;
         cplx v[16];
-#pragma unroll
-        for (int i = 0; i < C::NB1; i++)
-#pragma unroll
-            for (int a = 0; a < C::R1; a++) v[i * C::R1 + a] = s2_ld_slab(Ar + a * C::R2 + g + C::TG * i, pol);
+        load_tile(tile, v);
         sub_dit<C>(v, E, sm.T2, g);
 #pragma unroll
         for (int r = 0; r < C::NB2 * C::R2; r++) v[r] = make_double2(v[r].x * v[r].x + v[r].y * v[r].y, 0.0);
@@ -214,13 +229,17 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
     const int seq = lane % C::NS, g = lane / C::NS;
     cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
-    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
+    auto load_tile = [&](int tile, cplx (&w)[16]) {
         const int col = tile * C::NS + seq;
-        cplx v[16];
 #pragma unroll
         for (int i = 0; i < C::NB1; i++)
 #pragma unroll
-            for (int a = 0; a < C::R1; a++) v[i * C::R1 + a] = s2_ld_slab(A + (size_t)(a * C::R2 + g + C::TG * i) * n2 + col, pol);
+            for (int a = 0; a < C::R1; a++) w[i * C::R1 + a] = s2_ld_slab(A + (size_t)(a * C::R2 + g + C::TG * i) * n2 + col, pol);
+    };
+    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
+        const int col = tile * C::NS + seq;
+        cplx v[16];
+        load_tile(tile, v);
         sub_dit<C>(v, E, sm.T1, g);
         __syncwarp();          // every lane of the warp has its column in registers before rows are overwritten
 #pragma unroll

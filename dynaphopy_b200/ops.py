@@ -168,6 +168,25 @@ class Ops:
         self.lib.call("dp_project_phonon_blocked", be.ptr(vc), be.ptr(e), T, Q, M, qb, be.ptr(out), be.stream())
         return out.reshape(T, Q, M) if (inplace and qb == Q) else out
 
+    def project_phonon_series(self, vc, eigenvectors, q_block=None, out=None, t_offset=0, t_total=None):
+        """vc (T,Q,n_p,3)|(T,Q,M) -> series-major vq: ``out[g, qq*M + s, t_offset + t]`` with q = g*q_block + qq,
+        shape (Q/q_block, q_block*M, t_total).  ``out`` lets a long trajectory be contracted chunk by chunk."""
+        be = self.be
+        vc = be.asarray(vc, np.complex128)
+        T, Q = be.shape(vc)[:2]
+        M = int(np.prod(be.shape(vc)[2:]))
+        e = be.asarray(eigenvectors, np.complex128)
+        assert be.shape(e)[0] == Q and int(np.prod(be.shape(e)[1:])) == M * M, "eigenvector shape mismatch"
+        qb = Q if q_block is None else int(q_block)
+        t_total = T if t_total is None else int(t_total)
+        if out is None:
+            out = be.empty((Q // qb, qb * M, t_total), np.complex128)
+        else:
+            assert be.shape(out) == (Q // qb, qb * M, t_total), "bad `out` buffer"
+        self.lib.call("dp_project_phonon_series", be.ptr(vc), be.ptr(e), T, Q, M, qb, int(t_offset), t_total,
+                      be.ptr(out), be.stream())
+        return out
+
     def launch_count(self):
         return int(self.lib.cdll.dp_launch_count())
 

@@ -6,10 +6,11 @@ dynaphopy/__init__.py:1130-1174, done here for all q in one pass).
 
 Multi-GPU: frames are sharded by contiguous time blocks -- projection and
 contraction are independent per frame -- then ONE all-to-all over NCCL/NVLink turns the
-time-sharded ``vq`` into series-sharded, time-major matrices and every rank computes the spectra
-of its own Q/G wave vectors.  The contraction kernel writes the send layout directly
-(``dp_project_phonon_blocked``), and the received blocks concatenate into the (T, S/G) matrix the
-spectrum kernels consume, so there is no pack or unpack pass.
+time-sharded ``vq`` into series-sharded data and every rank computes the spectra of its own Q/G
+wave vectors.  The contraction kernel writes the send layout directly (``dp_project_phonon_series``:
+one contiguous block per destination rank, every (q, s) series contiguous in time), and the FFT
+spectrum kernel reads the received (source rank, series, time) blocks in place
+(``dp_power_fft_strided``), so there is no pack or unpack pass and every stage streams contiguous runs.
 """
 import numpy as np
 
@@ -149,24 +150,60 @@ class MeshPipeline:
                                               self.integration_method, self.correlation_weight)
         raise ValueError("Power spectrum algorithm number not found")
 
-    def run(self, velocity_local):
+    # -- series-major path (the one run() uses) ---------------------------------------------------------
+    def series(self, velocity_local, chunk_frames=4096, out=None, t_offset=0, t_total=None):
+        """Local frames -> series-major contracted series ``(G, (Q/G)*M, Tl)``: block g is the contiguous
+        message for rank g, every (q, s) series is contiguous in time.  Projection and contraction run chunk
+        by chunk so that only one chunk of ``vc`` is ever materialised."""
+        be = self.be
+        tl = be.shape(velocity_local)[0]
+        t_total = tl if t_total is None else t_total
+        if out is None:
+            out = be.empty((self.world, self.q_block * self.M, t_total), np.complex128)
+        for t0 in range(0, tl, chunk_frames):
+            t1 = min(t0 + chunk_frames, tl)
+            vc = self.project(velocity_local[t0:t1])
+            self.ops.project_phonon_series(vc, self.d_eig, q_block=self.q_block, out=out, t_offset=t_offset + t0,
+                                           t_total=t_total)
+            del vc
+        return out
+
+    def exchange_series(self, send):
+        """The one all-to-all on the series-major layout: (G, S_loc, Tl) -> (G, S_loc, Tl) where block g now
+        holds the time block of source rank g for THIS rank's series."""
+        if self.world == 1:
+            return send
+        import torch
+        import torch.distributed as dist
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
+        return recv
+
+    def spectra_series(self, blocks):
+        """(G, S_loc, Tb) time blocks of series-major series -> (F, S_loc) power spectra."""
+        if self.algorithm in (2, 3, 4, 5):
+            return self.ops.power_fft(blocks, self.dt, self.freq, series_major=True)
+        g, s_loc, tb = self.be.shape(blocks)
+        tm = blocks.permute(0, 2, 1).reshape(g * tb, s_loc) if hasattr(blocks, "permute") else \
+            np.ascontiguousarray(np.transpose(blocks, (0, 2, 1)).reshape(g * tb, s_loc))
+        return self.spectra(tm)
+
+    def run(self, velocity_local, chunk_frames=4096):
         """Whole step on device-resident local frames; returns the (F, S_local) spectra of this rank."""
-        vc = self.project(velocity_local)
-        send = self.contract(vc)
-        del vc
-        series = self.exchange(send)
-        return self.spectra(series)
+        send = self.series(velocity_local, chunk_frames)
+        blocks = self.exchange_series(send)
+        return self.spectra_series(blocks)
 
     # -- host-resident trajectory: chunked H2D copies overlapped with the projection ------------------
     def run_from_host(self, velocity_host, chunk_frames=2048):
         """velocity_host: pinned (Tl, N, 3) float64 torch tensor on the host.  Frames are copied in
         chunks on a side stream into a two-slot staging buffer while the previous chunk is being
-        projected; the spectra come back to the host as numpy."""
+        projected and contracted; the spectra come back to the host as numpy."""
         import torch
         be = self.be
         tl = velocity_host.shape[0]
         n = velocity_host.shape[1]
-        out = be.empty((tl, self.Q, self.plan.n_prim, 3), np.complex128)
+        send = be.empty((self.world, self.q_block * self.M, tl), np.complex128)
         stage = [be.empty((min(chunk_frames, tl), n, 3), np.float64) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=be.device)
         main = torch.cuda.current_stream(be.device)
@@ -182,14 +219,11 @@ class MeshPipeline:
                 stage[slot][: t1 - t0].copy_(velocity_host[t0:t1], non_blocking=True)
                 ready[slot].record(copy_stream)
             main.wait_event(ready[slot])
-            self.ops.project_commensurate(stage[slot][: t1 - t0], self.plan.dims, self.plan.unit_type,
-                                          self.plan.n_prim, self.d_qbin, self.d_tw, out=out[t0:t1])
+            self.series(stage[slot][: t1 - t0], chunk_frames, out=send, t_offset=t0, t_total=tl)
             freed[slot].record(main)
         del stage
-        send = self.contract(out)
-        del out
-        series = self.exchange(send)
-        ps = self.spectra(series)
+        blocks = self.exchange_series(send)
+        ps = self.spectra_series(blocks)
         return ps.cpu().numpy()
 
 

@@ -144,6 +144,14 @@ int dp_project_phonon(const double* vc, const double* eig, int64_t T, int Q, int
 int dp_project_phonon_blocked(const double* vc, const double* eig, int64_t T, int Q, int M, int q_block,
                               double* vq, void* stream);
 
+/* Same contraction, SERIES-MAJOR output: one contiguous time series per (q, s) -- the layout the spectrum
+ * kernels stream at full HBM bandwidth -- grouped by blocks of q_block wave vectors (one block per
+ * destination rank of the all-to-all, q_block == Q: a plain (Q*M, T_total) matrix):
+ *   out[((q / q_block)*q_block*M + (q % q_block)*M + s) * T_total + t_offset + t],   t < T.
+ * t_offset / T_total let a long trajectory be contracted chunk by chunk into one series matrix. */
+int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int Q, int M, int q_block,
+                             int64_t t_offset, int64_t T_total, double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A7  power spectrum, FFT method (selector keys 2 and 3).
  * Replaces: get_fft_numpy_spectra / _numpy_power / _division_of_data

@@ -203,6 +203,10 @@ def test_project_phonon_wide(kops):
         vq = to_np(kops.project_phonon(vc, eig))
         ref = np.stack([port.project_onto_phonon(vc[:, q], eig[q]) for q in range(nq)], axis=1)
         assert relerr(vq, ref) < TOL
+        # series-major output (one contiguous series per (q, s)), written in two time chunks
+        out = kops.project_phonon_series(vc[:50], eig, t_total=nt)
+        out = to_np(kops.project_phonon_series(vc[50:], eig, out=out, t_offset=50, t_total=nt))
+        assert np.array_equal(out[0].T.reshape(nt, nq, m), vq)
 
 
 # ------------------------------------------------------------------------------- FFT engine

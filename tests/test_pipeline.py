@@ -59,7 +59,9 @@ def test_mesh_pipeline_single_rank(kops):
     vc = pipe.project(c["v"])
     vq = pipe.contract(vc)
     assert relerr(to_np(vq).reshape(c["ref_vq"].shape), c["ref_vq"]) < 1e-10
-    ps = to_np(pipe.run(c["v"]))
+    ser = to_np(pipe.series(c["v"], chunk_frames=24))                    # (1, Q*M, T) series-major
+    assert relerr(ser[0].T.reshape(c["ref_vq"].shape), c["ref_vq"]) < 1e-10
+    ps = to_np(pipe.run(c["v"], chunk_frames=24))
     assert relerr(ps, c["ref_ps"]) < 1e-10
     assert np.array_equal(ps.argmax(0), c["ref_ps"].argmax(0))
     for alg, ref in ((1, port.mem_spectra(c["ref_vq"].reshape(64, -1)[:, :6], c["dt"], c["freq"], 10)),):
@@ -105,9 +107,14 @@ def _rank_main(rank, world, port_no, out_dir):
     nt = c["v"].shape[0]
     tl = nt // world
     v_local = c["v"][rank * tl:(rank + 1) * tl]
-    send = pipe.contract(pipe.project(v_local))                       # numpy (G, Tl, Q/G, M)
+    send = pipe.contract(pipe.project(v_local))                       # numpy (G, Tl, Q/G, M)  time-major path
     series = pipe.exchange(torch.from_numpy(np.ascontiguousarray(send))).numpy()
-    ps = pipe.spectra(series)
+    ps_tm = pipe.spectra(series)
+    send2 = pipe.series(v_local, chunk_frames=5)                      # numpy (G, S_loc, Tl)  series-major path
+    blocks = pipe.exchange_series(torch.from_numpy(np.ascontiguousarray(send2))).numpy()
+    ps = pipe.spectra_series(blocks)
+    assert np.array_equal(ps, ps_tm)
+    assert np.array_equal(blocks.transpose(0, 2, 1).reshape(series.shape), series)
     np.save(os.path.join(out_dir, f"ps{rank}.npy"), ps)
     np.save(os.path.join(out_dir, f"series{rank}.npy"), series)
     dist.barrier()
