@@ -225,6 +225,7 @@ def run_ours(args):
     assert plan.usable() and plan.commensurate.all()
     eig = random_unitary_eigenvectors(torch, dev, wl["Q"], wl["M"])
     pipe = pipeline.MeshPipeline(plan, eig, FREQ, DT, ops=ops, algorithm=2)
+    assert pipe.fold_twiddle        # primitive cell: the projection twiddle rides on the eigenvectors
 
     # ---- device-resident inputs -------------------------------------------------------------------
     v = torch.empty((tl, wl["n_atoms"], 3), dtype=torch.float64, device=dev)
@@ -249,9 +250,9 @@ def run_ours(args):
         for t0 in range(0, tl, CH):
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a.record()
-            vc = pipe.project(v[t0:t0 + CH])
+            vc = ops.project_commensurate(v[t0:t0 + CH], plan.dims, plan.unit_type, plan.n_prim, pipe.d_qbin, None)
             b.record()
-            ops.project_phonon_series(vc, pipe.d_eig, q_block=pipe.q_block, out=send, t_offset=t0, t_total=tl)
+            ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send, t_offset=t0, t_total=tl)
             c.record()
             del vc
             evs.append((a, b, c))

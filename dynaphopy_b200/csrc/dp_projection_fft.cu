@@ -30,7 +30,8 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 // pencil pc: base = (pc % A)*sa + (pc / A)*sb, elements at base + i*st
 template <int N>
-__device__ __noinline__ void axis_pass_n(cplx* W, int npencil, int A, int sa, int sb, int st, int tid, int nthreads) {
+__device__ __noinline__ void axis_pass_n(int npencil, int A, int sa, int sb, int st, int tid, int nthreads) {
+    DP_DYNSMEM(cplx, W);             // the transform is the CTA's dynamic shared memory: keep the address space visible
     for (int pc = tid; pc < npencil; pc += nthreads) {
         const int base = (pc % A) * sa + (pc / A) * sb;
         cplx in[N], out[N];
@@ -42,8 +43,8 @@ __device__ __noinline__ void axis_pass_n(cplx* W, int npencil, int A, int sa, in
     }
 }
 
-#define DP_AXIS_CASE(n) case n: axis_pass_n<n>(W, npencil, A, sa, sb, st, tid, nthreads); break;
-__device__ __forceinline__ void axis_pass(int n, cplx* W, int npencil, int A, int sa, int sb, int st, int tid,
+#define DP_AXIS_CASE(n) case n: axis_pass_n<n>(npencil, A, sa, sb, st, tid, nthreads); break;
+__device__ __forceinline__ void axis_pass(int n, int npencil, int A, int sa, int sb, int st, int tid,
                                           int nthreads) {
     switch (n) {
         DP_AXIS_CASE(2) DP_AXIS_CASE(3) DP_AXIS_CASE(4) DP_AXIS_CASE(5) DP_AXIS_CASE(6) DP_AXIS_CASE(7)
@@ -63,13 +64,14 @@ struct PfTerm { int uA, uB; };                              // uB < 0: none
 
 struct PfParams {
     const double* v;
-    int Nx, Ny, Nz, Px, Nc, N, n_unit, n_prim, Q, njobs;
+    int Nx, Ny, Nz, Px, Nc, N, n_unit, n_prim, Q, njobs, nterms, npad;
     int64_t T;
     const PfJob* jobs;
     const PfTerm* terms;
     const int2* qoff;        // (offset of bin m(q), offset of bin -m(q)) in the padded layout
-    const cplx* tw;          // [Q][n_unit]
+    const cplx* tw;          // [Q][n_unit], or nullptr: no twiddle (raw lattice DFT of every unit atom)
     cplx* out;               // [T][Q][n_prim][3]
+    int skip;                // development aid (DP_PF_SKIP): 1 = no loads, 2 = no transforms, 4 = no epilogue
 };
 
 __global__ void __launch_bounds__(256)
@@ -83,87 +85,133 @@ qoffset_kernel(const int* __restrict__ qbin, int Q, int Nx, int Ny, int Nz, int 
     }
 }
 
+// ---- phases of one (frame, transform) unit; each is its own function so that the register allocation of
+// the wide pencil codelets does not leak into the streaming phases (and vice versa) -----------------------
+struct PfUnit {
+    const double* srcA; const double* srcB;      // real sequences (stride 3 doubles), or nullptr
+    cplx* outA; cplx* outB;                      // first output element of slot A / B for q = 0
+    const cplx* twA; const cplx* twB;            // tw + unit atom
+    int64_t qstride;
+    bool hasA, hasB;
+};
+
+__device__ __noinline__ void pf_load(const PfUnit& u, int Nc, int Nx, int Px, int tid, int nthreads) {
+    DP_DYNSMEM(cplx, W);
+    const double* __restrict__ srcA = u.srcA;
+    const double* __restrict__ srcB = u.srcB;
+    // two real sequences -> one complex array (8 independent loads in flight per thread)
+    for (int c0 = tid; c0 < Nc; c0 += 4 * nthreads) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = c0 + i * nthreads;
+            a[i] = (srcA && c < Nc) ? __ldg(srcA + (int64_t)c * 3) : 0.0;
+            b[i] = (srcB && c < Nc) ? __ldg(srcB + (int64_t)c * 3) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = c0 + i * nthreads;
+            if (c < Nc) W[(c / Nx) * Px + (c % Nx)] = make_double2(a[i], b[i]);
+        }
+    }
+}
+
+// epilogue: separate the two real sequences (A = (C + conj D)/2, B = (C - conj D)/(2i) with C, D the bins
+// m(q), -m(q)), twiddle, store.  ACC: add to what earlier unit atoms of the same type already stored.
+template <bool ACC, bool TW>
+__device__ __noinline__ void pf_epilogue(const PfUnit& u, int npad, int Q, int n_unit, int tid, int nthreads) {
+    DP_DYNSMEM(cplx, W);
+    const unsigned* __restrict__ qo = reinterpret_cast<const unsigned*>(W + npad);   // packed bin offsets (m, -m)
+    const bool hasA = u.hasA, hasB = u.hasB;
+    const cplx* __restrict__ twA = u.twA;
+    const cplx* __restrict__ twB = u.twB;
+    cplx* __restrict__ outA = u.outA;
+    cplx* __restrict__ outB = u.outB;
+    const int64_t qstride = u.qstride;
+    for (int q0 = tid; q0 < Q; q0 += 4 * nthreads) {
+        cplx wa[4], wb[4];
+        if (TW) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int q = imin(q0 + i * nthreads, Q - 1);
+                wa[i] = __ldg(twA + (int64_t)q * n_unit);
+                wb[i] = __ldg(twB + (int64_t)q * n_unit);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = q0 + i * nthreads;
+            if (q < Q) {
+                const unsigned o = qo[q];
+                const cplx C = W[o & 0xffffu], D = W[o >> 16];
+                cplx ra = make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y));
+                cplx rb = make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x));
+                if (TW) { ra = cmul(ra, wa[i]); rb = cmul(rb, wb[i]); }
+                if (ACC) {
+                    if (hasA) ra = cadd(outA[q * qstride], ra);
+                    if (hasB) rb = cadd(outB[q * qstride], rb);
+                }
+                // paired slots are adjacent: the two 16-byte stores of a thread fill one 32-byte sector
+                if (hasA) __stcs(outA + q * qstride, ra);
+                if (hasB) __stcs(outB + q * qstride, rb);
+            }
+        }
+    }
+}
+
 // MAXT / MINB: launch bounds (register budget): <=320 threads with 2 CTAs per SM, or <=512 with 1
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-project_fft_kernel(PfParams p) {
+project_fft_kernel(const __grid_constant__ PfParams p) {
     DP_DYNSMEM(cplx, W);
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz, Px = p.Px, Nc = p.Nc, Q = p.Q, n_unit = p.n_unit;
-    const int2* __restrict__ qoff = p.qoff;
-    const cplx* __restrict__ tw = p.tw;
+    // shared memory: transform [npad] | packed bin offsets [Q] | jobs | terms  (staged once per CTA)
+    unsigned* qo = reinterpret_cast<unsigned*>(W + p.npad);
+    PfJob* sjobs = reinterpret_cast<PfJob*>(qo + ((Q + 3) & ~3));
+    PfTerm* sterms = reinterpret_cast<PfTerm*>(sjobs + p.njobs);
+    for (int q = tid; q < Q; q += nthreads) {
+        const int2 o = p.qoff[q];
+        qo[q] = (unsigned)o.x | ((unsigned)o.y << 16);
+    }
+    for (int i = tid; i < p.njobs; i += nthreads) sjobs[i] = p.jobs[i];
+    for (int i = tid; i < p.nterms; i += nthreads) sterms[i] = p.terms[i];
+    __syncthreads();
     const int64_t nunits = p.T * p.njobs;
     for (int64_t unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
         const int64_t t = unit / p.njobs;
-        const PfJob job = p.jobs[(int)(unit % p.njobs)];
+        const PfJob job = sjobs[(int)(unit % p.njobs)];
         const double* __restrict__ vt = p.v + t * (int64_t)p.N * 3;
-        cplx* __restrict__ outA = p.out + ((t * Q) * p.n_prim + job.pA) * 3 + job.kA;
-        cplx* __restrict__ outB = job.pB >= 0 ? p.out + ((t * Q) * p.n_prim + job.pB) * 3 + job.kB : nullptr;
-        const int64_t qstride = (int64_t)p.n_prim * 3;
+        PfUnit u;
+        u.outA = p.out + ((t * Q) * p.n_prim + job.pA) * 3 + job.kA;
+        u.outB = job.pB >= 0 ? p.out + ((t * Q) * p.n_prim + job.pB) * 3 + job.kB : nullptr;
+        u.qstride = (int64_t)p.n_prim * 3;
         for (int term = 0; term < job.nterms; term++) {
-            const PfTerm tm = p.terms[job.term0 + term];
-            const double* __restrict__ srcA = tm.uA >= 0 ? vt + (int64_t)tm.uA * Nc * 3 + job.kA : nullptr;
-            const double* __restrict__ srcB = (tm.uB >= 0 && job.pB >= 0) ? vt + (int64_t)tm.uB * Nc * 3 + job.kB : nullptr;
+            const PfTerm tm = sterms[job.term0 + term];
+            u.srcA = tm.uA >= 0 ? vt + (int64_t)tm.uA * Nc * 3 + job.kA : nullptr;
+            u.srcB = (tm.uB >= 0 && job.pB >= 0) ? vt + (int64_t)tm.uB * Nc * 3 + job.kB : nullptr;
+            u.hasA = tm.uA >= 0;
+            u.hasB = u.srcB != nullptr;
+            u.twA = p.tw + (u.hasA ? tm.uA : 0);
+            u.twB = p.tw + (u.hasB ? tm.uB : 0);
             __syncthreads();
-            // ---- load: two real sequences -> one complex array (4 independent loads in flight) ----
-            for (int c0 = tid; c0 < Nc; c0 += 4 * nthreads) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int c = c0 + i * nthreads;
-                    a[i] = (srcA && c < Nc) ? __ldg(srcA + (int64_t)c * 3) : 0.0;
-                    b[i] = (srcB && c < Nc) ? __ldg(srcB + (int64_t)c * 3) : 0.0;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int c = c0 + i * nthreads;
-                    if (c < Nc) W[(c / Nx) * Px + (c % Nx)] = make_double2(a[i], b[i]);
-                }
+            if (!(p.skip & 1)) pf_load(u, Nc, Nx, Px, tid, nthreads);
+            __syncthreads();
+            if (!(p.skip & 2)) {
+                axis_pass(Nx, Ny * Nz, Ny * Nz, Px, 0, 1, tid, nthreads);
+                __syncthreads();
+                axis_pass(Ny, Nx * Nz, Nx, 1, Ny * Px, Px, tid, nthreads);
+                __syncthreads();
+                axis_pass(Nz, Nx * Ny, Nx, 1, Px, Ny * Px, tid, nthreads);
+                __syncthreads();
             }
-            __syncthreads();
-            axis_pass(Nx, W, Ny * Nz, Ny * Nz, Px, 0, 1, tid, nthreads);
-            __syncthreads();
-            axis_pass(Ny, W, Nx * Nz, Nx, 1, Ny * Px, Px, tid, nthreads);
-            __syncthreads();
-            axis_pass(Nz, W, Nx * Ny, Nx, 1, Px, Ny * Px, tid, nthreads);
-            __syncthreads();
-            // ---- epilogue: separate the two sequences, twiddle, store (4 q in flight per thread) ----
-            const bool hasA = tm.uA >= 0, hasB = srcB != nullptr;
-            const cplx* __restrict__ twA = tw + (hasA ? tm.uA : 0);
-            const cplx* __restrict__ twB = tw + (hasB ? tm.uB : 0);
-            for (int q0 = tid; q0 < Q; q0 += 4 * nthreads) {
-                int2 o[4];
-                cplx wa[4], wb[4], olda[4], oldb[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int q = q0 + i * nthreads;
-                    if (q < Q) {
-                        o[i] = __ldg(qoff + q);
-                        if (hasA) wa[i] = __ldg(twA + (int64_t)q * n_unit);
-                        if (hasB) wb[i] = __ldg(twB + (int64_t)q * n_unit);
-                        if (term) {
-                            if (hasA) olda[i] = outA[q * qstride];
-                            if (hasB) oldb[i] = outB[q * qstride];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int q = q0 + i * nthreads;
-                    if (q < Q) {
-                        const cplx C = W[o[i].x], D = W[o[i].y];
-                        // A = (C + conj D)/2,  B = (C - conj D)/(2i)
-                        if (hasA) {
-                            cplx r = cmul(make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y)), wa[i]);
-                            if (term) r = cadd(olda[i], r);
-                            outA[q * qstride] = r;
-                        }
-                        if (hasB) {
-                            cplx r = cmul(make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x)), wb[i]);
-                            if (term) r = cadd(oldb[i], r);
-                            outB[q * qstride] = r;
-                        }
-                    }
+            if (!(p.skip & 4)) {
+                if (p.tw) {
+                    if (term) pf_epilogue<true, true>(u, p.npad, Q, n_unit, tid, nthreads);
+                    else pf_epilogue<false, true>(u, p.npad, Q, n_unit, tid, nthreads);
+                } else {
+                    if (term) pf_epilogue<true, false>(u, p.npad, Q, n_unit, tid, nthreads);
+                    else pf_epilogue<false, false>(u, p.npad, Q, n_unit, tid, nthreads);
                 }
             }
         }
@@ -214,17 +262,23 @@ size_t dp_project_commensurate_workspace_bytes(const int* dims, int n_unit, int 
 int dp_project_commensurate(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
                             int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
                             double* out_vc, void* workspace, size_t workspace_bytes, void* stream) {
-    DP_REQUIRE((T == 0 || (v && out_vc)) && dims && unit_type && qbin && twiddle && workspace, DP_ERR_INVALID,
+    DP_REQUIRE((T == 0 || (v && out_vc)) && dims && unit_type && qbin && workspace, DP_ERR_INVALID,
                "dp_project_commensurate: null pointer");
     DP_REQUIRE(n_unit > 0 && n_prim > 0 && T >= 0 && Q > 0 && project_on_atom < n_prim, DP_ERR_INVALID,
                "dp_project_commensurate: bad sizes");
+    DP_REQUIRE(twiddle || n_unit == n_prim, DP_ERR_INVALID,
+               "dp_project_commensurate: twiddle == NULL (raw lattice DFT) needs one unit-cell atom per primitive type");
     const int Nx = dims[0], Ny = dims[1], Nz = dims[2];
     DP_REQUIRE(Nx >= 1 && Ny >= 1 && Nz >= 1, DP_ERR_INVALID, "dp_project_commensurate: bad dims");
     DP_REQUIRE(Nx <= DP_ROOTS_NMAX && Ny <= DP_ROOTS_NMAX && Nz <= DP_ROOTS_NMAX, DP_ERR_UNSUPPORTED,
                "dp_project_commensurate: supercell multiplicity > %d (use dp_project_wave_vector)", DP_ROOTS_NMAX);
     const int Px = (Nx % 2 == 0) ? Nx + 1 : Nx;
     const int64_t Nc64 = (int64_t)Nx * Ny * Nz;
-    const size_t smem = (size_t)Nz * Ny * Px * sizeof(dp::cplx);
+    const size_t smem_w = (size_t)Nz * Ny * Px * sizeof(dp::cplx);
+    const size_t smem = smem_w + dp::align_up((size_t)Q * sizeof(unsigned), 16) +
+                        (size_t)(2 * n_prim + 2) * sizeof(dp::PfJob) + (size_t)(3 * n_unit + 4) * sizeof(dp::PfTerm);
+    DP_REQUIRE((int64_t)Nz * Ny * Px <= 65535, DP_ERR_UNSUPPORTED,
+               "dp_project_commensurate: %lld cells exceed the 16-bit bin offsets (use dp_project_wave_vector)", (long long)Nc64);
     DP_REQUIRE(smem <= 220 * 1024, DP_ERR_UNSUPPORTED,
                "dp_project_commensurate: %lld cells need %zu B of shared memory (use dp_project_wave_vector)",
                (long long)Nc64, smem);
@@ -234,7 +288,6 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
     const int Nc = (int)Nc64;
     cudaStream_t st = (cudaStream_t)stream;
 
-    // jobs: (p,x)+(p,y) per type; z components of two types share a transform
     std::vector<std::vector<int>> units(n_prim);
     for (int u = 0; u < n_unit; u++) {
         DP_REQUIRE(unit_type[u] >= 0 && unit_type[u] < n_prim, DP_ERR_INVALID, "dp_project_commensurate: unit_type[%d]=%d", u, unit_type[u]);
@@ -253,8 +306,24 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
         j.nterms = (int)n;
         if (n) jobs.push_back(j);
     };
-    for (int p : types) add_job(p, 0, p, 1);
-    for (size_t i = 0; i < types.size(); i += 2) add_job(types[i], 2, i + 1 < types.size() ? types[i + 1] : -1, 2);
+    // output slots (p, k) = 3p + k of the selected types, two per transform; adjacent slots (2j, 2j+1) are
+    // paired so that a thread's two stores fill 32 contiguous bytes (a full sector) per wave vector
+    std::vector<int> slots;
+    for (int p : types)
+        for (int k = 0; k < 3; k++) slots.push_back(3 * p + k);
+    for (size_t i = 0; i < slots.size();) {
+        const int sa = slots[i];
+        if (sa % 2 == 0 && i + 1 < slots.size() && slots[i + 1] == sa + 1) {
+            add_job(sa / 3, sa % 3, (sa + 1) / 3, (sa + 1) % 3);
+            i += 2;
+        } else if (i + 1 < slots.size()) {              // unaligned pair: still one transform
+            add_job(sa / 3, sa % 3, slots[i + 1] / 3, slots[i + 1] % 3);
+            i += 2;
+        } else {
+            add_job(sa / 3, sa % 3, -1, 0);
+            i += 1;
+        }
+    }
     // a slot whose type has fewer unit atoms than its partner still needs its first term to STORE:
     // terms are ordered so that index 0 always carries both sequences when both exist.
     bool need_zero = project_on_atom >= 0;
@@ -284,14 +353,20 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
 
     dp::PfParams p;
     p.v = v; p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Px = Px; p.Nc = Nc; p.N = n_unit * Nc;
-    p.n_unit = n_unit; p.n_prim = n_prim; p.Q = Q; p.njobs = (int)jobs.size(); p.T = T;
+    p.n_unit = n_unit; p.n_prim = n_prim; p.Q = Q; p.njobs = (int)jobs.size(); p.nterms = (int)terms.size();
+    p.npad = Nz * Ny * Px; p.T = T;
+    p.skip = getenv("DP_PF_SKIP") ? atoi(getenv("DP_PF_SKIP")) : 0;
     p.jobs = d_jobs; p.terms = d_terms; p.qoff = d_qoff; p.tw = (const dp::cplx*)twiddle; p.out = (dp::cplx*)out_vc;
     int per_sm = (int)dp::imin<size_t>(2, dp::imax<size_t>(1, (size_t)(226 * 1024) / (smem + 1024)));
     int threads = dp::pick_threads(Nx, Ny, Nz, Q, per_sm >= 2 ? 320 : 512);
     if (threads > 320) per_sm = 1;
     int64_t nunits = T * (int64_t)jobs.size();
     int grid = (int)dp::imin<int64_t>(nunits, (int64_t)dp::imax(dp::sm_count(), 1) * per_sm);
-    if (per_sm >= 2) {
+    if (per_sm >= 2 && threads <= 256) {
+        auto k = dp::project_fft_kernel<256, 2>;
+        DP_CUDA_OK(DP_SET_SMEM(k, smem));
+        DP_LAUNCH(k, dim3(grid), dim3(threads), smem, st, p);
+    } else if (per_sm >= 2) {
         auto k = dp::project_fft_kernel<320, 2>;
         DP_CUDA_OK(DP_SET_SMEM(k, smem));
         DP_LAUNCH(k, dim3(grid), dim3(threads), smem, st, p);

@@ -138,7 +138,7 @@ class Ops:
         assert N == n_unit * int(np.prod(dims_h)), "atom count does not match dims * n_unit"
         qb = be.asarray(qbin, np.int32)
         Q = be.shape(qb)[0]
-        tw = be.asarray(twiddle, np.complex128)
+        tw = be.asarray(twiddle, np.complex128) if twiddle is not None else None      # None: bare lattice DFT
         nbytes = self.lib.size("dp_project_commensurate_workspace_bytes", _hptr(dims_h), n_unit, int(n_prim), Q)
         ws = be.empty((nbytes,), np.uint8)
         if out is None:

@@ -112,6 +112,14 @@ class MeshPipeline:
         self.d_qbin = self.be.asarray(plan.qbin, np.int32)
         self.d_tw = self.be.asarray(plan.twiddle, np.complex128)
         self.d_eig = self.be.asarray(eigenvectors, np.complex128).reshape(self.Q, self.M, self.M)
+        # fused path: the projection writes the bare lattice DFT of every unit atom and the twiddle
+        # (N/n_p)^-1/2 sqrt(m_u) exp(-i q.tau_u) rides on the eigenvectors: e'[q,s,u,k] = e[q,s,u,k] conj(tw[q,u])
+        self.fold_twiddle = plan.n_unit == plan.n_prim and bool(np.all(plan.unit_type == np.arange(plan.n_unit)))
+        if self.fold_twiddle:
+            e = np.asarray(self.be.asarray(eigenvectors, np.complex128).cpu() if hasattr(self.d_eig, "cpu")
+                           else eigenvectors, dtype=np.complex128).reshape(self.Q, self.M, plan.n_prim, 3)
+            e = e * np.conj(plan.twiddle)[:, None, :, None]
+            self.d_eig_folded = self.be.asarray(e.reshape(self.Q, self.M, self.M), np.complex128)
 
     # -- stages -----------------------------------------------------------------------------------
     def project(self, velocity):
@@ -162,8 +170,14 @@ class MeshPipeline:
             out = be.empty((self.world, self.q_block * self.M, t_total), np.complex128)
         for t0 in range(0, tl, chunk_frames):
             t1 = min(t0 + chunk_frames, tl)
-            vc = self.project(velocity_local[t0:t1])
-            self.ops.project_phonon_series(vc, self.d_eig, q_block=self.q_block, out=out, t_offset=t_offset + t0,
+            if self.fold_twiddle:
+                vc = self.ops.project_commensurate(velocity_local[t0:t1], self.plan.dims, self.plan.unit_type,
+                                                   self.plan.n_prim, self.d_qbin, None)
+                eig = self.d_eig_folded
+            else:
+                vc = self.project(velocity_local[t0:t1])
+                eig = self.d_eig
+            self.ops.project_phonon_series(vc, eig, q_block=self.q_block, out=out, t_offset=t_offset + t0,
                                            t_total=t_total)
             del vc
         return out

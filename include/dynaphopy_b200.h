@@ -116,7 +116,10 @@ int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt
  *   dims      [host] 3 supercell multiplicities (Dynamics.get_supercell_matrix)
  *   unit_type [host] n_unit primitive-atom index of every unit-cell atom
  *   qbin      [dev]  Q x 3 int32 DFT bin of every q: round(q_unitcell * dims) mod dims
- *   twiddle   [dev]  Q x n_unit complex128: (N/n_prim)^-1/2 sqrt(mass_u) exp(-i q.tau_u)
+ *   twiddle   [dev]  Q x n_unit complex128: (N/n_prim)^-1/2 sqrt(mass_u) exp(-i q.tau_u); or NULL (only when
+ *                    n_unit == n_prim): out_vc[t,q,u,k] is the bare lattice DFT of unit atom u, and the caller
+ *                    folds the twiddle into the eigenvectors of the contraction that follows
+ *                    (e'[q,s,u,k] = e[q,s,u,k] * conj(twiddle[q,u]) gives the same vq)
  *   out_vc    [dev]  T x Q x n_prim x 3 complex128
  * ------------------------------------------------------------------------------------ */
 size_t dp_project_commensurate_workspace_bytes(const int* dims, int n_unit, int n_prim, int Q);

@@ -113,8 +113,9 @@ def _rank_main(rank, world, port_no, out_dir):
     send2 = pipe.series(v_local, chunk_frames=5)                      # numpy (G, S_loc, Tl)  series-major path
     blocks = pipe.exchange_series(torch.from_numpy(np.ascontiguousarray(send2))).numpy()
     ps = pipe.spectra_series(blocks)
-    assert np.array_equal(ps, ps_tm)
-    assert np.array_equal(blocks.transpose(0, 2, 1).reshape(series.shape), series)
+    # (the two paths may pick different projection kernels: equal up to rounding, not bitwise)
+    assert relerr(ps, ps_tm) < 1e-12
+    assert relerr(blocks.transpose(0, 2, 1).reshape(series.shape), series) < 1e-12
     np.save(os.path.join(out_dir, f"ps{rank}.npy"), ps)
     np.save(os.path.join(out_dir, f"series{rank}.npy"), series)
     dist.barrier()
