@@ -5,9 +5,9 @@ spectra and the minimum-image displacement kernel, behind the reference's own AP
 Layers
   csrc/            hand-written CUDA kernels + the C ABI (include/dynaphopy_b200.h)
   _lib, ops        ctypes binding and array-level operators (PyTorch supplies device memory/streams)
-  structure, dynamics, projection, power_spectrum, quasiparticle
+  structure, dynamics, parameters, projection, power_spectrum, quasiparticle
                    host-side mirror of the reference interface (same names and arguments)
-  distributed      time-sharded projection + all-to-all for multi-GPU runs
+  pipeline         whole q-mesh driver: time-sharded projection, one all-to-all, series-sharded spectra
 
 There is no CPU fallback: importing works anywhere, computing needs a CUDA device.
 """

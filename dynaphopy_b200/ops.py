@@ -51,6 +51,19 @@ class TorchCudaBackend:
         return tuple(x.shape)
 
 
+def is_device_array(x):
+    return type(x).__module__.startswith("torch")
+
+
+def to_host(x):
+    """Device (torch) array -> numpy, numpy passes through."""
+    return x.detach().cpu().numpy() if is_device_array(x) else np.asarray(x)
+
+
+def shape_of(x):
+    return tuple(x.shape)
+
+
 def _host(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 

@@ -1,0 +1,189 @@
+"""``Quasiparticle`` -- the callers of the hot path, with the reference's method names and caching contract
+(dynaphopy/__init__.py:23-186, 610-854) for everything that does not need phonopy: q handling, projections,
+power spectra of phonon modes / wave vector / all atoms.  Eigenvectors come from phonopy in the reference
+(`get_eigenvectors`, :172-186); here they are injected with ``set_eigenvectors`` (same (M, n_p, 3) layout,
+``phonopy_link.py:189-192``).  Peak fitting, renormalised force constants, plotting and I/O stay in the
+reference.
+"""
+import numpy as np
+
+from . import projection
+from .parameters import Parameters
+from .power_spectrum import power_spectrum_functions
+
+
+class Quasiparticle:
+    def __init__(self, dynamic, last_steps=None, vc=None):
+        self._dynamic = dynamic
+        self._vc = vc
+        self._vq = None
+        self._eigenvectors = None
+        self._frequencies = None
+        self._power_spectrum_phonon = None
+        self._power_spectrum_wave_vector = None
+        self._power_spectrum_direct = None
+        self._power_spectrum_partials = None
+        self._parameters = Parameters()
+        self.crop_trajectory(last_steps)
+
+    # -- state -----------------------------------------------------------------------------------------
+    @property
+    def dynamic(self):
+        return self._dynamic
+
+    @property
+    def parameters(self):
+        return self._parameters
+
+    def crop_trajectory(self, last_steps):
+        if last_steps is not None:
+            self._dynamic.crop_trajectory(last_steps)
+        print("Using {0} steps".format(len(self._dynamic.get_time())))
+
+    def power_spectra_clear(self):                       # :47-51
+        self._power_spectrum_phonon = None
+        self._power_spectrum_wave_vector = None
+        self._power_spectrum_direct = None
+        self._power_spectrum_partials = None
+
+    def full_clear(self):                                # :58-65
+        self._eigenvectors = None
+        self._frequencies = None
+        self._vc = None
+        self._vq = None
+        self.power_spectra_clear()
+
+    # -- parameters ------------------------------------------------------------------------------------
+    def set_number_of_mem_coefficients(self, coefficients):                  # :128-130
+        self.power_spectra_clear()
+        self.parameters.number_of_coefficients_mem = coefficients
+
+    def set_projection_onto_atom_type(self, atom_type):                      # :132-137
+        if atom_type in range(self.dynamic.structure.get_number_of_primitive_atoms()):
+            self.parameters.project_on_atom = atom_type
+        else:
+            print('Atom type {} does not exist'.format(atom_type))
+            raise SystemExit
+
+    def set_frequency_limits(self, limits):                                  # :139-142
+        self.power_spectra_clear()
+        self.parameters.frequency_range = np.arange(limits[0], limits[1] + self.parameters.spectrum_resolution,
+                                                    self.parameters.spectrum_resolution)
+
+    def set_spectra_resolution(self, resolution):                            # :144-150
+        self.power_spectra_clear()
+        limits = [self.get_frequency_range()[0], self.get_frequency_range()[-1]]
+        self.parameters.spectrum_resolution = resolution
+        self.parameters.frequency_range = np.arange(limits[0], limits[1] + resolution, resolution)
+
+    def get_frequency_range(self):
+        return self.parameters.frequency_range
+
+    def set_reduced_q_vector(self, q_vector):                                # :157-162
+        q_vector = np.array(q_vector, dtype=float)
+        if not np.array_equal(q_vector, np.asarray(self.parameters.reduced_q_vector, dtype=float)):
+            self.full_clear()
+        self.parameters.reduced_q_vector = q_vector
+
+    def get_reduced_q_vector(self):
+        return self.parameters.reduced_q_vector
+
+    def get_q_vector(self):                                                  # :167-169
+        return np.dot(self.parameters.reduced_q_vector,
+                      2.0 * np.pi * np.linalg.inv(self.dynamic.structure.get_primitive_cell()).T)
+
+    def check_commensurate(self, q_point, decimals=4):                       # :610-623
+        supercell = self.dynamic.get_supercell_matrix()
+        primitive_matrix = self.dynamic.structure.get_primitive_matrix()
+        transform = np.dot(q_point, np.linalg.inv(primitive_matrix)) * supercell
+        transform = np.round(transform, decimals=decimals)
+        return bool(np.all(np.equal(np.mod(transform, 1), 0)))
+
+    def select_power_spectra_algorithm(self, algorithm):                     # :697-707
+        if algorithm in power_spectrum_functions.keys():
+            if algorithm != self.parameters.power_spectra_algorithm:
+                self.power_spectra_clear()
+                self.parameters.power_spectra_algorithm = algorithm
+            print("Using {0} function".format(power_spectrum_functions[algorithm][1]))
+        else:
+            print("Power spectrum algorithm number not found!\nPlease select:")
+            for i in power_spectrum_functions.keys():
+                print('{0} : {1}'.format(i, power_spectrum_functions[i][1]))
+            raise SystemExit
+
+    def get_algorithm_list(self):                                            # :1097-1098
+        return power_spectrum_functions.values()
+
+    # -- harmonic inputs (phonopy in the reference) -------------------------------------------------------
+    def set_eigenvectors(self, eigenvectors, frequencies=None):
+        """(M, n_p, 3) complex eigenvectors of the current q, arranged as phonopy_link.py:189-192."""
+        self._eigenvectors = np.asarray(eigenvectors, dtype=complex)
+        self._frequencies = frequencies
+        self._vq = None
+        self._power_spectrum_phonon = None
+
+    def get_eigenvectors(self):
+        if self._eigenvectors is None:
+            raise RuntimeError("eigenvectors come from phonopy in the reference (dynaphopy/__init__.py:172-186); "
+                               "inject them with set_eigenvectors()")
+        return self._eigenvectors
+
+    def get_frequencies(self):
+        return self._frequencies
+
+    # -- projections -----------------------------------------------------------------------------------------
+    def get_vc(self):                                                        # :626-640
+        if self._vc is None:
+            print("Projecting into wave vector")
+            if not self.check_commensurate(self.get_reduced_q_vector()):
+                print("warning! This wave vector is not a commensurate q-point in MD supercell")
+            self._vc = projection.project_onto_wave_vector(self.dynamic, self.get_q_vector(),
+                                                           project_on_atom=self.parameters.project_on_atom)
+        return self._vc
+
+    def get_vq(self):                                                        # :642-646
+        if self._vq is None:
+            print("Projecting into phonon mode")
+            self._vq = projection.project_onto_phonon(self.get_vc(), self.get_eigenvectors())
+        return self._vq
+
+    # -- power spectra -----------------------------------------------------------------------------------------
+    def _spectrum(self, columns):
+        fn = power_spectrum_functions[self.parameters.power_spectra_algorithm][0]
+        return fn(columns, self.dynamic, self.parameters)
+
+    def get_power_spectrum_phonon(self):                                     # :721-746 (no symmetry star: phonopy)
+        if self._power_spectrum_phonon is None:
+            print("Calculating phonon projection power spectra")
+            self._power_spectrum_phonon = self._spectrum(self.get_vq())
+        return self._power_spectrum_phonon
+
+    def get_power_spectrum_wave_vector(self):                                # :748-779
+        if self._power_spectrum_wave_vector is None:
+            print('Calculating wave vector projection power spectrum')
+            vc = self.get_vc()
+            size = vc.shape[1] * vc.shape[2]
+            self._power_spectrum_wave_vector = self._spectrum(vc.swapaxes(1, 2).reshape(-1, size))
+        return np.nansum(self._power_spectrum_wave_vector, axis=1)
+
+    def get_power_spectrum_full(self, projection_on_coordinate=-1):          # :781-831
+        if self._power_spectrum_direct is None:
+            print("Calculating full power spectrum")
+            vm = self.dynamic.velocity_mass_average_device() if hasattr(self.dynamic, "velocity_mass_average_device") \
+                else self.dynamic.get_velocity_mass_average()
+            n = vm.shape[1]
+            if projection_on_coordinate == -1:
+                cols = vm.swapaxes(1, 2).reshape(-1, n * vm.shape[2]) if isinstance(vm, np.ndarray) \
+                    else vm.transpose(1, 2).reshape(-1, n * vm.shape[2])
+            else:
+                cols = vm[:, :, projection_on_coordinate]
+            self._power_spectrum_direct = np.sum(self._spectrum(cols), axis=1)
+        return self._power_spectrum_direct
+
+    def get_power_spectrum_partials(self):                                   # :833-854
+        if self._power_spectrum_partials is None:
+            vm = self.dynamic.velocity_mass_average_device() if hasattr(self.dynamic, "velocity_mass_average_device") \
+                else self.dynamic.get_velocity_mass_average()
+            parts = [self._spectrum(vm[:, :, k]) for k in range(vm.shape[2])]
+            self._power_spectrum_partials = np.sum(parts, axis=0)
+        return self._power_spectrum_partials

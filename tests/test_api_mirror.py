@@ -1,0 +1,94 @@
+"""The reference-facing Python API (Dynamics / projection / power_spectrum selector / Quasiparticle) on top
+of the kernels, driven the way the reference's own scripts and unit tests drive it
+(unittest/Si_test.py:29-41: build a Dynamics, make a Quasiparticle, set q, select the algorithm, read the
+spectra), and compared with what the REFERENCE returned for the same inputs (tests/golden)."""
+import numpy as np
+import pytest
+
+from conftest import golden, relerr
+
+TOL = 1e-10
+
+
+def _patch_default_ops(monkeypatch, kops):
+    from dynaphopy_b200 import ops as dops
+    monkeypatch.setattr(dops, "_default", kops)
+
+
+def _dynamics(g, kops):
+    from dynaphopy_b200.dynamics import Dynamics
+    from dynaphopy_b200.structure import Structure
+    st = Structure(cell=g["unit_cell"], positions=g["unit_pos"], masses=g["unit_masses"],
+                   primitive_matrix=g["prim_matrix"])
+    return Dynamics(structure=st, velocity=g["velocity"].astype(complex), time=g["time"], supercell=g["supercell"],
+                    ops=kops)
+
+
+@pytest.mark.parametrize("name", ["cubic2_232", "si_conv_222", "cubic2_222_complex"])
+def test_quasiparticle_path_vs_reference(kops, monkeypatch, name):
+    from dynaphopy_b200.quasiparticle import Quasiparticle
+    from dynaphopy_b200.parameters import Parameters
+    _patch_default_ops(monkeypatch, kops)
+    g = golden(name)
+    Parameters().reset()
+    dyn = _dynamics(g, kops)
+    assert dyn.get_time_step_average() == float(g["time_step_average"])
+    assert relerr(dyn.get_velocity_mass_average(), g["vm"]) < 1e-15
+    calc = Quasiparticle(dyn)
+    calc.parameters.use_symmetry = False
+    calc.set_frequency_limits([g["freq"][0], g["freq"][-1]])
+    calc.parameters.frequency_range = g["freq"]
+    for i, q in enumerate(g["q_reduced"]):
+        calc.set_reduced_q_vector(q)
+        assert np.allclose(calc.get_q_vector(), g["q_cart"][i], rtol=0, atol=1e-13)
+        vc = calc.get_vc()
+        assert vc.shape == g["vc"][i].shape and vc.dtype == np.complex128
+        assert relerr(vc, g["vc"][i]) < TOL
+        calc.set_eigenvectors(g["eigenvectors"][i])
+        assert relerr(calc.get_vq(), g["vq"][i]) < TOL
+    # spectra of q index 1 with the three methods of the selector
+    calc.set_reduced_q_vector(g["q_reduced"][1])
+    calc.set_eigenvectors(g["eigenvectors"][1])
+    calc.set_number_of_mem_coefficients(int(g["mem_order"]))
+    for alg, key in ((2, "ps_fft"), (1, "ps_mem"), (3, "ps_fft")):
+        calc.select_power_spectra_algorithm(alg)
+        ps = calc.get_power_spectrum_phonon()
+        assert ps.shape == g[key].shape
+        assert relerr(ps, g[key]) < TOL
+        assert np.array_equal(ps.argmax(0), g[key].argmax(0))
+    calc.select_power_spectra_algorithm(0)
+    ps = calc.get_power_spectrum_phonon()
+    assert np.array_equal(np.isfinite(ps), np.isfinite(g["ps_corr_m1"]))
+    assert relerr(ps, g["ps_corr_m1"]) < TOL
+    calc.select_power_spectra_algorithm(2)
+    assert relerr(calc.get_power_spectrum_wave_vector(), np.nansum(g["ps_fft_wave_vector_cols"], axis=1)) < TOL
+    # project_on_atom keeps the normalisation (projection.py:26-28, 38-39)
+    calc.set_projection_onto_atom_type(0)
+    calc.full_clear()
+    assert relerr(calc.get_vc(), g["vc_atom0"]) < TOL
+    Parameters().reset()
+
+
+def test_selector_contract_and_errors(kops, monkeypatch):
+    from dynaphopy_b200 import power_spectrum
+    from dynaphopy_b200.quasiparticle import Quasiparticle
+    from dynaphopy_b200.parameters import Parameters
+    _patch_default_ops(monkeypatch, kops)
+    assert sorted(power_spectrum.power_spectrum_functions) == [0, 1, 2, 3, 4, 5]
+    assert power_spectrum.power_spectrum_functions[1][1] == 'Maximum entropy method'
+    g = golden("cubic2_232")
+    Parameters().reset()
+    calc = Quasiparticle(_dynamics(g, kops))
+    with pytest.raises(SystemExit):
+        calc.select_power_spectra_algorithm(9)             # reference prints the menu and exit()s
+    with pytest.raises(SystemExit):
+        calc.set_projection_onto_atom_type(7)
+    calc.parameters.number_of_coefficients_mem = 10 ** 6
+    with pytest.raises(SystemExit):                        # power_spectrum/__init__.py:85-87
+        power_spectrum.get_mem_power_spectra(g["vq"][0], calc.dynamic, calc.parameters)
+    # cropping keeps the last frames and invalidates the caches (dynamics.py:65-107)
+    calc2 = Quasiparticle(_dynamics(g, kops), last_steps=100)
+    assert calc2.dynamic.get_velocity_mass_average().shape[0] == 100
+    assert relerr(calc2.dynamic.get_velocity_mass_average(), g["vm"][-100:]) < 1e-15
+    assert power_spectrum._division_of_data(0.05, 50001, 0.001) == [[0, 20000], [15000, 35000], [30001, 50001]]
+    Parameters().reset()
