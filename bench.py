@@ -183,10 +183,11 @@ def run_reference(args):
             "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(wl, frames, args.gpus),
-            "cpu_baseline": {"value": value, "unit": "atom*frames/s", "cores": os.cpu_count(), "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "atom*frames/s", "cores": 1, "kind": "port",
                              "sample": sample, "host_cores": os.cpu_count(),
-                             "note": "Python-level loops serial as in the reference (SURVEY 0.1), numpy/BLAS threads at default "
-                                     "(all cores); each step = the bounded sample, value extrapolated",
+                             "note": "the reference's FFT-method path is serial numpy (per-atom np.exp products, np.correlate, "
+                                     "pocketfft; no OpenMP on this path, SURVEY 0.1): one host thread does the work even with "
+                                     "BLAS threading left at its default; each step = the bounded sample, value extrapolated",
                              "full_job_extrapolated_s": res["t_full_extrapolated_s"]},
             "e2e": {"value": value, "unit": "atom*frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -340,9 +341,23 @@ def run_ours(args):
         ach = bytes_stage[k] / (mean[k] * 1e-3) / 1e9 if mean[k] > 0 else 0.0
         stages[k] = {"kernel": kernels[k], "ms": mean[k], "achieved_GBps": ach, "frac_of_hbm": ach / hbm}
     stages["exchange"] = {"kernel": "nccl all_to_all_single" if world > 1 else "none", "ms": mean["exchange"]}
+    # DRAM traffic of the dominant kernels from `ncu --set full` captures of smaller launches of the same
+    # kernels (profiles/r01_ncu_*.jsonl), scaled linearly to this launch: bytes per series / per frame
+    ncu_traffic = {"spectra": (0.985820672e9 + 1.042886e9) / 296.0 * s_loc,           # 296 series captured
+                   "project": (1.077133e9 + 2.219636e9) / 4096.0 * tl,               # 4096 frames captured
+                   "contract": (2.016264e9 + 1.960431e9) / 4096.0 * tl}
+    # fp64 view of the spectrum stage: 157 k warp-level fp64 instructions per (series, window) item (ncu
+    # instruction mix) against the measured 64 lanes/clk/SM (tools/micro/fp64_rate.cu: 18.3 T lane-ops/s)
+    fp64_lane_ops = 157.0e3 * 32 * npieces * s_loc
+    fp64 = {"lane_ops": fp64_lane_ops, "achieved_Tops": fp64_lane_ops / (mean["spectra"] * 1e-3) / 1e12 if mean["spectra"] else 0.0,
+            "peak_Tops": 18.3, "peak_source": "measured, tools/micro/fp64_rate.cu (DFMA/DADD/DMUL, 63.6 of 64 lanes/clk/SM)"}
+    fp64["frac"] = fp64["achieved_Tops"] / fp64["peak_Tops"]
     dom = max(("project", "contract", "spectra"), key=lambda k: mean[k])
     roofline = {"kernel": kernels[dom], "bound": "hbm", "achieved": stages[dom]["achieved_GBps"], "peak": hbm,
-                "unit": "GB/s", "frac": stages[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": stages[dom]["frac_of_hbm"], "traffic": ncu_traffic[dom],
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture of a smaller launch "
+                                "(profiles/r01_ncu_*.jsonl), scaled linearly to this launch", "algorithmic_bytes": bytes_stage[dom],
+                "fp64": fp64 if dom == "spectra" else None, "peak_source": peak_src,
                 "share_of_step": mean[dom] / max(sum(mean.values()), 1e-9),
                 "note": "algorithmic bytes per launch / CUDA-event duration of the stage on rank 0; "
                         "the FFT-spectrum kernel is fp64-FMA limited before it is HBM limited (DESIGN.md)"}
@@ -365,13 +380,14 @@ def run_ours(args):
         eig_sub = eig[q_idx].cpu().numpy()
         res = cpu_sample(wl, vsub, eig_sub, q_idx, args.cpu_series, frames)
         line["cpu_baseline"] = {
-            "value": res["value"], "unit": "atom*frames/s", "cores": os.cpu_count(), "kind": "port", "host_cores": os.cpu_count(),
+            "value": res["value"], "unit": "atom*frames/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
             "sample": f"projection of {args.cpu_frames} frames x {wl['n_atoms']} atoms onto {len(q_idx)} q "
                       f"({res['t_proj_sample_s']:.2f} s) + contraction ({res['t_phonon_sample_s']:.3f} s) + FFT spectra of "
                       f"{args.cpu_series} series of {frames} samples ({res['t_fft_sample_s']:.2f} s); scaled linearly "
                       "to the full job (extrapolated)",
             "full_job_extrapolated_s": res["t_full_extrapolated_s"],
-            "note": "oracle port = the reference's numpy projection / np.correlate+np.fft spectrum; Python-level loops are serial as in the reference, numpy/BLAS threading left at its default (all cores)"}
+            "note": "oracle port = the reference's numpy projection / np.correlate+np.fft spectrum; this path is serial "
+                    "numpy in the reference (no OpenMP), so one host thread does the work"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
