@@ -361,7 +361,11 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
     int threads = dp::pick_threads(Nx, Ny, Nz, Q, per_sm >= 2 ? 320 : 512);
     if (threads > 320) per_sm = 1;
     int64_t nunits = T * (int64_t)jobs.size();
-    int grid = (int)dp::imin<int64_t>(nunits, (int64_t)dp::imax(dp::sm_count(), 1) * per_sm);
+    // DP_RESERVE_SMS: leave some SMs to a concurrently running collective (the chunked all-to-all of the
+    // multi-GPU pipeline); a persistent grid that fills every SM would make the NCCL kernel wait or be waited for
+    int sms = dp::imax(dp::sm_count(), 1);
+    if (getenv("DP_RESERVE_SMS")) sms = dp::imax(sms - atoi(getenv("DP_RESERVE_SMS")), 1);
+    int grid = (int)dp::imin<int64_t>(nunits, (int64_t)sms * per_sm);
     if (per_sm >= 2 && threads <= 256) {
         auto k = dp::project_fft_kernel<256, 2>;
         DP_CUDA_OK(DP_SET_SMEM(k, smem));

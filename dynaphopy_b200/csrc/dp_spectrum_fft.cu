@@ -365,6 +365,8 @@ int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_
         dp::S2Params p;
         p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;
         p.tb_len = (int)tb_len; p.tb_stride = tb_stride; p.S = S; p.npieces = npieces;
+        p.tb_shift = -1;
+        if (tb_len > 0 && (tb_len & (tb_len - 1)) == 0) { p.tb_shift = 0; while ((1LL << p.tb_shift) < tb_len) p.tb_shift++; }
         p.starts = (const int*)(ws + lay.off_starts);
         p.pl = pl.s2;
         p.g_tables = tw[0]; p.g_twL = tw[5];

@@ -51,6 +51,7 @@ struct S2Params {
     const cplx* series;
     int64_t stride_s, stride_t;    // element strides of the series index and of time
     int tb_len;                    // 0: plain time axis, else time is blocked ...
+    int tb_shift;                  // log2(tb_len) when it is a power of two (no integer division), else -1
     int64_t tb_stride;             // ... block b = t / tb_len starts at b * tb_stride
     int S, npieces;
     const int* starts;
@@ -90,7 +91,7 @@ __device__ __forceinline__ S2Smem s2_carve(cplx* smem) {
 
 __device__ __forceinline__ int64_t s2_time_offset(const S2Params& p, int t) {
     if (p.tb_len == 0) return (int64_t)t * p.stride_t;
-    const int b = t / p.tb_len;
+    const int b = p.tb_shift >= 0 ? (t >> p.tb_shift) : t / p.tb_len;
     return (int64_t)b * p.tb_stride + (int64_t)(t - b * p.tb_len) * p.stride_t;
 }
 

@@ -204,9 +204,46 @@ class MeshPipeline:
 
     def run(self, velocity_local, chunk_frames=4096):
         """Whole step on device-resident local frames; returns the (F, S_local) spectra of this rank."""
+        if self.world > 1 and self.be.shape(velocity_local)[0] % chunk_frames == 0 and hasattr(velocity_local, "device"):
+            return self.spectra_series(self.series_exchanged(velocity_local, chunk_frames))
         send = self.series(velocity_local, chunk_frames)
         blocks = self.exchange_series(send)
         return self.spectra_series(blocks)
+
+    def series_exchanged(self, velocity_local, chunk_frames=4096):
+        """Multi-rank path with the exchange hidden behind the projection: every time chunk is projected and
+        contracted into a (G, S_loc, Tc) send slot and handed to an asynchronous all-to-all (NCCL runs it on
+        its own stream) while the next chunk is being computed.  Returns the received blocks
+        ``(G*n_chunks, S_loc, Tc)``: block (g, c) holds samples [c*Tc, (c+1)*Tc) of source rank g's time
+        block -- consecutive time blocks, which the spectrum kernel reads in place."""
+        import torch
+        import torch.distributed as dist
+        be = self.be
+        tl = be.shape(velocity_local)[0]
+        assert tl % chunk_frames == 0, "local frame count must be a multiple of the chunk length"
+        nch, tc, g, s_loc = tl // chunk_frames, chunk_frames, self.world, self.q_block * self.M
+        send = be.empty((2, g, s_loc, tc), np.complex128)
+        recv = be.empty((g, nch, s_loc, tc), np.complex128)
+        pending = [None, None]
+        as_t = (lambda x: x) if torch.is_tensor(send) else torch.from_numpy      # numpy back-end of the test-suite
+        send_t, recv_t = as_t(send), as_t(recv)
+        for c in range(nch):
+            slot = c % 2
+            if pending[slot] is not None:
+                pending[slot].wait()                     # the slot's previous message has left
+            self.series(velocity_local[c * tc:(c + 1) * tc], chunk_frames, out=send[slot])
+            if dist.get_backend(self.group) == "nccl":
+                outs = [torch.view_as_real(recv_t[src, c]) for src in range(g)]
+                ins = [torch.view_as_real(send_t[slot, dst]) for dst in range(g)]
+                pending[slot] = dist.all_to_all(outs, ins, group=self.group, async_op=True)
+            else:                                        # gloo (CPU tests): no list all-to-all; same data movement
+                tmp = torch.empty_like(send_t[slot])
+                dist.all_to_all_single(torch.view_as_real(tmp), torch.view_as_real(send_t[slot]), group=self.group)
+                recv_t[:, c] = tmp
+        for w in pending:
+            if w is not None:
+                w.wait()
+        return recv.reshape(g * nch, s_loc, tc)
 
     # -- host-resident trajectory: chunked H2D copies overlapped with the projection ------------------
     def run_from_host(self, velocity_host, chunk_frames=2048):

@@ -116,6 +116,11 @@ def _rank_main(rank, world, port_no, out_dir):
     # (the two paths may pick different projection kernels: equal up to rounding, not bitwise)
     assert relerr(ps, ps_tm) < 1e-12
     assert relerr(blocks.transpose(0, 2, 1).reshape(series.shape), series) < 1e-12
+    # overlapped path: chunked asynchronous all-to-all, (G*n_chunks, S_loc, Tc) time blocks
+    blocks3 = pipe.series_exchanged(np.ascontiguousarray(v_local), chunk_frames=tl // 2)
+    assert tuple(blocks3.shape) == (world * 2, pipe.q_block * pipe.M, tl // 2)
+    ps3 = pipe.spectra_series(blocks3)
+    assert relerr(ps3, ps) < 1e-12
     np.save(os.path.join(out_dir, f"ps{rank}.npy"), ps)
     np.save(os.path.join(out_dir, f"series{rank}.npy"), series)
     dist.barrier()
