@@ -279,11 +279,11 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
     l.off_dx = o;     o += align_up((size_t)F * sizeof(double), 256);
     l.off_den = o;    o += align_up((size_t)F * sizeof(double), 256);
     l.off_spec = o;   o += align_up((size_t)S * pl.starts.size() * pl.nkeep * sizeof(double), 256);
-    int64_t items = (int64_t)S * (int64_t)pl.starts.size();
+    int64_t items = (int64_t)S * (int64_t)(pl.use_v2 ? (pl.starts.size() + 1) / 2 : pl.starts.size());
     l.nslots = (int)imin<int64_t>(items, (int64_t)imax(sm_count(), 1));
     if (getenv("DP_S2_GRID") && atoi(getenv("DP_S2_GRID")) > 0)      // development aid: fewer persistent CTAs
         l.nslots = (int)imin<int64_t>(l.nslots, atoi(getenv("DP_S2_GRID")));
-    l.slab_elems = pl.use_v2 ? (size_t)pl.P : (size_t)pl.P + pl.L;
+    l.slab_elems = pl.use_v2 ? (size_t)pl.P + (size_t)pl.P / 2 : (size_t)pl.P + pl.L;   // v2: A[P] complex + Sr[P] real
     l.off_scratch = o; o += align_up((size_t)l.nslots * l.slab_elems * sizeof(cplx), 256);
     l.total = o;
     return l;
@@ -374,6 +374,7 @@ int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_
         p.spec = spec; p.lo = pl.lo; p.nkeep = pl.nkeep;
         p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
         p.skip_mask = getenv("DP_S2_SKIP") ? atoi(getenv("DP_S2_SKIP")) : 0;
+        p.pair = (npieces >= 2 && !(getenv("DP_S2_PAIR") && atoi(getenv("DP_S2_PAIR")) == 0)) ? 1 : 0;
         auto k = dp::spectrum2_kernel;
         DP_CUDA_OK(DP_SET_SMEM(k, dp::S2_SMEM_BYTES));
         DP_LAUNCH(k, dim3(lay.nslots), dim3(dp::S2_THREADS), dp::S2_SMEM_BYTES, st, p);

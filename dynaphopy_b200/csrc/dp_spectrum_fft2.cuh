@@ -27,7 +27,7 @@ constexpr int S2_THREADS = DP_S2_THREADS;          // 8 warps x <= 255 registers
 constexpr int S2_WARPS = S2_THREADS / 32;
 constexpr int S2_BINSLOTS = 8;                    // bins per residue thread in pass 4
 constexpr int S2_TILE_COLS = S2_THREADS / 16;     // pass-4 column tile: 16 threads per column
-constexpr int S2_NP_MAX = 240;                    // largest n1' of the menu
+constexpr int S2_NP_MAX = 192;                    // largest n1' of the menu
 constexpr int S2_CPITCH = S2_TILE_COLS + 1;       // odd pitch (in 16-byte elements)
 
 typedef SubCfg<16, 1, 1> C16;
@@ -38,7 +38,7 @@ typedef SubCfg<16, 16, 16> C256;
 
 // mixed-radix menu for n1' (pass 4): all with 16 lanes per column
 #define DP_S2_MIXED_MENU(X) \
-    X(16, 15) X(16, 12) X(16, 10) X(15, 10) X(16, 9) X(16, 8) X(12, 10) X(10, 10) X(16, 6) X(16, 5) \
+    X(16, 12) X(16, 10) X(15, 10) X(16, 9) X(16, 8) X(12, 10) X(10, 10) X(16, 6) X(16, 5) \
     X(8, 8) X(10, 5) X(8, 5) X(8, 4) X(5, 5) X(4, 4)
 
 struct S2Plan {
@@ -64,6 +64,7 @@ struct S2Params {
     int lo, nkeep;
     double dt, acf_scale;
     int skip_mask;                 // development aid (DP_S2_SKIP): bit i set = skip pass i+1
+    int pair;                      // 1: process the windows of a series two at a time (see spectrum2_kernel)
 };
 
 struct S2Smem {
@@ -137,12 +138,16 @@ __device__ __forceinline__ void s2_st_slab(cplx* ptr, cplx v, unsigned long long
 }
 
 // ---- pass 1: window -> column FFTs -> A -----------------------------------------------------------
-template <class C>
+// LAYOUT 0: time axis contiguous (stride_t == 1, no blocks) -- plain pointer arithmetic in the unrolled loads;
+// 1: contiguous power-of-two time blocks (the all-to-all's receive layout); 2: anything else.
+template <class C, int LAYOUT>
 __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict__ x, int t0, cplx* __restrict__ A,
                                       int warp, int lane) {
     S2_SMEM_HERE();
     const unsigned long long pol = s2_slab_policy();
     const int n2 = p.pl.n2, L = p.pl.L;
+    const int tb_shift = p.tb_shift;
+    const int64_t tb_stride = p.tb_stride;
     const int seq = lane % C::NS, g = lane / C::NS;
     cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
@@ -153,7 +158,15 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
 #pragma unroll
             for (int a = 0; a < C::R1; a++) {
                 const int idx = (a * C::R2 + g + C::TG * i) * n2 + col;
-                w[i * C::R1 + a] = idx < L ? __ldcs(x + s2_time_offset(p, t0 + idx)) : make_double2(0.0, 0.0);
+                cplx val = make_double2(0.0, 0.0);
+                if (idx < L) {
+                    if (LAYOUT == 0) val = __ldcs(x + t0 + idx);
+                    else if (LAYOUT == 1) {
+                        const int t = t0 + idx, b = t >> tb_shift;
+                        val = __ldcs(x + (int64_t)b * tb_stride + (t - (b << tb_shift)));
+                    } else val = __ldcs(x + s2_time_offset(p, t0 + idx));
+                }
+                w[i * C::R1 + a] = val;
             }
     };
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
@@ -178,8 +191,12 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
 }
 
 // ---- pass 2: rows: FFT -> |.|^2 -> FFT (DIF) -> twiddle, in place ------------------------------------
-template <class C>
-__device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, int warp, int lane) {
+// MODE 0: single window.  Paired windows (two windows of one series share the second half of the pipeline,
+// see spectrum2_kernel): MODE 1 = first window, rows FFT -> |X|^2 parked as REAL values in Sr (digit order);
+// MODE 2 = second window, rows FFT -> |X|^2, z = Sr + i |X|^2, FFT (DIF) -> twiddle -> A.
+template <class C, int MODE>
+__device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, double* __restrict__ Sr, int warp,
+                                      int lane) {
     S2_SMEM_HERE();
     const unsigned long long pol = s2_slab_policy();
     const int n1 = p.pl.n1, n2 = p.pl.n2;
@@ -198,9 +215,31 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, i
         cplx* __restrict__ Ar = A + (size_t)row * n2;
         cplx v[16];
         load_tile(tile, v);
-        sub_dit<C>(v, E, sm.T2, g);
+        double sa[16];
+        double* __restrict__ Srow = Sr + (size_t)row * n2;
+        if (MODE == 2) {                       // |X_a|^2 of the partner window, requested before the butterflies
 #pragma unroll
-        for (int r = 0; r < C::NB2 * C::R2; r++) v[r] = make_double2(v[r].x * v[r].x + v[r].y * v[r].y, 0.0);
+            for (int i = 0; i < C::NB2; i++)
+#pragma unroll
+                for (int k2 = 0; k2 < C::R2; k2++) sa[i * C::R2 + k2] = __ldcg(Srow + g + C::TG * i + C::R1 * k2);
+        }
+        sub_dit<C>(v, E, sm.T2, g);
+        if (MODE == 1) {
+#pragma unroll
+            for (int i = 0; i < C::NB2; i++)
+#pragma unroll
+                for (int k2 = 0; k2 < C::R2; k2++) {
+                    const cplx x = v[i * C::R2 + k2];
+                    __stcg(Srow + g + C::TG * i + C::R1 * k2, x.x * x.x + x.y * x.y);
+                }
+            __syncwarp();
+            continue;
+        }
+#pragma unroll
+        for (int r = 0; r < C::NB2 * C::R2; r++) {
+            const double sb = v[r].x * v[r].x + v[r].y * v[r].y;
+            v[r] = MODE == 2 ? make_double2(sa[r], sb) : make_double2(sb, 0.0);
+        }
         __syncwarp();
         sub_dif<C>(v, E, sm.T2f, g);
         // four-step twiddle w_P^(row*k), k = d*R2 + c: geometric in d
@@ -221,7 +260,9 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, i
 
 // ---- pass 3: column FFTs -> conj -> lags 0..half of the autocorrelation, in place ------------------------
 // r[kappa] lands at A[kappa]: a warp overwrites only rows of the columns it has just read.
-template <class C>
+// PAIRED: A holds Y = FFT_P(|X_a|^2 + i |X_b|^2); rho[kappa] = r_a[kappa] + i r_b[kappa] = Y[-kappa] / P, so the
+// lags -half..half are Y at indices 0..half and P-half..P-1 (no conjugation, no Hermitian shortcut).
+template <class C, bool PAIRED>
 __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, int warp, int lane) {
     S2_SMEM_HERE();
     const unsigned long long pol = s2_slab_policy();
@@ -248,7 +289,12 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
 #pragma unroll
             for (int k2 = 0; k2 < C::R2; k2++) {
                 const int kap = (g + C::TG * i + C::R1 * k2) * n2 + col;
-                if (kap <= half) s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, -v[i * C::R2 + k2].y * sc), pol);
+                if (PAIRED) {
+                    if (kap <= half || kap >= p.pl.P - half)
+                        s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, v[i * C::R2 + k2].y * sc), pol);
+                } else if (kap <= half) {
+                    s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, -v[i * C::R2 + k2].y * sc), pol);
+                }
             }
     }
 }
@@ -260,7 +306,9 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
 // the radix-m2 butterfly.  Bin phase: thread r < n1' owns the kept bins k = k_lo + r + n1'*b (all of
 // residue (k_lo + r) mod n1', so one tile value feeds up to S2_BINSLOTS bins) and advances Horner's rule
 //   X_k <- X_k * z_k + C_col[k mod n1'],  z_k = w_L^k,  over the columns in descending order.
-template <class C>
+// PAIRED: a[m] = rho[m - half] = Y[(half - m) mod P]; the Horner sums give FFT_L(a_a) + i FFT_L(a_b), which are
+// separated at the end (each is real up to the phase w_L^(half k) and, for even L, the unpaired lag -L/2).
+template <class C, bool PAIRED>
 __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict__ R, double* __restrict__ spec,
                                       int tid) {
     S2_SMEM_HERE();
@@ -276,8 +324,12 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
 #pragma unroll
             for (int a = 0; a < R1; a++) {
                 const int kap = (a * R2 + g) * n2L + col - half;
-                v[a] = s2_ld_slab(R + (kap >= 0 ? kap : -kap), pol);
-                if (kap < 0) v[a].y = -v[a].y;                     // negative lag: conj(r[-kappa])
+                if (PAIRED) {
+                    v[a] = s2_ld_slab(R + (kap > 0 ? p.pl.P - kap : -kap), pol);      // Y[-kappa]
+                } else {
+                    v[a] = s2_ld_slab(R + (kap >= 0 ? kap : -kap), pol);
+                    if (kap < 0) v[a].y = -v[a].y;                 // negative lag: conj(r[-kappa])
+                }
             }
         } else {
 #pragma unroll
@@ -335,11 +387,61 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
             }
         }
     }
+    if (!PAIRED) {
 #pragma unroll
-    for (int b = 0; b < S2_BINSLOTS; b++)
-        if (b < nbins) spec[tid + NP * b] = __dmul_rn(hypot(acc[b].x, acc[b].y), p.dt);
+        for (int b = 0; b < S2_BINSLOTS; b++)
+            if (b < nbins) spec[tid + NP * b] = __dmul_rn(hypot(acc[b].x, acc[b].y), p.dt);
+    } else {
+        // Im r_a[-L/2], Im r_b[-L/2] from rho[-half] = Y[half], rho[+half] = Y[P - half] (even L only)
+        double Ia = 0.0, Ib = 0.0;
+        if ((L & 1) == 0) {
+            const cplx rm = s2_ld_slab(R + half, pol), rp = s2_ld_slab(R + p.pl.P - half, pol);
+            Ia = 0.5 * (rm.y - rp.y);
+            Ib = 0.5 * (rp.x - rm.x);
+        }
+        double* __restrict__ spec_b = spec + p.nkeep;             // the pair's second window
+#pragma unroll
+        for (int b = 0; b < S2_BINSLOTS; b++) {
+            if (b < nbins) {
+                const int k = (k_lo + tid + NP * b) % L;
+                const cplx ph = __ldg(p.g_twL + (int)(((int64_t)half * k) % L));      // w_L^(half k)
+                const cplx wt = cmulc(acc[b], ph);                                     // remove the phase
+                const double sgn = (k & 1) ? -1.0 : 1.0;
+                spec[tid + NP * b] = __dmul_rn(hypot(wt.x + sgn * Ib, Ia), p.dt);
+                spec_b[tid + NP * b] = __dmul_rn(hypot(wt.y - sgn * Ia, Ib), p.dt);
+            }
+        }
+    }
 }
 
+#define DP_S2_PASS1_L(xptr, t0v, LAY)                                               \
+    switch (p.pl.n1) {                                                              \
+        case 16: s2_pass1<C16, LAY>(p, xptr, t0v, A, warp, lane); break;            \
+        case 32: s2_pass1<C32, LAY>(p, xptr, t0v, A, warp, lane); break;            \
+        case 64: s2_pass1<C64, LAY>(p, xptr, t0v, A, warp, lane); break;            \
+        case 128: s2_pass1<C128, LAY>(p, xptr, t0v, A, warp, lane); break;          \
+        default: s2_pass1<C256, LAY>(p, xptr, t0v, A, warp, lane); break;           \
+    }
+#define DP_S2_PASS1(xptr, t0v)                                                      \
+    if (layout == 0) { DP_S2_PASS1_L(xptr, t0v, 0) }                                \
+    else if (layout == 1) { DP_S2_PASS1_L(xptr, t0v, 1) }                           \
+    else { DP_S2_PASS1_L(xptr, t0v, 2) }
+#define DP_S2_PASS2(MODE)                                                           \
+    if (p.pl.n2 == 64) s2_pass2<C64, MODE>(p, A, Sr, warp, lane);                   \
+    else s2_pass2<C256, MODE>(p, A, Sr, warp, lane);
+#define DP_S2_PASS3(PAIRED)                                                         \
+    switch (p.pl.n1) {                                                              \
+        case 16: s2_pass3<C16, PAIRED>(p, A, warp, lane); break;                    \
+        case 32: s2_pass3<C32, PAIRED>(p, A, warp, lane); break;                    \
+        case 64: s2_pass3<C64, PAIRED>(p, A, warp, lane); break;                    \
+        case 128: s2_pass3<C128, PAIRED>(p, A, warp, lane); break;                  \
+        default: s2_pass3<C256, PAIRED>(p, A, warp, lane); break;                   \
+    }
+
+// Items: (series, pair of consecutive windows).  Two windows of one series share everything after the
+// forward transforms: |X_a|^2 + i |X_b|^2 goes through ONE second transform, one column pass and one bin
+// evaluation (the two autocorrelations are Hermitian, so their transforms separate exactly) -- 3/4 of the
+// row work and 1/2 of passes 3-4.  An odd last window runs the single-window passes.
 __global__ void __launch_bounds__(S2_THREADS, 1)
 spectrum2_kernel(const __grid_constant__ S2Params p) {
     S2_SMEM_HERE();
@@ -347,48 +449,68 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
     for (int k = tid; k < 6 * 256; k += S2_THREADS) sm.T1[k] = p.g_tables[k];
     __syncthreads();
     cplx* A = p.scratch + (size_t)blockIdx.x * p.slab_elems;
-    const int64_t nitems = (int64_t)p.S * p.npieces;
+    double* Sr = reinterpret_cast<double*>(A + p.pl.P);            // [P] real: |X_a|^2 of a pair's first window
+    const int layout = p.stride_t != 1 ? 2 : (p.tb_len == 0 ? 0 : (p.tb_shift >= 0 ? 1 : 2));
+    const int npairs = p.pair ? (p.npieces + 1) / 2 : p.npieces;
+    const int64_t nitems = (int64_t)p.S * npairs;
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int pc = (int)(item / p.S), s = (int)(item % p.S);
+        const int pj = (int)(item / p.S), s = (int)(item % p.S);
+        const int w0 = p.pair ? 2 * pj : pj;
+        const bool paired = p.pair && (w0 + 1 < p.npieces);
         const cplx* x = p.series + (int64_t)s * p.stride_s;
-        const int t0 = p.starts[pc];
-        if (!(p.skip_mask & 1)) switch (p.pl.n1) {
-            case 16: s2_pass1<C16>(p, x, t0, A, warp, lane); break;
-            case 32: s2_pass1<C32>(p, x, t0, A, warp, lane); break;
-            case 64: s2_pass1<C64>(p, x, t0, A, warp, lane); break;
-            case 128: s2_pass1<C128>(p, x, t0, A, warp, lane); break;
-            default: s2_pass1<C256>(p, x, t0, A, warp, lane); break;
-        }
-        __syncthreads();
-        if (p.skip_mask & 2) {}
-        else if (p.pl.n2 == 64) s2_pass2<C64>(p, A, warp, lane);
-        else s2_pass2<C256>(p, A, warp, lane);
-        __syncthreads();
-        if (!(p.skip_mask & 4)) switch (p.pl.n1) {
-            case 16: s2_pass3<C16>(p, A, warp, lane); break;
-            case 32: s2_pass3<C32>(p, A, warp, lane); break;
-            case 64: s2_pass3<C64>(p, A, warp, lane); break;
-            case 128: s2_pass3<C128>(p, A, warp, lane); break;
-            default: s2_pass3<C256>(p, A, warp, lane); break;
-        }
-        __syncthreads();
-        // the next item's window starts its way from HBM to L2 now (time-contiguous layouts only)
-        if (item + gridDim.x < nitems && p.stride_t == 1 && !(p.skip_mask & 16)) {
-            const int64_t nxt = item + gridDim.x;
-            const cplx* xn = p.series + (int64_t)(nxt % p.S) * p.stride_s;
-            const int tn = p.starts[(int)(nxt / p.S)];
-            for (int i = tid * 8; i < p.pl.L; i += S2_THREADS * 8) s2_prefetch_l2(xn + s2_time_offset(p, tn + i));
-        }
-        double* spec = p.spec + ((size_t)s * p.npieces + pc) * p.nkeep;
-        if (!(p.skip_mask & 8)) switch (p.pl.m1 * 32 + p.pl.m2) {
-#define DP_S2_CASE(a, b) case (a) * 32 + (b): s2_pass4<SubCfg<a, b, 16>>(p, A, spec, tid); break;
-            DP_S2_MIXED_MENU(DP_S2_CASE)
+        double* spec = p.spec + ((size_t)s * p.npieces + w0) * p.nkeep;
+        // the next item's first window starts its way from HBM to L2 (time-contiguous layouts only)
+        auto prefetch_next = [&]() {
+            if (item + gridDim.x < nitems && p.stride_t == 1) {
+                const int64_t nxt = item + gridDim.x;
+                const cplx* xn = p.series + (int64_t)(nxt % p.S) * p.stride_s;
+                const int tn = p.starts[p.pair ? 2 * (int)(nxt / p.S) : (int)(nxt / p.S)];
+                for (int i = tid * 8; i < p.pl.L; i += S2_THREADS * 8) s2_prefetch_l2(xn + s2_time_offset(p, tn + i));
+            }
+        };
+        if (!paired) {
+            if (!(p.skip_mask & 1)) { DP_S2_PASS1(x, p.starts[w0]) }
+            __syncthreads();
+            if (!(p.skip_mask & 2)) { DP_S2_PASS2(0) }
+            __syncthreads();
+            if (!(p.skip_mask & 4)) { DP_S2_PASS3(false) }
+            __syncthreads();
+            prefetch_next();
+            if (!(p.skip_mask & 8)) switch (p.pl.m1 * 32 + p.pl.m2) {
+#define DP_S2_CASE(a, b) case (a) * 32 + (b): s2_pass4<SubCfg<a, b, 16>, false>(p, A, spec, tid); break;
+                DP_S2_MIXED_MENU(DP_S2_CASE)
 #undef DP_S2_CASE
-            default: break;
+                default: break;
+            }
+        } else {
+            if (!(p.skip_mask & 1)) { DP_S2_PASS1(x, p.starts[w0]) }
+            __syncthreads();
+            // the pair's second window is needed right after this pass: bring it to L2 now
+            if (p.stride_t == 1)
+                for (int i = tid * 8; i < p.pl.L; i += S2_THREADS * 8) s2_prefetch_l2(x + s2_time_offset(p, p.starts[w0 + 1] + i));
+            if (!(p.skip_mask & 2)) { DP_S2_PASS2(1) }
+            __syncthreads();
+            if (!(p.skip_mask & 1)) { DP_S2_PASS1(x, p.starts[w0 + 1]) }
+            __syncthreads();
+            if (!(p.skip_mask & 2)) { DP_S2_PASS2(2) }
+            __syncthreads();
+            if (!(p.skip_mask & 4)) { DP_S2_PASS3(true) }
+            __syncthreads();
+            prefetch_next();
+            if (!(p.skip_mask & 8)) switch (p.pl.m1 * 32 + p.pl.m2) {
+#define DP_S2_CASE(a, b) case (a) * 32 + (b): s2_pass4<SubCfg<a, b, 16>, true>(p, A, spec, tid); break;
+                DP_S2_MIXED_MENU(DP_S2_CASE)
+#undef DP_S2_CASE
+                default: break;
+            }
         }
         __syncthreads();
     }
 }
+#undef DP_S2_PASS1
+#undef DP_S2_PASS1_L
+#undef DP_S2_PASS2
+#undef DP_S2_PASS3
 
 // ---- host planning ---------------------------------------------------------------------------------------
 static inline void s2_radices(int n, int* r1, int* r2) {       // the SubCfg used for a power-of-two length

@@ -272,7 +272,10 @@ def _series(rng, nt, ns, dt):
                                             (3000, 0.001, 0.05, 25.0),      # cfg 4 (Ag2Cu2O4)
                                             (1201, 0.002, 2.0, 40.0),       # L = 250, 5 windows, odd T
                                             (700, 0.001, 3.0, 60.0),        # odd L = 333, grid beyond Nyquist? no: clamps
-                                            (640, 0.002, 1.7, 300.0)])      # grid far beyond +Nyquist (np.interp clamps)
+                                            (640, 0.002, 1.7, 300.0),       # grid far beyond +Nyquist (np.interp clamps)
+                                            (2000, 0.001, 8.0 / 3.0, 60.0),  # odd L = 375, 6 windows: paired windows, no lag -L/2
+                                            (4000, 0.001, 1.0, 40.0),        # even L = 1000, 4 windows: two pairs
+                                            (2300, 0.002, 1.0, 40.0)])       # L = 500, 5 windows: two pairs + a single
 def test_power_fft_vs_oracle(kops, nt, dt, res, fmax):
     rng = np.random.default_rng(nt)
     ns = 3 if not is_cuda(kops) else 12

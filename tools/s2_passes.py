@@ -19,6 +19,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     b.record(); torch.cuda.synchronize()
     print("skip=%s  %.3f ms" % (os.environ.get("DP_S2_SKIP", "0"), a.elapsed_time(b) / 3), flush=True)
 else:
-    for mask in (0, 1, 2, 4, 8, 14, 13, 11, 7, 15):
+    for mask in [int(m) for m in os.environ.get("S2_MASKS", "0,1,2,4,8,14,13,11,7,15").split(",")]:
         env = dict(os.environ, DP_S2_SKIP=str(mask))
         subprocess.run([sys.executable, __file__, "child"], env=env)
