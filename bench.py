@@ -259,16 +259,19 @@ def run_ours(args):
         for ci, t0 in enumerate(range(0, tl, CH)):
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a.record()
-            vc = ops.project_commensurate(v[t0:t0 + CH], plan.dims, plan.unit_type, plan.n_prim, pipe.d_qbin, None)
+            vc = ops.project_commensurate(v[t0:t0 + CH], plan.dims, plan.unit_type, plan.n_prim, pipe.d_qbin, None,
+                                          pair_major=True)
             b.record()
             if world == 1:
-                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send, t_offset=t0, t_total=tl)
+                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send, t_offset=t0, t_total=tl,
+                                          pair_major=True)
                 c.record()
             else:
                 slot = ci % 2
                 if pending[slot] is not None:
                     pending[slot].wait()
-                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send2[slot], t_total=CH)
+                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send2[slot], t_total=CH,
+                                          pair_major=True)
                 c.record()
                 outs = [torch.view_as_real(recv[src, ci]) for src in range(world)]
                 ins = [torch.view_as_real(send2[slot, dst]) for dst in range(world)]

@@ -27,6 +27,8 @@ SIGNATURES = {
     "dp_project_wave_vector": (_I, [_P, _I, _P, _P, _P, _I, _I, _L, _P, _I, _I, _P, _P, _Z, _P]),
     "dp_project_commensurate_workspace_bytes": (_Z, [_P, _I, _I, _I]),
     "dp_project_commensurate": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _I, _I, _P, _P, _Z, _P]),
+    "dp_project_commensurate_ex": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    "dp_project_phonon_series_ex": (_I, [_P, _I, _P, _L, _I, _I, _I, _L, _L, _P, _P]),
     "dp_project_phonon": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "dp_project_phonon_blocked": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
     "dp_project_phonon_series": (_I, [_P, _P, _L, _I, _I, _I, _L, _L, _P, _P]),
@@ -42,6 +44,8 @@ SIGNATURES = {
     "dp_fft_c2c": (_I, [_P, _P, _I, _I, _I, _P, _Z, _P]),
 }
 
+DP_VC_ROWS = 0
+DP_VC_PAIRS = 1
 DP_CORR_WEIGHT_REFERENCE = 0
 DP_CORR_WEIGHT_INTENDED = 1
 

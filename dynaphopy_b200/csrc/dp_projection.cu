@@ -151,7 +151,8 @@ constexpr int PS_QT_MAX = 16;       // wave vectors per CTA (fewer for wide M: s
 template <int MT>   // MT > 0: compile-time M (inputs kept in registers); 0: any M
 __global__ void __launch_bounds__(256)
 project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig, int64_t T, int Q, int Mdyn,
-                             int q_block, int qt, int64_t t_offset, int64_t T_total, cplx* __restrict__ out) {
+                             int q_block, int qt, int vc_pairs, int64_t t_offset, int64_t T_total,
+                             cplx* __restrict__ out) {
     DP_DYNSMEM(cplx, sm);
     const int M = MT > 0 ? MT : Mdyn;
     const int pitch = qt * M + 1;                   // odd: conflict-free column reads
@@ -161,11 +162,21 @@ project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict
     const int q0 = blockIdx.y * qt;
     const int nq = imin(qt, Q - q0);
     const int nthreads = blockDim.x, tid = threadIdx.x;
-    for (int e = tid; e < PS_TT * nq * M; e += nthreads) {
-        const int f = e / (nq * M), j = e % (nq * M);
-        cplx val = make_double2(0.0, 0.0);
-        if (t0 + f < T) val = __ldcs(vc + ((t0 + f) * Q + q0) * M + j);
-        in[f * pitch + j] = val;
+    if (!vc_pairs) {
+        for (int e = tid; e < PS_TT * nq * M; e += nthreads) {
+            const int f = e / (nq * M), j = e % (nq * M);
+            cplx val = make_double2(0.0, 0.0);
+            if (t0 + f < T) val = __ldcs(vc + ((t0 + f) * Q + q0) * M + j);
+            in[f * pitch + j] = val;
+        }
+    } else {                       // vc[t][slot pair][q][2]: runs of nq*2 contiguous values per (frame, pair)
+        const int np2 = M / 2, run = nq * 2;
+        for (int e = tid; e < PS_TT * np2 * run; e += nthreads) {
+            const int f = e / (np2 * run), r = e % (np2 * run), pr = r / run, w = r % run;
+            cplx val = make_double2(0.0, 0.0);
+            if (t0 + f < T) val = __ldcs(vc + (((t0 + f) * np2 + pr) * Q + q0) * 2 + w);
+            in[f * pitch + (w >> 1) * M + pr * 2 + (w & 1)] = val;
+        }
     }
     for (int e = tid; e < nq * M * M; e += nthreads) es[e] = __ldg(eig + (int64_t)q0 * M * M + e);
     __syncthreads();
@@ -306,6 +317,14 @@ int dp_project_phonon_blocked(const double* vc, const double* eig, int64_t T, in
 
 int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int Q, int M, int q_block,
                              int64_t t_offset, int64_t T_total, double* out, void* stream) {
+    return dp_project_phonon_series_ex(vc, DP_VC_ROWS, eig, T, Q, M, q_block, t_offset, T_total, out, stream);
+}
+
+int dp_project_phonon_series_ex(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M, int q_block,
+                                int64_t t_offset, int64_t T_total, double* out, void* stream) {
+    DP_REQUIRE(vc_layout == DP_VC_ROWS || (vc_layout == DP_VC_PAIRS && M % 2 == 0), DP_ERR_INVALID,
+               "dp_project_phonon_series: bad vc_layout %d (the pair-major layout needs an even M)", vc_layout);
+    const int vc_pairs = vc_layout == DP_VC_PAIRS;
     DP_REQUIRE((T == 0 || (vc && out)) && eig, DP_ERR_INVALID, "dp_project_phonon_series: null pointer");
     DP_REQUIRE(vc != out, DP_ERR_INVALID, "dp_project_phonon_series: cannot run in place (the output is transposed)");
     DP_REQUIRE(q_block > 0 && Q % q_block == 0, DP_ERR_INVALID, "dp_project_phonon_series: q_block=%d must divide Q=%d", q_block, Q);
@@ -326,7 +345,7 @@ int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int
         auto k = dp::project_phonon_series_kernel<MT>;                                                            \
         DP_CUDA_OK(DP_SET_SMEM(k, smem));                                                                         \
         DP_LAUNCH(k, grid, dim3(256), smem, st, (const dp::cplx*)vc, (const dp::cplx*)eig, T, Q, M, q_block,     \
-                  qt, t_offset, T_total, (dp::cplx*)out);                                                             \
+                  qt, vc_pairs, t_offset, T_total, (dp::cplx*)out);                                                             \
     } while (0)
     if (M == 6) DP_PS_LAUNCH(6);
     else if (M == 12) DP_PS_LAUNCH(12);

@@ -71,6 +71,7 @@ struct PfParams {
     const int2* qoff;        // (offset of bin m(q), offset of bin -m(q)) in the padded layout
     const cplx* tw;          // [Q][n_unit], or nullptr: no twiddle (raw lattice DFT of every unit atom)
     cplx* out;               // [T][Q][n_prim][3]
+    int pair_major;          // output layout: 0 = out[t][q][3*n_prim], 1 = out[t][slot pair][q][2]
     int skip;                // development aid (DP_PF_SKIP): 1 = no loads, 2 = no transforms, 4 = no epilogue
 };
 
@@ -183,9 +184,16 @@ project_fft_kernel(const __grid_constant__ PfParams p) {
         const PfJob job = sjobs[(int)(unit % p.njobs)];
         const double* __restrict__ vt = p.v + t * (int64_t)p.N * 3;
         PfUnit u;
-        u.outA = p.out + ((t * Q) * p.n_prim + job.pA) * 3 + job.kA;
-        u.outB = job.pB >= 0 ? p.out + ((t * Q) * p.n_prim + job.pB) * 3 + job.kB : nullptr;
-        u.qstride = (int64_t)p.n_prim * 3;
+        if (p.pair_major) {       // jobs are exactly the slot pairs (2j, 2j+1): [t][j][q][2], contiguous per job
+            const int j = (job.pA * 3 + job.kA) >> 1;
+            u.outA = p.out + ((t * (3 * p.n_prim / 2) + j) * Q) * 2;
+            u.outB = job.pB >= 0 ? u.outA + 1 : nullptr;
+            u.qstride = 2;
+        } else {
+            u.outA = p.out + ((t * Q) * p.n_prim + job.pA) * 3 + job.kA;
+            u.outB = job.pB >= 0 ? p.out + ((t * Q) * p.n_prim + job.pB) * 3 + job.kB : nullptr;
+            u.qstride = (int64_t)p.n_prim * 3;
+        }
         for (int term = 0; term < job.nterms; term++) {
             const PfTerm tm = sterms[job.term0 + term];
             u.srcA = tm.uA >= 0 ? vt + (int64_t)tm.uA * Nc * 3 + job.kA : nullptr;
@@ -262,6 +270,17 @@ size_t dp_project_commensurate_workspace_bytes(const int* dims, int n_unit, int 
 int dp_project_commensurate(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
                             int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
                             double* out_vc, void* workspace, size_t workspace_bytes, void* stream) {
+    return dp_project_commensurate_ex(v, dims, n_unit, unit_type, n_prim, T, qbin, twiddle, Q, project_on_atom,
+                                      DP_VC_ROWS, out_vc, workspace, workspace_bytes, stream);
+}
+
+int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
+                               int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
+                               int vc_layout, double* out_vc, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    DP_REQUIRE(vc_layout == DP_VC_ROWS || vc_layout == DP_VC_PAIRS, DP_ERR_INVALID, "dp_project_commensurate: bad vc_layout %d", vc_layout);
+    DP_REQUIRE(vc_layout == DP_VC_ROWS || (n_unit == n_prim && project_on_atom < 0 && (3 * n_prim) % 2 == 0), DP_ERR_INVALID,
+               "dp_project_commensurate: the pair-major layout needs one unit-cell atom per type, no atom filter and an even 3*n_prim");
     DP_REQUIRE((T == 0 || (v && out_vc)) && dims && unit_type && qbin && workspace, DP_ERR_INVALID,
                "dp_project_commensurate: null pointer");
     DP_REQUIRE(n_unit > 0 && n_prim > 0 && T >= 0 && Q > 0 && project_on_atom < n_prim, DP_ERR_INVALID,
@@ -354,7 +373,7 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
     dp::PfParams p;
     p.v = v; p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Px = Px; p.Nc = Nc; p.N = n_unit * Nc;
     p.n_unit = n_unit; p.n_prim = n_prim; p.Q = Q; p.njobs = (int)jobs.size(); p.nterms = (int)terms.size();
-    p.npad = Nz * Ny * Px; p.T = T;
+    p.npad = Nz * Ny * Px; p.T = T; p.pair_major = (vc_layout == DP_VC_PAIRS);
     p.skip = getenv("DP_PF_SKIP") ? atoi(getenv("DP_PF_SKIP")) : 0;
     p.jobs = d_jobs; p.terms = d_terms; p.qoff = d_qoff; p.tw = (const dp::cplx*)twiddle; p.out = (dp::cplx*)out_vc;
     int per_sm = (int)dp::imin<size_t>(2, dp::imax<size_t>(1, (size_t)(226 * 1024) / (smem + 1024)));

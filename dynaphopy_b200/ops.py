@@ -139,9 +139,12 @@ class Ops:
                       int(n_prim), T, _hptr(q), Q, int(project_on_atom), be.ptr(out), be.ptr(ws), nbytes, be.stream())
         return out
 
-    def project_commensurate(self, velocity, dims, unit_type, n_prim, qbin, twiddle, project_on_atom=-1, out=None):
+    def project_commensurate(self, velocity, dims, unit_type, n_prim, qbin, twiddle, project_on_atom=-1, out=None,
+                             pair_major=False):
         """3-D DFT projection: real (T,N,3) -> (T,Q,n_prim,3) complex128 for commensurate q.
-        ``out``: optional preallocated contiguous (T,Q,n_prim,3) destination (e.g. a time slice)."""
+        ``out``: optional preallocated contiguous (T,Q,n_prim,3) destination (e.g. a time slice).
+        ``pair_major``: write the intermediate layout (T, 3*n_prim/2, Q, 2) instead (DP_VC_PAIRS), to be
+        consumed by ``project_phonon_series(..., pair_major=True)``."""
         be = self.be
         v = be.asarray(velocity, np.float64)
         T, N, _ = be.shape(v)
@@ -154,12 +157,14 @@ class Ops:
         tw = be.asarray(twiddle, np.complex128) if twiddle is not None else None      # None: bare lattice DFT
         nbytes = self.lib.size("dp_project_commensurate_workspace_bytes", _hptr(dims_h), n_unit, int(n_prim), Q)
         ws = be.empty((nbytes,), np.uint8)
+        shape = (T, 3 * int(n_prim) // 2, Q, 2) if pair_major else (T, Q, int(n_prim), 3)
         if out is None:
-            out = be.empty((T, Q, n_prim, 3), np.complex128)
+            out = be.empty(shape, np.complex128)
         else:
-            assert be.shape(out) == (T, Q, int(n_prim), 3) and out.is_contiguous(), "bad `out` buffer"
-        self.lib.call("dp_project_commensurate", be.ptr(v), _hptr(dims_h), n_unit, _hptr(ut), int(n_prim), T,
-                      be.ptr(qb), be.ptr(tw), Q, int(project_on_atom), be.ptr(out), be.ptr(ws), nbytes, be.stream())
+            assert be.shape(out) == shape and out.is_contiguous(), "bad `out` buffer"
+        self.lib.call("dp_project_commensurate_ex", be.ptr(v), _hptr(dims_h), n_unit, _hptr(ut), int(n_prim), T,
+                      be.ptr(qb), be.ptr(tw), Q, int(project_on_atom), int(bool(pair_major)), be.ptr(out), be.ptr(ws),
+                      nbytes, be.stream())
         return out
 
     def project_phonon(self, vc, eigenvectors, q_block=None, out=None, inplace=False):
@@ -181,13 +186,18 @@ class Ops:
         self.lib.call("dp_project_phonon_blocked", be.ptr(vc), be.ptr(e), T, Q, M, qb, be.ptr(out), be.stream())
         return out.reshape(T, Q, M) if (inplace and qb == Q) else out
 
-    def project_phonon_series(self, vc, eigenvectors, q_block=None, out=None, t_offset=0, t_total=None):
+    def project_phonon_series(self, vc, eigenvectors, q_block=None, out=None, t_offset=0, t_total=None,
+                              pair_major=False):
         """vc (T,Q,n_p,3)|(T,Q,M) -> series-major vq: ``out[g, qq*M + s, t_offset + t]`` with q = g*q_block + qq,
         shape (Q/q_block, q_block*M, t_total).  ``out`` lets a long trajectory be contracted chunk by chunk."""
         be = self.be
         vc = be.asarray(vc, np.complex128)
-        T, Q = be.shape(vc)[:2]
-        M = int(np.prod(be.shape(vc)[2:]))
+        if pair_major:                                   # (T, M/2, Q, 2) from project_commensurate(pair_major=True)
+            T, half_m, Q, _ = be.shape(vc)
+            M = 2 * half_m
+        else:
+            T, Q = be.shape(vc)[:2]
+            M = int(np.prod(be.shape(vc)[2:]))
         e = be.asarray(eigenvectors, np.complex128)
         assert be.shape(e)[0] == Q and int(np.prod(be.shape(e)[1:])) == M * M, "eigenvector shape mismatch"
         qb = Q if q_block is None else int(q_block)
@@ -196,8 +206,8 @@ class Ops:
             out = be.empty((Q // qb, qb * M, t_total), np.complex128)
         else:
             assert be.shape(out) == (Q // qb, qb * M, t_total), "bad `out` buffer"
-        self.lib.call("dp_project_phonon_series", be.ptr(vc), be.ptr(e), T, Q, M, qb, int(t_offset), t_total,
-                      be.ptr(out), be.stream())
+        self.lib.call("dp_project_phonon_series_ex", be.ptr(vc), int(bool(pair_major)), be.ptr(e), T, Q, M, qb,
+                      int(t_offset), t_total, be.ptr(out), be.stream())
         return out
 
     def launch_count(self):

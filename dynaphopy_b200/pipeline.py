@@ -171,14 +171,16 @@ class MeshPipeline:
         for t0 in range(0, tl, chunk_frames):
             t1 = min(t0 + chunk_frames, tl)
             if self.fold_twiddle:
+                pm = self.M % 2 == 0        # pair-major intermediate: every transform stores one contiguous run
                 vc = self.ops.project_commensurate(velocity_local[t0:t1], self.plan.dims, self.plan.unit_type,
-                                                   self.plan.n_prim, self.d_qbin, None)
+                                                   self.plan.n_prim, self.d_qbin, None, pair_major=pm)
                 eig = self.d_eig_folded
             else:
+                pm = False
                 vc = self.project(velocity_local[t0:t1])
                 eig = self.d_eig
             self.ops.project_phonon_series(vc, eig, q_block=self.q_block, out=out, t_offset=t_offset + t0,
-                                           t_total=t_total)
+                                           t_total=t_total, pair_major=pm)
             del vc
         return out
 

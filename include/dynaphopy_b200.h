@@ -36,6 +36,12 @@ extern "C" {
 #define DP_ERR_WORKSPACE (-3)   /* workspace too small                                   */
 #define DP_ERR_CUDA (-4)        /* CUDA runtime error (includes "no device")             */
 
+/* vc_layout of the *_ex projection / contraction entry points */
+#define DP_VC_ROWS 0   /* vc[t][q][3*n_prim]        (the reference's (T, n_p, 3) per q; default)            */
+#define DP_VC_PAIRS 1  /* vc[t][j][q][2], j = slot pair (2j, 2j+1) of the 3*n_prim (p, k) slots: every       */
+                       /* transform of the projection kernel stores one contiguous run -- an INTERMEDIATE    */
+                       /* layout between dp_project_commensurate_ex and dp_project_phonon_series_ex          */
+
 /* weight_mode of dp_power_correlation */
 #define DP_CORR_WEIGHT_REFERENCE 0 /* as shipped: exp(w*tau + 1i)  (c/correlation.c:158) */
 #define DP_CORR_WEIGHT_INTENDED 1  /* exp(i*w*tau)  (comments at c/correlation.c:166-172) */
@@ -128,6 +134,11 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
                             int project_on_atom, double* out_vc, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, const int* unit_type,
+                               int n_prim, int64_t T, const int* qbin, const double* twiddle, int Q,
+                               int project_on_atom, int vc_layout, double* out_vc, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A3  eigenvector contraction, batched over q.
  * Replaces: projection.project_onto_phonon(vc, eigenvectors) (dynaphopy/projection.py:43-54)
@@ -154,6 +165,8 @@ int dp_project_phonon_blocked(const double* vc, const double* eig, int64_t T, in
  * t_offset / T_total let a long trajectory be contracted chunk by chunk into one series matrix. */
 int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int Q, int M, int q_block,
                              int64_t t_offset, int64_t T_total, double* out, void* stream);
+int dp_project_phonon_series_ex(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M,
+                                int q_block, int64_t t_offset, int64_t T_total, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * A7  power spectrum, FFT method (selector keys 2 and 3).

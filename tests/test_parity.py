@@ -193,6 +193,28 @@ def test_projection_ragged_and_empty(kops):
         kops.project_commensurate(g["velocity"], dims, unit_type, n_prim, qb + 7, tw)
 
 
+def test_pair_major_intermediate_layout(kops):
+    """Bare lattice DFT in the pair-major layout + twiddle folded into the eigenvectors == projection with
+    twiddle + contraction in the reference layout (what MeshPipeline relies on)."""
+    g = golden("cubic2_232")
+    dims, unit_type, n_prim, qb, tw, keep = _commensurate_inputs(g)
+    v = g["velocity"]
+    nq, m = len(keep), 3 * n_prim
+    rng = np.random.default_rng(9)
+    eig = rng.normal(size=(nq, m, n_prim, 3)) + 1j * rng.normal(size=(nq, m, n_prim, 3))
+    vc = kops.project_commensurate(v, dims, unit_type, n_prim, qb, tw)
+    ref = to_np(kops.project_phonon_series(vc, eig))
+    raw = kops.project_commensurate(v, dims, unit_type, n_prim, qb, None, pair_major=True)
+    assert tuple(raw.shape) == (v.shape[0], m // 2, nq, 2)
+    folded = eig * np.conj(np.asarray(tw))[:, None, :, None]
+    out = to_np(kops.project_phonon_series(raw, folded, pair_major=True))
+    assert relerr(out, ref) < 1e-13
+    # and the rows layout of the bare DFT carries the same numbers
+    raw_rows = to_np(kops.project_commensurate(v, dims, unit_type, n_prim, qb, None))
+    assert np.array_equal(to_np(raw).transpose(0, 2, 1, 3).reshape(raw_rows.shape[0], nq, -1),
+                          raw_rows.reshape(raw_rows.shape[0], nq, -1))
+
+
 def test_project_phonon_wide(kops):
     """M = 12 and 30 modes (GaN / larger cells), ragged frame count."""
     rng = np.random.default_rng(5)
