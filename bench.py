@@ -370,12 +370,13 @@ def run_ours(args):
                           "ms": mean["exchange"]}
     # DRAM traffic of the dominant kernels from `ncu --set full` captures of smaller launches of the same
     # kernels (profiles/r01_ncu_*.jsonl), scaled linearly to this launch: bytes per series / per frame
-    ncu_traffic = {"spectra": (0.985820672e9 + 1.042886e9) / 296.0 * s_loc,           # 296 series captured
+    ncu_traffic = {"spectra": (1.901760e9 + 1.569485e9) / 296.0 * s_loc,              # 296 series captured
                    "project": (1.077133e9 + 2.219636e9) / 4096.0 * tl,               # 4096 frames captured
                    "contract": (2.016264e9 + 1.960431e9) / 4096.0 * tl}
-    # fp64 view of the spectrum stage: 157 k warp-level fp64 instructions per (series, window) item (ncu
-    # instruction mix) against the measured 64 lanes/clk/SM (tools/micro/fp64_rate.cu: 18.3 T lane-ops/s)
-    fp64_lane_ops = 157.0e3 * 32 * npieces * s_loc
+    # fp64 view of the spectrum stage: 770.5 k warp-level fp64 instructions per series (7 windows, processed as
+    # 3 pairs + 1 single; ncu instruction mix, profiles/r01_ncu_spectrum2.jsonl) against the measured
+    # 64 lanes/clk/SM (tools/micro/fp64_rate.cu: 18.3 T lane-ops/s)
+    fp64_lane_ops = 770.5e3 * 32 * s_loc
     fp64 = {"lane_ops": fp64_lane_ops, "achieved_Tops": fp64_lane_ops / (mean["spectra"] * 1e-3) / 1e12 if mean["spectra"] else 0.0,
             "peak_Tops": 18.3, "peak_source": "measured, tools/micro/fp64_rate.cu (DFMA/DADD/DMUL, 63.6 of 64 lanes/clk/SM)"}
     fp64["frac"] = fp64["achieved_Tops"] / fp64["peak_Tops"]

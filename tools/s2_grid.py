@@ -19,6 +19,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     b.record(); torch.cuda.synchronize()
     print("grid=%s  %.3f ms" % (os.environ.get("DP_S2_GRID", "148"), a.elapsed_time(b) / 3), flush=True)
 else:
-    for g in (148, 128, 111, 96, 74, 48, 37):
+    for g in [int(x) for x in os.environ.get("S2_GRIDS", "148,128,111,96,74,48,37").split(",")]:
         env = dict(os.environ, DP_S2_GRID=str(g))
         subprocess.run([sys.executable, __file__, "child"], env=env)
