@@ -132,6 +132,7 @@ static int make_spec_plan(int64_t T, double dt, const double* freq, int F, SpecH
 struct SpecParams {
     const cplx* series; int64_t stride_s, stride_t; int tb_len; int64_t tb_stride; int S;
     int L, P, half, npieces;
+    int w_first, w_count;     // windows [w_first, w_first + w_count) are transformed by this launch
     const int* starts;
     FftSplit sp, sl;
     const cplx *twP1, *twP2, *twPN, *twL1, *twL2, *twLN;
@@ -162,9 +163,9 @@ spectrum_items_kernel(SpecParams p) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     cplx* A = p.scratch + (size_t)blockIdx.x * ((size_t)p.P + p.L);
     cplx* B = A + p.P;
-    const int64_t nitems = (int64_t)p.S * p.npieces;
+    const int64_t nitems = (int64_t)p.S * p.w_count;
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int pc = (int)(item / p.S), s = (int)(item % p.S);
+        const int pc = p.w_first + (int)(item / p.S), s = (int)(item % p.S);
         const cplx* x0 = p.series + (int64_t)s * p.stride_s;
         const int t0 = p.starts[pc];
         const int64_t stride_t = p.stride_t, tb_stride = p.tb_stride;
@@ -319,22 +320,29 @@ int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* pi
     return DP_OK;
 }
 
-int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
-                         int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, double scale,
-                         double* out, void* workspace, size_t workspace_bytes, void* stream) {
-    DP_REQUIRE(series && freq && out && workspace, DP_ERR_INVALID, "dp_power_fft: null pointer");
+int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                         int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
+                         int n_windows, void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(series && freq && workspace, DP_ERR_INVALID, "dp_power_fft: null pointer");
     DP_REQUIRE(S > 0 && stride_t != 0, DP_ERR_INVALID, "dp_power_fft: bad S=%d stride_t=%lld", S, (long long)stride_t);
     DP_REQUIRE(tb_len >= 0 && tb_len < (1LL << 31), DP_ERR_INVALID, "dp_power_fft: bad time-block length %lld", (long long)tb_len);
     if (tb_len >= T) tb_len = 0;
     dp::SpecHostPlan pl;
     int rc = dp::make_spec_plan(T, dt, freq, F, &pl);
     if (rc) return rc;
+    const int npieces = (int)pl.starts.size();
+    if (n_windows < 0) n_windows = npieces - first_window;
+    DP_REQUIRE(first_window >= 0 && n_windows >= 0 && first_window + n_windows <= npieces, DP_ERR_INVALID,
+               "dp_power_fft_windows: windows [%d, %d) outside the %d distinct windows", first_window,
+               first_window + n_windows, npieces);
     dp::SpecLayout lay = dp::spec_layout(pl, S, F);
     DP_REQUIRE(workspace_bytes >= lay.total, DP_ERR_WORKSPACE, "dp_power_fft: workspace %zu < %zu", workspace_bytes, lay.total);
+    if (n_windows == 0) return DP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     dp::cplx* tw[6];
     for (int i = 0; i < 6; i++) tw[i] = (dp::cplx*)(ws + lay.off_tw[i]);
+    // tables and window starts are (re)written by every call: deterministic, and stream-ordered with the kernels
     if (pl.use_v2) {
         auto kt = dp::s2_tables_kernel;
         int a1, a2, b1, b2;
@@ -352,19 +360,17 @@ int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_
         }
     }
     DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_starts, pl.starts.data(), pl.starts.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_idx0, pl.idx0.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_mode, pl.mode.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_dx, pl.dx.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_den, pl.den.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
 #ifndef DP_EMUL
     DP_CUDA_OK(cudaStreamSynchronize(st));   // plan vectors are host temporaries
 #endif
-    const int npieces = (int)pl.starts.size();
     double* spec = (double*)(ws + lay.off_spec);
+    const int64_t items = (int64_t)S * (pl.use_v2 ? (n_windows + 1) / 2 : n_windows);
+    const int grid = (int)dp::imin<int64_t>(items, lay.nslots);
     if (pl.use_v2) {
         dp::S2Params p;
         p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;
         p.tb_len = (int)tb_len; p.tb_stride = tb_stride; p.S = S; p.npieces = npieces;
+        p.w_first = first_window; p.w_count = n_windows;
         p.tb_shift = -1;
         if (tb_len > 0 && (tb_len & (tb_len - 1)) == 0) { p.tb_shift = 0; while ((1LL << p.tb_shift) < tb_len) p.tb_shift++; }
         p.starts = (const int*)(ws + lay.off_starts);
@@ -374,16 +380,17 @@ int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_
         p.spec = spec; p.lo = pl.lo; p.nkeep = pl.nkeep;
         p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
         p.skip_mask = getenv("DP_S2_SKIP") ? atoi(getenv("DP_S2_SKIP")) : 0;
-        p.pair = (npieces >= 2 && !(getenv("DP_S2_PAIR") && atoi(getenv("DP_S2_PAIR")) == 0)) ? 1 : 0;
+        p.pair = (n_windows >= 2 && !(getenv("DP_S2_PAIR") && atoi(getenv("DP_S2_PAIR")) == 0)) ? 1 : 0;
         auto k = dp::spectrum2_kernel;
         DP_CUDA_OK(DP_SET_SMEM(k, dp::S2_SMEM_BYTES));
-        DP_LAUNCH(k, dim3(lay.nslots), dim3(dp::S2_THREADS), dp::S2_SMEM_BYTES, st, p);
+        DP_LAUNCH(k, dim3(grid), dim3(dp::S2_THREADS), dp::S2_SMEM_BYTES, st, p);
         DP_CUDA_OK(cudaGetLastError());
     } else {
         dp::SpecParams p;
         p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;
         p.tb_len = (int)tb_len; p.tb_stride = tb_stride; p.S = S;
         p.L = pl.L; p.P = pl.P; p.half = pl.half; p.npieces = npieces;
+        p.w_first = first_window; p.w_count = n_windows;
         p.starts = (const int*)(ws + lay.off_starts);
         p.sp = pl.sp; p.sl = pl.sl;
         p.twP1 = tw[0]; p.twP2 = tw[1]; p.twPN = tw[2]; p.twL1 = tw[3]; p.twL2 = tw[4]; p.twLN = tw[5];
@@ -394,17 +401,48 @@ int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_
         size_t smem = std::max(dp::fft_split_smem_elems(pl.sp), dp::fft_split_smem_elems(pl.sl)) * sizeof(dp::cplx);
         auto k = dp::spectrum_items_kernel;
         DP_CUDA_OK(DP_SET_SMEM(k, smem));
-        DP_LAUNCH(k, dim3(lay.nslots), dim3(dp::FFT_THREADS), smem, st, p);
+        DP_LAUNCH(k, dim3(grid), dim3(dp::FFT_THREADS), smem, st, p);
         DP_CUDA_OK(cudaGetLastError());
     }
+    return DP_OK;
+}
+
+int dp_power_fft_finish(int64_t T, int S, double dt, const double* freq, int F, double scale, double* out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(freq && out && workspace && S > 0, DP_ERR_INVALID, "dp_power_fft_finish: null pointer");
+    dp::SpecHostPlan pl;
+    int rc = dp::make_spec_plan(T, dt, freq, F, &pl);
+    if (rc) return rc;
+    dp::SpecLayout lay = dp::spec_layout(pl, S, F);
+    DP_REQUIRE(workspace_bytes >= lay.total, DP_ERR_WORKSPACE, "dp_power_fft: workspace %zu < %zu", workspace_bytes, lay.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_idx0, pl.idx0.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_mode, pl.mode.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_dx, pl.dx.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_den, pl.den.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+#ifndef DP_EMUL
+    DP_CUDA_OK(cudaStreamSynchronize(st));   // plan vectors are host temporaries
+#endif
+    const int npieces = (int)pl.starts.size();
     auto kf = dp::spectrum_finalize_kernel;
     int64_t total = (int64_t)F * S;
     DP_LAUNCH(kf, dim3((unsigned)dp::imin<int64_t>((total + 255) / 256, 4096)), dim3(256), 0, st,
-              (const double*)spec, S, npieces, pl.n_avg, pl.nkeep, pl.lo, (const int*)(ws + lay.off_idx0),
+              (const double*)(ws + lay.off_spec), S, npieces, pl.n_avg, pl.nkeep, pl.lo, (const int*)(ws + lay.off_idx0),
               (const int*)(ws + lay.off_mode), (const double*)(ws + lay.off_dx), (const double*)(ws + lay.off_den), F,
               scale, out);
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
+}
+
+int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                         int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, double scale,
+                         double* out, void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(out, DP_ERR_INVALID, "dp_power_fft: null pointer");
+    int rc = dp_power_fft_windows(series, T, S, stride_s, stride_t, tb_len, tb_stride, dt, freq, F, 0, -1, workspace,
+                                  workspace_bytes, stream);
+    if (rc) return rc;
+    return dp_power_fft_finish(T, S, dt, freq, F, scale, out, workspace, workspace_bytes, stream);
 }
 
 int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq, int F,

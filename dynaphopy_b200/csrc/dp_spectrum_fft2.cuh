@@ -54,6 +54,7 @@ struct S2Params {
     int tb_shift;                  // log2(tb_len) when it is a power of two (no integer division), else -1
     int64_t tb_stride;             // ... block b = t / tb_len starts at b * tb_stride
     int S, npieces;
+    int w_first, w_count;          // windows [w_first, w_first + w_count) are transformed by this launch
     const int* starts;
     S2Plan pl;
     const cplx* g_tables;          // 6 x 256: T1, T2, T2f, Ts, fine, coarse (s2_tables_kernel)
@@ -451,12 +452,12 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
     cplx* A = p.scratch + (size_t)blockIdx.x * p.slab_elems;
     double* Sr = reinterpret_cast<double*>(A + p.pl.P);            // [P] real: |X_a|^2 of a pair's first window
     const int layout = p.stride_t != 1 ? 2 : (p.tb_len == 0 ? 0 : (p.tb_shift >= 0 ? 1 : 2));
-    const int npairs = p.pair ? (p.npieces + 1) / 2 : p.npieces;
+    const int npairs = p.pair ? (p.w_count + 1) / 2 : p.w_count;
     const int64_t nitems = (int64_t)p.S * npairs;
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int pj = (int)(item / p.S), s = (int)(item % p.S);
-        const int w0 = p.pair ? 2 * pj : pj;
-        const bool paired = p.pair && (w0 + 1 < p.npieces);
+        const int w0 = p.w_first + (p.pair ? 2 * pj : pj);
+        const bool paired = p.pair && (w0 + 1 < p.w_first + p.w_count);
         const cplx* x = p.series + (int64_t)s * p.stride_s;
         double* spec = p.spec + ((size_t)s * p.npieces + w0) * p.nkeep;
         // the next item's first window starts its way from HBM to L2 (time-contiguous layouts only)
@@ -464,7 +465,7 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
             if (item + gridDim.x < nitems && p.stride_t == 1) {
                 const int64_t nxt = item + gridDim.x;
                 const cplx* xn = p.series + (int64_t)(nxt % p.S) * p.stride_s;
-                const int tn = p.starts[p.pair ? 2 * (int)(nxt / p.S) : (int)(nxt / p.S)];
+                const int tn = p.starts[p.w_first + (p.pair ? 2 * (int)(nxt / p.S) : (int)(nxt / p.S))];
                 for (int i = tid * 8; i < p.pl.L; i += S2_THREADS * 8) s2_prefetch_l2(xn + s2_time_offset(p, tn + i));
             }
         };

@@ -253,6 +253,47 @@ class Ops:
                       _hptr(f), f.size, float(scale), be.ptr(out), be.ptr(ws), nbytes, be.stream())
         return out
 
+    # -- the same spectrum in steps (series produced incrementally) ----------------------------------------
+    def _series_layout(self, series, series_major):
+        be = self.be
+        s = be.asarray(series, np.complex128)
+        shp = be.shape(s)
+        if not series_major:
+            assert len(shp) == 2, "series must be (T, S)"
+            return s, shp[0], shp[1], (1, shp[1], 0, 0)
+        if len(shp) == 2:
+            return s, shp[1], shp[0], (shp[1], 1, 0, 0)
+        g, n, tb = shp
+        return s, g * tb, n, (tb, 1, tb, n * tb)
+
+    def power_fft_begin(self, T, S, dt, frequency_range):
+        """Workspace of one incremental FFT spectrum (see power_fft_windows / power_fft_finish)."""
+        f = _host(frequency_range, np.float64)
+        nbytes = self.lib.size("dp_power_fft_workspace_bytes", int(T), int(S), float(dt), _hptr(f), f.size)
+        if nbytes == 0:
+            self.lib.call("dp_power_fft", None, int(T), int(S), int(S), float(dt), _hptr(f), f.size, 1.0, None, None, 0,
+                          self.be.stream())
+        return self.be.empty((nbytes,), np.uint8)
+
+    def power_fft_windows(self, series, dt, frequency_range, first_window, n_windows, workspace, series_major=False):
+        """Transform windows [first_window, first_window + n_windows) of every series into ``workspace``; reads
+        no sample outside those windows (the rest of ``series`` may still be in production)."""
+        be = self.be
+        s, T, S, st = self._series_layout(series, series_major)
+        f = _host(frequency_range, np.float64)
+        self.lib.call("dp_power_fft_windows", be.ptr(s), T, S, st[0], st[1], st[2], st[3], float(dt), _hptr(f), f.size,
+                      int(first_window), int(n_windows), be.ptr(workspace), int(workspace.numel() if hasattr(workspace, "numel")
+                                                                                else workspace.size), be.stream())
+
+    def power_fft_finish(self, T, S, dt, frequency_range, workspace, scale=UNIT_CONVERSION):
+        be = self.be
+        f = _host(frequency_range, np.float64)
+        out = be.empty((f.size, S), np.float64)
+        self.lib.call("dp_power_fft_finish", int(T), int(S), float(dt), _hptr(f), f.size, float(scale), be.ptr(out),
+                      be.ptr(workspace), int(workspace.numel() if hasattr(workspace, "numel") else workspace.size),
+                      be.stream())
+        return out
+
     def power_mem(self, series, dt, frequency_range, coefficients, scale=UNIT_CONVERSION, nan_to_num=True):
         be = self.be
         s, T, S = self._series(series)

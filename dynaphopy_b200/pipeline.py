@@ -262,6 +262,15 @@ class MeshPipeline:
         main = torch.cuda.current_stream(be.device)
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
+        # single rank + FFT method: the spectra of a window start as soon as its frames have been contracted,
+        # underneath the remaining host->device copies (windows go in pairs, the unit the kernel works in)
+        stream_windows = self.world == 1 and self.algorithm in (2, 3, 4, 5)
+        if stream_windows:
+            n_series = self.q_block * self.M
+            L, pieces = self.ops.fft_pieces(tl, self.dt, self.freq)
+            pieces = [p for i, p in enumerate(pieces) if i == 0 or p != pieces[i - 1]]      # distinct windows
+            ws = self.ops.power_fft_begin(tl, n_series, self.dt, self.freq)
+            done = 0
         starts = list(range(0, tl, chunk_frames))
         for i, t0 in enumerate(starts):
             slot = i % 2
@@ -274,7 +283,16 @@ class MeshPipeline:
             main.wait_event(ready[slot])
             self.series(stage[slot][: t1 - t0], chunk_frames, out=send, t_offset=t0, t_total=tl)
             freed[slot].record(main)
+            if stream_windows:
+                complete = sum(1 for p in pieces if p[1] <= t1)
+                ready_now = (complete - done) // 2 * 2 if complete < len(pieces) else complete - done
+                if ready_now > 0:
+                    self.ops.power_fft_windows(send, self.dt, self.freq, done, ready_now, ws, series_major=True)
+                    done += ready_now
         del stage
+        if stream_windows:
+            ps = self.ops.power_fft_finish(tl, n_series, self.dt, self.freq, ws)
+            return ps.cpu().numpy()
         blocks = self.exchange_series(send)
         ps = self.spectra_series(blocks)
         return ps.cpu().numpy()

@@ -192,6 +192,17 @@ int dp_power_fft(const double* series, int64_t T, int S, int64_t ld, double dt, 
 int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
                          int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, double scale,
                          double* out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same spectrum in two steps, for callers that produce the series incrementally (e.g. a host-resident
+ * trajectory streamed to the device): dp_power_fft_windows transforms the distinct windows
+ * [first_window, first_window + n_windows) (n_windows < 0: all remaining; see dp_power_fft_pieces for the
+ * list) into the workspace and reads no sample outside them, so it can run as soon as those frames exist;
+ * dp_power_fft_finish averages the windows and interpolates onto the grid once all of them are done.  Every
+ * call of one spectrum must use the same workspace and the same (T, S, dt, freq, F). */
+int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                         int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
+                         int n_windows, void* workspace, size_t workspace_bytes, void* stream);
+int dp_power_fft_finish(int64_t T, int S, double dt, const double* freq, int F, double scale, double* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* piece_len,
                         int* n_pieces, int* starts, int max_pieces);
 

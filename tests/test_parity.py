@@ -399,3 +399,30 @@ def test_power_fft_series_major_and_time_blocks(kops):
     c = to_np(kops.power_fft(blocks, 0.002, f, series_major=True))
     assert relerr(a, ref) < TOL
     assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_power_fft_incremental_windows(kops):
+    """dp_power_fft_windows / dp_power_fft_finish: windows transformed in several calls (any split, even while
+    later samples are still garbage) give exactly the one-shot spectrum."""
+    rng = np.random.default_rng(29)
+    nt, ns, dt = 2300, 3, 0.002
+    x = _series(rng, nt, ns, dt)
+    f = np.arange(0, 40.0, 1.0)                              # L = 500, 5 windows
+    L, pieces = kops.fft_pieces(nt, dt, f)
+    assert len(pieces) == 5
+    ref = to_np(kops.power_fft(x, dt, f))
+    xs = np.ascontiguousarray(x.T)                           # series-major
+    for split in ([2, 2, 1], [1, 1, 1, 1, 1], [4, 1], [5]):
+        ws = kops.power_fft_begin(nt, ns, dt, f)
+        part = xs.copy()
+        first = 0
+        for n in split:
+            end = pieces[first + n - 1][1]
+            part[:, end:] = np.nan                           # frames after the requested windows do not exist yet
+            kops.power_fft_windows(part, dt, f, first, n, ws, series_major=True)
+            part = xs.copy()
+            first += n
+        out = to_np(kops.power_fft_finish(nt, ns, dt, f, ws))
+        assert relerr(out, ref) < 1e-13
+        if split == [2, 2, 1]:
+            assert np.array_equal(out, ref)                  # same pairing as the one-shot call: bitwise
