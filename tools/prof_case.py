@@ -34,9 +34,10 @@ elif case in ("project", "contract"):
     v = torch.randn((T, 2 * nc, 3), dtype=torch.float64, device=dev)
     eig = torch.randn((len(mm), 6, 6), dtype=torch.complex128, device=dev)
     for _ in range(reps):
-        vc = ops.project_commensurate(v, dims, [0, 1], 2, qb, None)     # bare lattice DFT, as the pipeline runs it
+        # bare lattice DFT in the pair-major intermediate layout, as the pipeline runs it
+        vc = ops.project_commensurate(v, dims, [0, 1], 2, qb, None, pair_major=True)
         if case == "contract":
-            vq = ops.project_phonon_series(vc, eig)
+            vq = ops.project_phonon_series(vc, eig, pair_major=True)
 elif case == "mem":
     T, S = (int(os.environ.get("PC_T", 2500)), int(os.environ.get("PC_S", 592)))
     x = torch.randn((T, S), dtype=torch.complex128, device=dev)
