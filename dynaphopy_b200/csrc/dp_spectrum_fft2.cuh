@@ -225,7 +225,7 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
                 for (int k2 = 0; k2 < C::R2; k2++) sa[i * C::R2 + k2] = __ldcg(Srow + g + C::TG * i + C::R1 * k2);
         }
         sub_dit<C>(v, E, sm.T2, g);
-        if (MODE == 1) {
+        if constexpr (MODE == 1) {
 #pragma unroll
             for (int i = 0; i < C::NB2; i++)
 #pragma unroll
@@ -233,26 +233,25 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
                     const cplx x = v[i * C::R2 + k2];
                     __stcg(Srow + g + C::TG * i + C::R1 * k2, x.x * x.x + x.y * x.y);
                 }
+        } else {
+#pragma unroll
+            for (int r = 0; r < C::NB2 * C::R2; r++) {
+                const double sb = v[r].x * v[r].x + v[r].y * v[r].y;
+                v[r] = MODE == 2 ? make_double2(sa[r], sb) : make_double2(sb, 0.0);
+            }
             __syncwarp();
-            continue;
-        }
+            sub_dif<C>(v, E, sm.T2f, g);
+            // four-step twiddle w_P^(row*k), k = d*R2 + c: geometric in d
+            const cplx ratio = tw2level(sm.fine, sm.coarse, row * C::R2);
 #pragma unroll
-        for (int r = 0; r < C::NB2 * C::R2; r++) {
-            const double sb = v[r].x * v[r].x + v[r].y * v[r].y;
-            v[r] = MODE == 2 ? make_double2(sa[r], sb) : make_double2(sb, 0.0);
-        }
-        __syncwarp();
-        sub_dif<C>(v, E, sm.T2f, g);
-        // four-step twiddle w_P^(row*k), k = d*R2 + c: geometric in d
-        const cplx ratio = tw2level(sm.fine, sm.coarse, row * C::R2);
+            for (int i = 0; i < C::NB1; i++) {
+                const int c = g + C::TG * i;
+                cplx tw = tw2level(sm.fine, sm.coarse, row * c);
 #pragma unroll
-        for (int i = 0; i < C::NB1; i++) {
-            const int c = g + C::TG * i;
-            cplx tw = tw2level(sm.fine, sm.coarse, row * c);
-#pragma unroll
-            for (int d = 0; d < C::R1; d++) {
-                s2_st_slab(Ar + d * C::R2 + c, cmul(v[i * C::R1 + d], tw), pol);
-                if (d + 1 < C::R1) tw = cmul(tw, ratio);
+                for (int d = 0; d < C::R1; d++) {
+                    s2_st_slab(Ar + d * C::R2 + c, cmul(v[i * C::R1 + d], tw), pol);
+                    if (d + 1 < C::R1) tw = cmul(tw, ratio);
+                }
             }
         }
         __syncwarp();
