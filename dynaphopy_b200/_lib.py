@@ -23,6 +23,8 @@ SIGNATURES = {
     "dp_atomic_displacements": (_I, [_P, _I, _P, _P, _L, _I, _P, _P]),
     "dp_velocity_from_positions": (_I, [_P, _I, _P, _P, _P, _L, _I, _D, _P, _P, _P, _P, _P]),
     "dp_mass_weight": (_I, [_P, _I, _P, _L, _I, _P, _P]),
+    "dp_displacement_moments_workspace_bytes": (_Z, [_L, _I]),
+    "dp_displacement_moments": (_I, [_P, _I, _P, _P, _L, _I, _P, _P, _Z, _P]),
     "dp_project_wave_vector_workspace_bytes": (_Z, [_I, _I]),
     "dp_project_wave_vector": (_I, [_P, _I, _P, _P, _P, _I, _I, _L, _P, _I, _I, _P, _P, _Z, _P]),
     "dp_project_commensurate_workspace_bytes": (_Z, [_P, _I, _I, _I]),

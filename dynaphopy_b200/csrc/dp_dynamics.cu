@@ -175,6 +175,54 @@ mass_weight_kernel(const double* __restrict__ v, const double* __restrict__ sqrt
     }
 }
 
+// (f)3: per-atom moments of the displacement, fused with the minimum-image map: every position is read once
+// (24 B per atom*frame) and nothing of size T is written.  Thread = (atom, time split); lanes run over atoms so a
+// warp reads 768 contiguous bytes per frame.  part[split][atom][9] = (sum u_k ; sum u_a u_b for a <= b).
+template <int NC>
+__global__ void __launch_bounds__(256)
+displacement_moments_kernel(const double* __restrict__ traj, const double* __restrict__ pos0, CellMats m,
+                            int64_t T, int N, int splits, double* __restrict__ part) {
+    const int atom = blockIdx.x * blockDim.x + threadIdx.x;
+    const int split = blockIdx.y;
+    if (atom >= N) return;
+    const int64_t per = (T + splits - 1) / splits;
+    const int64_t t0 = split * per, t1 = imin<int64_t>(t0 + per, T);
+    double p[3], x[3], u[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = __ldg(pos0 + atom * 3 + k);
+    double s[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) s[k] = 0.0;
+    for (int64_t t = t0; t < t1; t++) {
+        load_pos<NC>(traj, t * N + atom, x);
+        displacement3(x, p, m, u);
+        s[0] += u[0]; s[1] += u[1]; s[2] += u[2];
+        s[3] += u[0] * u[0]; s[4] += u[0] * u[1]; s[5] += u[0] * u[2];
+        s[6] += u[1] * u[1]; s[7] += u[1] * u[2]; s[8] += u[2] * u[2];
+    }
+    double* o = part + ((size_t)split * N + atom) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; k++) o[k] = s[k];
+}
+
+// fixed-order sum over the time splits (run-to-run reproducible, no atomics)
+__global__ void __launch_bounds__(256)
+moments_reduce_kernel(const double* __restrict__ part, int64_t n9, int splits, double* __restrict__ sums) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n9; idx += stride) {
+        double a = 0.0;
+        for (int sp = 0; sp < splits; sp++) a += part[(size_t)sp * n9 + idx];
+        sums[idx] = a;
+    }
+}
+
+static int moment_splits(int64_t T, int N) {
+    // enough (atom, split) threads to fill the machine, runs of at least 16 frames
+    int64_t want = ((int64_t)imax(sm_count(), 1) * 2048 + N - 1) / N;
+    int64_t cap = imax<int64_t>(1, T / 16);
+    return (int)imax<int64_t>(1, imin(imin(want, cap), (int64_t)65535));
+}
+
 static int grid_for(int64_t work, int block) {
     int64_t g = (work + block - 1) / block;
     int64_t cap = (int64_t)imax(sm_count(), 1) * 16;
@@ -232,6 +280,38 @@ int dp_velocity_from_positions(const double* traj, int traj_is_complex, const do
         DP_LAUNCH(k, dim3(grid), dim3(256), 0, st, traj, pos0, m, sqrt_mass, Tl, N, dt, run, prev_frame,
                   next_frame, out_u, out_v);
     }
+    DP_CUDA_OK(cudaGetLastError());
+    return DP_OK;
+}
+
+size_t dp_displacement_moments_workspace_bytes(int64_t T, int N) {
+    if (T <= 0 || N <= 0) return 0;
+    return (size_t)dp::moment_splits(T, N) * (size_t)N * 9 * sizeof(double);
+}
+
+int dp_displacement_moments(const double* traj, int traj_is_complex, const double* pos0, const double* cell,
+                            int64_t T, int N, double* sums, void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(T > 0 && N > 0, DP_ERR_INVALID, "dp_displacement_moments: bad sizes T=%lld N=%d", (long long)T, N);
+    DP_REQUIRE(traj && pos0 && cell && sums && workspace, DP_ERR_INVALID, "dp_displacement_moments: null pointer");
+    const int splits = dp::moment_splits(T, N);
+    const size_t need = (size_t)splits * (size_t)N * 9 * sizeof(double);
+    DP_REQUIRE(workspace_bytes >= need, DP_ERR_WORKSPACE, "dp_displacement_moments: workspace %zu < %zu", workspace_bytes, need);
+    dp::CellMats m;
+    dp::make_cell_mats(cell, &m);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* part = (double*)workspace;
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)splits);
+    if (traj_is_complex) {
+        auto k = dp::displacement_moments_kernel<2>;
+        DP_LAUNCH(k, grid, dim3(256), 0, st, traj, pos0, m, T, N, splits, part);
+    } else {
+        auto k = dp::displacement_moments_kernel<1>;
+        DP_LAUNCH(k, grid, dim3(256), 0, st, traj, pos0, m, T, N, splits, part);
+    }
+    DP_CUDA_OK(cudaGetLastError());
+    auto kr = dp::moments_reduce_kernel;
+    const int64_t n9 = (int64_t)N * 9;
+    DP_LAUNCH(kr, dim3(dp::grid_for(n9, 256)), dim3(256), 0, st, (const double*)part, n9, splits, sums);
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
 }

@@ -129,7 +129,9 @@ __device__ __noinline__ void pf_epilogue(const PfUnit& u, int npad, int Q, int n
     cplx* __restrict__ outA = u.outA;
     cplx* __restrict__ outB = u.outB;
     const int64_t qstride = u.qstride;
-    for (int q0 = tid; q0 < Q; q0 += 4 * nthreads) {
+    const bool xpose = hasA && hasB && qstride == 2 && outB == outA + 1 && (nthreads & 31) == 0;    // warp-uniform
+    // the trip count is warp-uniform (first lane's q decides): every lane takes part in the shuffles below
+    for (int q0 = tid; q0 - (tid & 31) < Q; q0 += 4 * nthreads) {
         cplx wa[4], wb[4];
         if (TW) {
 #pragma unroll
@@ -142,12 +144,25 @@ __device__ __noinline__ void pf_epilogue(const PfUnit& u, int npad, int Q, int n
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int q = q0 + i * nthreads;
-            if (q < Q) {
-                const unsigned o = qo[q];
-                const cplx C = W[o & 0xffffu], D = W[o >> 16];
-                cplx ra = make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y));
-                cplx rb = make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x));
-                if (TW) { ra = cmul(ra, wa[i]); rb = cmul(rb, wb[i]); }
+            const unsigned o = qo[imin(q, Q - 1)];
+            const cplx C = W[o & 0xffffu], D = W[o >> 16];
+            cplx ra = make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y));
+            cplx rb = make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x));
+            if (TW) { ra = cmul(ra, wa[i]); rb = cmul(rb, wb[i]); }
+            if (!ACC && xpose) {
+                // pair-major layout: (A, B) of 32 consecutive q are 1 KB contiguous.  Exchange inside the warp so
+                // that consecutive lanes store consecutive 16-byte values: two fully coalesced 512-byte stores
+                // instead of two stores of half-filled sectors.
+                const int lane = tid & 31, qbase = q - lane;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int src = h * 16 + (lane >> 1);
+                    const double ax = __shfl_sync(0xffffffffu, ra.x, src), ay = __shfl_sync(0xffffffffu, ra.y, src);
+                    const double bx = __shfl_sync(0xffffffffu, rb.x, src), by = __shfl_sync(0xffffffffu, rb.y, src);
+                    if (qbase + src < Q)
+                        __stcs(outA + (int64_t)(qbase + h * 16) * 2 + lane, (lane & 1) ? make_double2(bx, by) : make_double2(ax, ay));
+                }
+            } else if (q < Q) {
                 if (ACC) {
                     if (hasA) ra = cadd(outA[q * qstride], ra);
                     if (hasB) rb = cadd(outB[q * qstride], rb);

@@ -5,7 +5,8 @@
 // The reference recomputes every lag product for every output frequency: O(F * N^2 / step).
 // The products do not depend on the frequency, so this implementation factors the sum:
 //   stage 1  C(i) = sum_{j < N-i-step} conj(v_j) v_{j+i}   for lags i = 0, step, 2 step, ...
-//            -- the compute-bound fp64 FMA kernel (4 N^2 / step flop per series);
+//            -- the compute-bound fp64 FMA kernel (4 N^2 / step flop per series): `step` independent
+//            autocorrelations of the decimated sequences v[r + n*step], register-tiled (lag_sums_kernel);
 //            D(i) = sum_{j < N-i-step} conj(v_j) v_{j+i+step} when integration_method == 0
 //   stage 2  P(f) = Re[ sum_i weight terms ] * dt / (N div step), lag-major like the reference.
 // weight_mode REFERENCE reproduces the shipped weight exp(w*tau + 1i) (real exponential growth,
@@ -20,12 +21,15 @@ namespace dp {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// series[t*ld + s] -> vt[(s - s0)*N + t]  (32 x 32 tile through shared memory)
+// Decimated layout of one series: u_r[n] = v[r + n*step], r in [0, step), stored as ud[s][r][n] with row pitch NP.
+// series[t*ld + s] -> ud[((s - s0)*step + t % step)*NP + t / step]   (32 x 32 tile through shared memory)
 __global__ void __launch_bounds__(256)
-transpose_series_kernel(const cplx* __restrict__ series, int64_t ld, int N, int s0, int ns, cplx* __restrict__ vt) {
+decimate_series_kernel(const cplx* __restrict__ series, int64_t ld, int N, int s0, int ns, int step, int NP,
+                       cplx* __restrict__ ud) {
     __shared__ cplx tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-    const int tb = blockIdx.x * 32, sb = blockIdx.y * 32;
+    const int ntb = (N + 31) / 32;
+    const int tb = (int)(blockIdx.x % ntb) * 32, sb = (int)(blockIdx.x / ntb) * 32;
     for (int r = ty; r < 32; r += 8) {
         int t = tb + r, s = sb + tx;
         if (t < N && s < ns) tile[r][tx] = series[(int64_t)t * ld + s0 + s];
@@ -33,74 +37,99 @@ transpose_series_kernel(const cplx* __restrict__ series, int64_t ld, int N, int 
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         int s = sb + r, t = tb + tx;
-        if (t < N && s < ns) vt[(size_t)s * N + t] = tile[tx][r];
+        if (t < N && s < ns) ud[((size_t)s * step + t % step) * NP + t / step] = tile[tx][r];
     }
 }
 
-constexpr int CR_LAGS = 64;       // lags per CTA
-constexpr int CR_JP = 4;          // origin phases (threads per lag)
-constexpr int CR_CHUNK = 1024;    // origins per shared-memory window
+constexpr int CR_R = 8;           // lags per thread (register tile)
+constexpr int CR_CH = 512;        // origins per staged chunk
+constexpr int CR_MAXW = 4;        // warps per CTA (a CTA covers 32 * CR_R lags per warp)
 
-// C[s][a] for a in [a0, a0 + CR_LAGS): window of v staged in shared memory.
-__global__ void __launch_bounds__(CR_LAGS* CR_JP)
-lag_sums_kernel(const cplx* __restrict__ vt, int N, int step, int nl_valid, cplx* __restrict__ C, int c_ld) {
-    DP_DYNSMEM(cplx, win);
-    __shared__ cplx part[CR_JP][CR_LAGS];
-    const int s = blockIdx.y;
-    const int a0 = blockIdx.x * CR_LAGS;
-    const int la = threadIdx.x % CR_LAGS, jp = threadIdx.x / CR_LAGS;
-    const int a = a0 + la;
-    const int lag = a * step;
-    const int cnt = (a < nl_valid) ? N - lag - step : 0;          // origins j in [0, cnt)
-    const int lag_min = a0 * step;
-    const int span = CR_CHUNK + (CR_LAGS - 1) * step;             // window length in elements
-    const int cnt_max = N - lag_min - step;                       // largest origin count in this tile
-    const cplx* v = vt + (size_t)s * N;
-    double ar = 0.0, ai = 0.0;
-    for (int j0 = 0; j0 < cnt_max; j0 += CR_CHUNK) {
-        __syncthreads();
-        // origins v[j0 .. j0+CHUNK) and partners v[j0+lag_min .. j0+lag_min+span)
-        for (int e = threadIdx.x; e < CR_CHUNK; e += blockDim.x) {
-            int j = j0 + e;
-            win[e] = j < N ? v[j] : make_double2(0.0, 0.0);
-        }
-        for (int e = threadIdx.x; e < span; e += blockDim.x) {
-            int j = j0 + lag_min + e;
-            win[CR_CHUNK + e] = j < N ? v[j] : make_double2(0.0, 0.0);
-        }
-        __syncthreads();
-        const int jend = imin(CR_CHUNK, cnt - j0);
-        const cplx* pw = win + CR_CHUNK + la * step;
-        for (int e = jp; e < jend; e += CR_JP) {
-            cplx x = win[e], y = pw[e];
-            ar = fma(x.x, y.x, fma(x.y, y.y, ar));                // conj(x) * y
-            ai = fma(x.x, y.y, fma(-x.y, y.x, ai));
+// C(a) = sum_j conj(v_j) v_{j + a*step}, j < N - a*step - step  (c/correlation.c:153-157 summed once instead of
+// once per frequency).  With j = r + n*step the sum is, for every residue r, the plain autocorrelation at lag a of
+// the decimated sequence u_r WITHOUT its last element (partner index n + a <= len(u_r) - 2), so
+//   C(a) = sum_r sum_n conj(u'_r[n]) u'_r[n + a],   u'_r zero beyond len_r = (N - 1 - r) / step.
+// Register tiling: a thread owns CR_R consecutive lags and slides a CR_R-deep window of partners through registers:
+// per origin one broadcast LDS.128 (the origin) + one LDS.128 (the new partner; 9/8 padding makes the 128-byte lane
+// stride conflict-free) feed 4*CR_R = 32 DFMA, so the loop is bound by the fp64 pipe, not by shared memory.
+__global__ void __launch_bounds__(32 * CR_MAXW)
+lag_sums_kernel(const cplx* __restrict__ ud, int N, int step, int NP, int nl_valid, int nblk,
+                cplx* __restrict__ C, int c_ld) {
+    DP_DYNSMEM(cplx, sm);
+    const int nthreads = blockDim.x, tid = threadIdx.x;
+    const int LB = nthreads * CR_R;                 // lags per CTA
+    cplx* xs = sm;                                  // origins  [CR_CH]
+    cplx* ys = sm + CR_CH;                          // partners [CR_CH + LB], index k stored at k + k/8
+    const int s = (int)(blockIdx.x / nblk);
+    const int A = (int)(blockIdx.x % nblk) * LB;    // first lag of this CTA
+    const int W = CR_CH + LB;
+    const cplx* us = ud + (size_t)s * step * NP;
+    const cplx zero = make_double2(0.0, 0.0);
+    double ar[CR_R], ai[CR_R];
+#pragma unroll
+    for (int i = 0; i < CR_R; i++) { ar[i] = 0.0; ai[i] = 0.0; }
+    for (int r = 0; r < step && r < N; r++) {
+        const int len = (N - 1 - r) / step;         // u'_r
+        const int cnt = len - A;                    // origins with a partner inside this CTA's lag range
+        const cplx* u = us + (size_t)r * NP;
+        for (int n0 = 0; n0 < cnt; n0 += CR_CH) {
+            __syncthreads();
+            for (int e = tid; e < CR_CH; e += nthreads) {
+                const int j = n0 + e;
+                xs[e] = j < len ? u[j] : zero;
+            }
+            for (int k = tid; k < W; k += nthreads) {
+                const int j = n0 + A + k;
+                ys[k + (k >> 3)] = j < len ? u[j] : zero;
+            }
+            __syncthreads();
+            const int mend = (imin(CR_CH, cnt - n0) + 7) >> 3;
+            const cplx* yp = ys + 9 * tid;
+            cplx w[CR_R];
+#pragma unroll
+            for (int j = 0; j < CR_R; j++) w[j] = yp[j];
+            for (int m = 0; m < mend; m++) {
+                const cplx* xp = xs + 8 * m;
+                const cplx* yn = yp + 9 * (m + 1);
+#pragma unroll
+                for (int kk = 0; kk < CR_R; kk++) {
+                    const cplx x = xp[kk];
+                    const double nxy = -x.y;
+#pragma unroll
+                    for (int i = 0; i < CR_R; i++) {
+                        const cplx y = w[(kk + i) & (CR_R - 1)];
+                        ar[i] = fma(x.x, y.x, fma(x.y, y.y, ar[i]));          // conj(x) * y
+                        ai[i] = fma(x.x, y.y, fma(nxy, y.x, ai[i]));
+                    }
+                    w[kk] = yn[kk];
+                }
+            }
         }
     }
-    part[jp][la] = make_double2(ar, ai);
-    __syncthreads();
-    if (jp == 0 && a < nl_valid) {
-        cplx acc = part[0][la];
 #pragma unroll
-        for (int q = 1; q < CR_JP; q++) acc = cadd(acc, part[q][la]);
-        C[(size_t)s * c_ld + a] = acc;
+    for (int i = 0; i < CR_R; i++) {
+        const int a = A + tid * CR_R + i;
+        if (a < nl_valid) C[(size_t)s * c_ld + a] = make_double2(ar[i], ai[i]);
     }
 }
 
 // D(a) = sum_{j < cnt_a} conj(v_j) v_{j + lag_a + step} = C(a+1) + the `step` trailing origins
 __global__ void __launch_bounds__(256)
-lag_sums_shifted_kernel(const cplx* __restrict__ vt, int N, int step, int nl_valid, int ns,
+lag_sums_shifted_kernel(const cplx* __restrict__ ud, int N, int step, int NP, int nl_valid, int ns,
                         const cplx* __restrict__ C, cplx* __restrict__ D, int c_ld) {
     int64_t total = (int64_t)ns * nl_valid;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
         int s = (int)(e / nl_valid), a = (int)(e % nl_valid);
-        const cplx* v = vt + (size_t)s * N;
+        const cplx* us = ud + (size_t)s * step * NP;
         int lag1 = (a + 1) * step;
         int cnt = N - a * step - step;
         int cnt1 = imax(cnt - step, 0);
         cplx acc = (a + 1 < nl_valid) ? C[(size_t)s * c_ld + a + 1] : make_double2(0.0, 0.0);
-        for (int j = cnt1; j < cnt; j++) acc = cadd(acc, cmul(cconj(v[j]), v[j + lag1]));
+        for (int j = cnt1; j < cnt; j++) {
+            const int k = j + lag1;
+            acc = cadd(acc, cmul(cconj(us[(size_t)(j % step) * NP + j / step]), us[(size_t)(k % step) * NP + k / step]));
+        }
         D[(size_t)s * c_ld + a] = acc;
     }
 }
@@ -145,37 +174,61 @@ corr_weights_kernel(const double* __restrict__ freq, int F, int nl_valid, int st
     }
 }
 
+constexpr int CS_SB = 4;          // series per thread of the weighting pass (one weight load serves CS_SB products)
+
+// out[f][s] = Re sum_a (weight terms) * dt / (N div step): thread = (frequency, block of CS_SB series)
 __global__ void __launch_bounds__(256)
 corr_spectrum_kernel(const cplx* __restrict__ C, const cplx* __restrict__ D, const cplx* __restrict__ W,
                      int s0, int ns, int S, int F, int nl_valid, int c_ld, int method, double dt, double ndiv, double scale,
                      double* __restrict__ out) {
-    int64_t total = (int64_t)ns * F;
+    const int nsb = (ns + CS_SB - 1) / CS_SB;
+    int64_t total = (int64_t)nsb * F;
     const int64_t wsz = (int64_t)nl_valid * F;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
-        int s = (int)(e / F), f = (int)(e % F);
-        double ar = 0.0, ai = 0.0;
-        for (int a = 0; a < nl_valid; a++) {
-            cplx c = C[(size_t)s * c_ld + a];
-            cplx t = cmul(c, W[(int64_t)a * F + f]);
-            ar += t.x; ai += t.y;
-            if (method == 0) {
-                cplx ti = cmul(D[(size_t)s * c_ld + a], W[wsz + (int64_t)a * F + f]);
-                cplx tj = cmul(c, W[2 * wsz + (int64_t)a * F + f]);
-                ar = ar + ti.x + tj.x; ai = ai + ti.y + tj.y;
-            } else {
-                ar += t.x; ai += t.y;
+        const int sb = (int)(e / F) * CS_SB, f = (int)(e % F);
+        const cplx* c[CS_SB];
+        const cplx* d[CS_SB];
+        double ar[CS_SB];
+#pragma unroll
+        for (int i = 0; i < CS_SB; i++) {
+            const int s = imin(sb + i, ns - 1);
+            c[i] = C + (size_t)s * c_ld;
+            d[i] = D + (size_t)s * c_ld;
+            ar[i] = 0.0;
+        }
+        if (method == 0) {
+            for (int a = 0; a < nl_valid; a++) {
+                const cplx w0 = W[(int64_t)a * F + f], w1 = W[wsz + (int64_t)a * F + f], w2 = W[2 * wsz + (int64_t)a * F + f];
+#pragma unroll
+                for (int i = 0; i < CS_SB; i++) {
+                    const cplx ci = c[i][a], di = d[i][a];
+                    ar[i] += ci.x * w0.x - ci.y * w0.y;
+                    ar[i] = ar[i] + (di.x * w1.x - di.y * w1.y) + (ci.x * w2.x - ci.y * w2.y);
+                }
+            }
+        } else {
+            for (int a = 0; a < nl_valid; a++) {
+                const cplx w0 = W[(int64_t)a * F + f];
+#pragma unroll
+                for (int i = 0; i < CS_SB; i++) {
+                    const cplx ci = c[i][a];
+                    const double t = ci.x * w0.x - ci.y * w0.y;
+                    ar[i] += t;                                    // the reference adds Correl_i twice (:158-159, :170-171)
+                    ar[i] += t;
+                }
             }
         }
         // creal(Correl) * TimeStep / (NumberOfData / Increment)   (c/correlation.c:177)
-        out[(size_t)f * S + s0 + s] = __dmul_rn(__ddiv_rn(__dmul_rn(ar, dt), ndiv), scale);
-        (void)ai;
+#pragma unroll
+        for (int i = 0; i < CS_SB; i++)
+            if (sb + i < ns) out[(size_t)f * S + s0 + sb + i] = __dmul_rn(__ddiv_rn(__dmul_rn(ar[i], dt), ndiv), scale);
     }
 }
 
 struct CorrLayout {
-    size_t off_freq, off_W, off_C, off_D, off_vt, total;
-    int nl_valid, c_ld, chunk;
+    size_t off_freq, off_W, off_C, off_D, off_ud, total;
+    int nl_valid, c_ld, chunk, NP;
 };
 
 static CorrLayout corr_layout(int64_t T, int S, int F, int step, int method) {
@@ -189,10 +242,11 @@ static CorrLayout corr_layout(int64_t T, int S, int F, int step, int method) {
     l.off_W = o;    o += align_up((size_t)(method == 0 ? 3 : 1) * l.c_ld * F * sizeof(cplx), 256);
     l.off_C = o;    o += align_up((size_t)S * l.c_ld * sizeof(cplx), 256);
     l.off_D = o;    o += align_up((size_t)S * l.c_ld * sizeof(cplx), 256);
-    // series are transposed chunk-wise into a contiguous [chunk][N] slab of at most 1 GiB
-    size_t per = (size_t)N * sizeof(cplx);
+    // series are decimated chunk-wise into a [chunk][step][NP] slab of at most 1 GiB
+    l.NP = ((N + step - 1) / step + 7) / 8 * 8;
+    size_t per = (size_t)imin(step, N) * l.NP * sizeof(cplx);     // step >= N: no valid lag, the slab is not used
     l.chunk = (int)imin<size_t>((size_t)S, imax<size_t>(1, ((size_t)1 << 30) / per));
-    l.off_vt = o;   o += align_up((size_t)l.chunk * per, 256);
+    l.off_ud = o;   o += align_up((size_t)l.chunk * per, 256);
     l.total = o;
     return l;
 }
@@ -226,7 +280,7 @@ int dp_power_correlation(const double* series, int64_t T, int S, int64_t ld, dou
     dp::cplx* W = (dp::cplx*)(ws + lay.off_W);
     dp::cplx* C = (dp::cplx*)(ws + lay.off_C);
     dp::cplx* D = (dp::cplx*)(ws + lay.off_D);
-    dp::cplx* vt = (dp::cplx*)(ws + lay.off_vt);
+    dp::cplx* ud = (dp::cplx*)(ws + lay.off_ud);
     const double ndiv = (double)(N / step);               // integer division, c/correlation.c:177
     if (lay.nl_valid == 0) {
         // no lag has any origin: the reference returns 0 * dt / (N div step) (NaN when N < step)
@@ -243,35 +297,40 @@ int dp_power_correlation(const double* series, int64_t T, int S, int64_t ld, dou
                   (const double*)d_freq, F, lay.nl_valid, step, dt, integration_method, weight_mode, W);
         DP_CUDA_OK(cudaGetLastError());
     }
-    size_t smem = ((size_t)2 * dp::CR_CHUNK + (size_t)(dp::CR_LAGS - 1) * step) * sizeof(dp::cplx);
-    DP_REQUIRE(smem <= 200 * 1024, DP_ERR_UNSUPPORTED, "dp_power_correlation: step=%d too large", step);
+    // CTA = nw warps x 32 lanes x CR_R lags; small problems use fewer warps per CTA
+    const int nw = dp::imax(1, dp::imin(dp::CR_MAXW, (lay.nl_valid + 32 * dp::CR_R - 1) / (32 * dp::CR_R)));
+    const int lags_per_cta = nw * 32 * dp::CR_R;
+    const int nblk = (lay.nl_valid + lags_per_cta - 1) / lags_per_cta;
+    const size_t smem = ((size_t)dp::CR_CH + 9 * ((size_t)dp::CR_CH / 8 + nw * 32)) * sizeof(dp::cplx);
     for (int s0 = 0; s0 < S; s0 += lay.chunk) {
         const int ns = dp::imin(lay.chunk, S - s0);
         {
-            auto k = dp::transpose_series_kernel;
-            dim3 grid((unsigned)((N + 31) / 32), (unsigned)((ns + 31) / 32));
-            DP_LAUNCH(k, grid, dim3(256), 0, st, (const dp::cplx*)series, ld, N, s0, ns, vt);
+            auto k = dp::decimate_series_kernel;
+            const int64_t nblocks = (int64_t)((N + 31) / 32) * ((ns + 31) / 32);
+            DP_REQUIRE(nblocks < (1LL << 31), DP_ERR_UNSUPPORTED, "dp_power_correlation: chunk too large");
+            DP_LAUNCH(k, dim3((unsigned)nblocks), dim3(256), 0, st, (const dp::cplx*)series, ld, N, s0, ns, step, lay.NP, ud);
             DP_CUDA_OK(cudaGetLastError());
         }
         {
             auto k = dp::lag_sums_kernel;
             DP_CUDA_OK(DP_SET_SMEM(k, smem));
-            dim3 grid((unsigned)((lay.nl_valid + dp::CR_LAGS - 1) / dp::CR_LAGS), (unsigned)ns);
-            DP_LAUNCH(k, grid, dim3(dp::CR_LAGS * dp::CR_JP), smem, st, (const dp::cplx*)vt, N, step, lay.nl_valid,
-                      C + (size_t)s0 * lay.c_ld, lay.c_ld);
+            const int64_t nblocks = (int64_t)ns * nblk;
+            DP_REQUIRE(nblocks < (1LL << 31), DP_ERR_UNSUPPORTED, "dp_power_correlation: chunk too large");
+            DP_LAUNCH(k, dim3((unsigned)nblocks), dim3(nw * 32), smem, st, (const dp::cplx*)ud, N, step, lay.NP,
+                      lay.nl_valid, nblk, C + (size_t)s0 * lay.c_ld, lay.c_ld);
             DP_CUDA_OK(cudaGetLastError());
         }
         if (integration_method == 0) {
             auto k = dp::lag_sums_shifted_kernel;
             int64_t total = (int64_t)ns * lay.nl_valid;
             DP_LAUNCH(k, dim3((unsigned)dp::imin<int64_t>((total + 255) / 256, 65535)), dim3(256), 0, st,
-                      (const dp::cplx*)vt, N, step, lay.nl_valid, ns, (const dp::cplx*)(C + (size_t)s0 * lay.c_ld),
+                      (const dp::cplx*)ud, N, step, lay.NP, lay.nl_valid, ns, (const dp::cplx*)(C + (size_t)s0 * lay.c_ld),
                       D + (size_t)s0 * lay.c_ld, lay.c_ld);
             DP_CUDA_OK(cudaGetLastError());
         }
         {
             auto k = dp::corr_spectrum_kernel;
-            int64_t total = (int64_t)ns * F;
+            int64_t total = (int64_t)((ns + dp::CS_SB - 1) / dp::CS_SB) * F;
             DP_LAUNCH(k, dim3((unsigned)dp::imin<int64_t>((total + 255) / 256, 65535)), dim3(256), 0, st,
                       (const dp::cplx*)(C + (size_t)s0 * lay.c_ld), (const dp::cplx*)(D + (size_t)s0 * lay.c_ld),
                       (const dp::cplx*)W, s0, ns, S, F, lay.nl_valid, lay.c_ld, integration_method, dt, ndiv, scale, out);

@@ -37,6 +37,8 @@ class Dynamics:
         self._d_vm = None
         self._d_relative = None
         self._sqrt_mass = None
+        self._moments = None                      # per-atom displacement sums (host, N x 3 and N x 3 x 3)
+        self._mean_displacement_matrix = None
 
     # -- plumbing ---------------------------------------------------------------------------
     @property
@@ -120,6 +122,8 @@ class Dynamics:
         self._d_vm = None
         self._d_relative = None
         self._time_step_average = None
+        self._moments = None
+        self._mean_displacement_matrix = None
 
     @property
     def trajectory(self):
@@ -187,3 +191,62 @@ class Dynamics:
 
     def get_relative_trajectory(self):
         return self._to_host_complex(self.relative_trajectory_device())
+
+    # -- displacement statistics (dynamics.py:207-295) from ONE fused pass over the positions ---------
+    def _displacement_moments(self):
+        if self._moments is None:
+            from .ops import to_host
+            sums = to_host(self.ops.displacement_moments(self._to_device(self.trajectory), self.positions_supercell(),
+                                                         self.get_supercell()))
+            s1 = sums[:, :3]
+            i, j = np.triu_indices(3)
+            s2 = np.empty((sums.shape[0], 3, 3))
+            s2[:, i, j] = sums[:, 3:]
+            s2[:, j, i] = sums[:, 3:]
+            self._moments = (s1, s2)
+        return self._moments
+
+    def get_mean_displacement_matrix(self, use_average_positions=False):
+        """dynamics.py:207-239: per atom type, sum_i sum_t u_t^T (u_t - shift_i) / (n_equiv(type) * N_cells * T)."""
+        if self._mean_displacement_matrix is None:
+            supercell = self.get_supercell_matrix()
+            atom_type = np.asarray(self.structure.get_atom_type_index())
+            per_type = np.unique(atom_type, return_counts=True)[1]
+            type_index = np.asarray(self.structure.get_atom_type_index(supercell=supercell))
+            s1, s2 = self._displacement_moments()
+            nt = self.trajectory.shape[0]
+            shift = s1 / nt if use_average_positions else np.zeros_like(s1)
+            per_atom = s2 - s1[:, :, None] * shift[:, None, :]          # sum_t u_a (u_b - shift_b)
+            nd = self.structure.get_number_of_dimensions()
+            mats = np.zeros((self.structure.get_number_of_atom_types(), nd, nd))
+            for i in range(per_atom.shape[0]):                            # reference accumulation order (:228-232)
+                mats[type_index[i]] += per_atom[i] / per_type[type_index[i]]
+            self._mean_displacement_matrix = mats / (np.prod(supercell) * nt)
+        return self._mean_displacement_matrix
+
+    def average_positions(self, number_of_samples=None, to_unit_cell=False):
+        """dynamics.py:241-295 (complex result like the reference; ``number_of_samples`` draws frames at random
+        there, which has no deterministic counterpart -- the full average is used)."""
+        supercell = self.get_supercell_matrix()
+        nd = self.structure.get_number_of_dimensions()
+        cell = self.get_supercell()
+        positions = self.structure.get_positions(supercell=supercell)
+        s1, _ = self._displacement_moments()
+        averaged = (s1 / self.trajectory.shape[0]).astype(complex)
+        natoms = averaged.shape[0]
+        if to_unit_cell:
+            cell = self.structure.get_cell()
+            natoms = self.structure.get_number_of_atoms()
+            positions = self.structure.get_positions()
+            type_unit = self.structure.get_atom_type_index()
+            type_index = self.structure.get_atom_type_index(supercell=supercell)
+            unit = np.zeros((self.structure.get_number_of_atom_types(), nd), dtype=complex)
+            norm = np.prod(supercell)
+            for i, coordinates in enumerate(averaged):
+                unit[type_index[i], :] += coordinates / norm
+            averaged = np.array([unit[type_unit[i]] for i in range(positions.shape[0])])
+        averaged = averaged + positions
+        for j in range(natoms):
+            diff = np.around(np.dot(np.linalg.inv(cell.T), averaged[j, :] - 0.5 * np.dot(np.ones(nd), cell)), decimals=0)
+            averaged[j, :] -= np.dot(diff, cell)
+        return averaged

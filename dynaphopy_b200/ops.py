@@ -110,6 +110,22 @@ class Ops:
                       T, N, float(dt), be.ptr(pf), be.ptr(nf), be.ptr(out_u), be.ptr(out_v), be.stream())
         return (out_u, out_v) if want_displacements else out_v
 
+    def displacement_moments(self, trajectory, positions, cell):
+        """(T,N,3) positions -> (N,9) per-atom sums over frames of u_k and u_a*u_b (a <= b) of the minimum-image
+        displacement (feeds dynamics.py:207-295 without materialising the relative trajectory)."""
+        be = self.be
+        cplx = be.is_complex(trajectory)
+        traj = be.asarray(trajectory, np.complex128 if cplx else np.float64)
+        T, N, _ = be.shape(traj)
+        pos = be.asarray(positions, np.float64)
+        cellh = _host(cell, np.float64)
+        sums = be.empty((N, 9), np.float64)
+        nbytes = max(self.lib.size("dp_displacement_moments_workspace_bytes", T, N), 256)
+        ws = be.empty((nbytes,), np.uint8)
+        self.lib.call("dp_displacement_moments", be.ptr(traj), int(cplx), be.ptr(pos), _hptr(cellh), T, N,
+                      be.ptr(sums), be.ptr(ws), nbytes, be.stream())
+        return sums
+
     def mass_weight(self, velocity, sqrt_mass):
         be = self.be
         cplx = be.is_complex(velocity)

@@ -87,6 +87,20 @@ int dp_velocity_from_positions(const double* traj, int traj_is_complex, const do
                                double dt, const double* prev_frame, const double* next_frame,
                                double* out_u, double* out_v, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Per-atom moments of the minimum-image displacement, fused with A8 (no T-sized output).
+ * Replaces: the per-atom np.dot / np.average loops of Dynamics.get_mean_displacement_matrix
+ *           (dynaphopy/dynamics.py:207-239) and Dynamics.average_positions (:241-295) over
+ *           Dynamics.get_relative_trajectory; the host combines the N x 9 sums per atom type.
+ *   traj, pos0, cell: as dp_atomic_displacements
+ *   sums  [dev]  N x 9: sum_t u_x, u_y, u_z, u_x u_x, u_x u_y, u_x u_z, u_y u_y, u_y u_z, u_z u_z
+ *   workspace [dev] dp_displacement_moments_workspace_bytes(T, N)
+ * ------------------------------------------------------------------------------------ */
+size_t dp_displacement_moments_workspace_bytes(int64_t T, int N);
+int dp_displacement_moments(const double* traj, int traj_is_complex, const double* pos0,
+                            const double* cell, int64_t T, int N, double* sums, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* A1 stand-alone: out = v * sqrt_mass[atom]  (dynaphopy/dynamics.py:143-156).
  * v/out: T x N x 3, real (ncomp = 1) or complex128 (ncomp = 2).                         */
 int dp_mass_weight(const double* v, int ncomp, const double* sqrt_mass, int64_t T, int N,

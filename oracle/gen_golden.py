@@ -161,6 +161,21 @@ def reading_test_case():
             out[tag + "_relative"] = np.array(dyn.get_relative_trajectory()).real
             out[tag + "_mean_matrix"] = np.average(dyn.get_mean_displacement_matrix(), axis=0)
             out[tag + "_time_step"] = dyn.get_time_step_average()
+            # dynamics.py:207-295 in full: per-type matrices, the average-position variant, average positions
+            out[tag + "_mean_matrix_types"] = np.array(dyn.get_mean_displacement_matrix())
+            dyn._mean_displacement_matrix = None
+            out[tag + "_mean_matrix_avgpos"] = np.array(dyn.get_mean_displacement_matrix(use_average_positions=True))
+            dyn._mean_displacement_matrix = None
+            out[tag + "_average_positions"] = np.array(dyn.average_positions())
+            out[tag + "_average_positions_unit"] = np.array(dyn.average_positions(to_unit_cell=True))
+            # the quantity reading_test.py:44-45, 84-85 compares with its rel_traj_ref literals
+            out[tag + "_rel_traj"] = np.array([np.average(dyn.average_positions().real - traj, axis=0).real
+                                               for traj in dyn.trajectory])
+        out["unit_cell"] = np.array(st.get_cell())
+        out["unit_pos"] = np.array(st.get_positions())
+        out["unit_masses"] = np.array(st.get_masses())
+        out["prim_matrix"] = np.array(st.get_primitive_matrix())
+        out["unit_atom_type"] = np.array(st.get_atom_type_index(), dtype=np.int32)
         # literals asserted by the reference test (reading_test.py:54-56, 94-96), rtol=1e-3, atol=1e-6
         out["xdatcar_mean_matrix_literal"] = np.array([[0.00065253, 0.00016701, 0.00033313],
                                                        [0.00016701, 0.00063413, 0.00023646],
@@ -179,6 +194,9 @@ def main():
         sys.exit("needs /root/reference and `make -C oracle ref`")
     os.makedirs(OUT, exist_ok=True)
     ref_python.load()
+    if "--reading-only" in sys.argv:
+        reading_test_case()
+        return
     a = 4.0
     # identity-primitive 2-atom cubic cell, 2x3x2 supercell; commensurate q incl. Gamma, zone
     # boundary, a q outside the first zone, and one non-commensurate q

@@ -269,6 +269,19 @@ def relative_trajectory(trajectory, positions, cell):
     return out
 
 
+def mean_displacement_matrix(rel, atom_type_supercell, atom_type_unit, n_cells, use_average_positions=False):
+    """Dynamics.get_mean_displacement_matrix (dynamics.py:207-239) on a (T,N,3) relative trajectory."""
+    rel = np.asarray(rel)
+    per_type = np.unique(atom_type_unit, return_counts=True)[1]
+    ntypes = len(per_type)
+    diff = np.average(rel, axis=0) if use_average_positions else np.zeros(rel.shape[1:])
+    mats = np.zeros((ntypes, 3, 3))
+    for i in range(rel.shape[1]):
+        mats[atom_type_supercell[i]] += np.dot(np.conj(rel[:, i, :]).T, rel[:, i, :] - diff[i]).real \
+            / per_type[atom_type_supercell[i]]
+    return mats / (n_cells * rel.shape[0])
+
+
 def velocity_from_relative(rel, time_step):
     """Dynamics.velocity (dynamics.py:313-329): np.gradient along time for every (atom, dim)."""
     return np.gradient(rel, time_step, axis=0)

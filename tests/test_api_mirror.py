@@ -92,3 +92,30 @@ def test_selector_contract_and_errors(kops, monkeypatch):
     assert relerr(calc2.dynamic.get_velocity_mass_average(), g["vm"][-100:]) < 1e-15
     assert power_spectrum._division_of_data(0.05, 50001, 0.001) == [[0, 20000], [15000, 35000], [30001, 50001]]
     Parameters().reset()
+
+
+@pytest.mark.parametrize("tag", ["xdatcar", "lammps"])
+def test_dynamics_displacement_statistics_vs_reference(kops, tag):
+    """Dynamics.get_mean_displacement_matrix / average_positions (dynamics.py:207-295) as unittest/reading_test.py
+    drives them, against what the reference returned (and its literals, reading_test.py:54-60, 94-99)."""
+    from dynaphopy_b200.dynamics import Dynamics
+    from dynaphopy_b200.structure import Structure
+    g = golden("reading_test")
+    st = Structure(cell=g["unit_cell"], positions=g["unit_pos"], masses=g["unit_masses"], primitive_matrix=g["prim_matrix"])
+    assert np.array_equal(st.get_atom_type_index(), g["unit_atom_type"])
+
+    def make():
+        return Dynamics(structure=st, trajectory=g[tag + "_trajectory"].astype(complex), supercell=g[tag + "_supercell"],
+                        time=np.arange(12) * float(g[tag + "_time_step"]), ops=kops)
+    dyn = make()
+    assert np.array_equal(dyn.get_supercell_matrix(), [2, 2, 2])
+    mats = dyn.get_mean_displacement_matrix()
+    assert relerr(mats, g[tag + "_mean_matrix_types"]) < 1e-12
+    assert np.allclose(np.average(mats, axis=0), g[tag + "_mean_matrix_literal"], rtol=1e-3, atol=1e-6)
+    assert relerr(make().get_mean_displacement_matrix(use_average_positions=True), g[tag + "_mean_matrix_avgpos"]) < 1e-12
+    ap = dyn.average_positions()
+    assert ap.dtype == np.complex128 and relerr(ap, g[tag + "_average_positions"]) < 1e-14
+    assert relerr(dyn.average_positions(to_unit_cell=True), g[tag + "_average_positions_unit"]) < 1e-14
+    # the reference's rel_traj check is a difference of O(10) numbers compared at 1e-9: only meaningful to ~1e-14 absolute
+    rel_traj = np.array([np.average(ap.real - traj, axis=0).real for traj in g[tag + "_trajectory"]])
+    assert np.abs(rel_traj - g[tag + "_rel_traj"]).max() < 1e-13

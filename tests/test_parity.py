@@ -73,6 +73,28 @@ def test_reading_test_known_answers(kops, tag):
     assert np.allclose(mean, g[tag + "_mean_matrix_literal"], rtol=1e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("tag", ["xdatcar", "lammps"])
+def test_displacement_moments(kops, tag):
+    """Fused displacement + per-atom sums (feeds dynamics.py:207-295) against the reference's relative trajectory."""
+    g = golden("reading_test")
+    u = g[tag + "_relative"]
+    sums = to_np(kops.displacement_moments(g[tag + "_trajectory"], g[tag + "_positions"], g[tag + "_supercell"]))
+    i, j = np.triu_indices(3)
+    ref = np.concatenate([u.sum(0), (u[:, :, i] * u[:, :, j]).sum(0)], axis=1)
+    assert sums.shape == (u.shape[1], 9)
+    assert np.abs(sums - ref).max() <= 1e-13 * np.abs(ref).max()
+    # long run, several time splits, complex128 positions (real part used), wrapped atoms
+    rng = np.random.default_rng(31)
+    cell = np.array([[8.0, 0.3, 0.0], [0.0, 9.0, 0.4], [0.5, 0.0, 7.0]])
+    pos = rng.random((37, 3)) @ cell
+    tr = pos[None] + rng.normal(scale=0.1, size=(2000, 37, 3)) + rng.integers(-2, 3, size=(2000, 37, 3)) @ cell
+    u = np.stack([port.atomic_displacements(tr[:, a, :], pos[a], cell) for a in range(37)], axis=1)
+    ref = np.concatenate([u.sum(0), (u[:, :, i] * u[:, :, j]).sum(0)], axis=1)
+    for arr in (tr, tr + 1j * rng.normal(size=tr.shape)):
+        sums = to_np(kops.displacement_moments(arr, pos, cell))
+        assert np.abs(sums - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
 def test_displacements_empty_and_errors(kops):
     g = golden("displacements_triclinic")
     out = kops.atomic_displacements(np.zeros((0, 24, 3)), g["positions"], g["supercell"])
@@ -374,6 +396,25 @@ def test_power_correlation_vs_oracle(kops):
     from dynaphopy_b200._lib import DpError
     with pytest.raises(DpError, match="Integration method"):         # c/correlation.c:138-141
         kops.power_correlation(x, 0.002, f, 10, 2, 0)
+
+
+def test_power_correlation_lag_tiling_edges(kops):
+    """Register-tiled lag sums: several warps / several CTAs per series, ragged residue lengths, T <= step."""
+    rng = np.random.default_rng(29)
+    f = np.array([0.0, 3.3, 17.0])
+    for nt, step in ((3000, 1), (2111, 2), (1237, 1), (300, 7), (523, 10), (21, 10), (11, 10)):
+        x = _series(rng, nt, 2, 0.002)
+        for method in (1, 0):
+            ref = port.correlation_spectra(x, 0.002, f, step, method, "intended")
+            pc = to_np(kops.power_correlation(x, 0.002, f, step, method, 1))
+            assert relerr(pc, ref) < TOL, (nt, step, method)
+    # no lag has an origin (N <= step): 0 * dt / (N div step), NaN when N < step -- c/correlation.c:153,177
+    for nt in (10, 5):
+        x = _series(rng, nt, 2, 0.002)
+        ref = port.correlation_spectra(x, 0.002, f, 10, 1, "intended")
+        pc = to_np(kops.power_correlation(x, 0.002, f, 10, 1, 1))
+        assert np.array_equal(np.isnan(pc), np.isnan(ref))
+        assert np.array_equal(np.nan_to_num(pc), np.nan_to_num(ref))
 
 
 def test_spectra_single_column_and_two_frequencies(kops):

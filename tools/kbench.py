@@ -57,6 +57,8 @@ if "disp" in which:
     report("velocity_from_positions", t, nbytes=48.0 * N * T)
     t = timeit(lambda: ops.atomic_displacements(traj, pos, supercell))
     report("atomic_displacements", t, nbytes=48.0 * N * T)
+    t = timeit(lambda: ops.displacement_moments(traj, pos, supercell))
+    report("displacement_moments", t, nbytes=24.0 * N * T)
     del traj
 
 v = torch.randn((T, N, 3), dtype=torch.float64, device=dev, generator=g)
@@ -110,7 +112,7 @@ if "mem" in which:
         report(f"power_mem T={Ts} S={S} m={m}", t, flops=20.0 * m * Ts * S * 2 / 2, extra=f"series/s={S / t[0]:.2f}")
         del x
 if "corr" in which:
-    for (Ts, S) in ((2500, 192), (32768, int(os.environ.get("KB_SC", 64)))):
+    for (Ts, S) in ((2500, 192), (32768, int(os.environ.get("KB_SC", 64))), (131072, int(os.environ.get("KB_SC", 64)))):
         x = torch.randn((Ts, S), dtype=torch.complex128, device=dev)
         t = timeit(lambda: ops.power_correlation(x, 0.001, freq, 10, 1, 1), reps=2, warm=1)
         report(f"power_correlation T={Ts} S={S}", t, flops=4.0 * Ts * Ts / 10 * S, extra=f"series/s={S / t[0]:.2f}")
