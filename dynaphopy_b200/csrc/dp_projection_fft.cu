@@ -129,9 +129,45 @@ __device__ __noinline__ void pf_epilogue(const PfUnit& u, int npad, int Q, int n
     cplx* __restrict__ outA = u.outA;
     cplx* __restrict__ outB = u.outB;
     const int64_t qstride = u.qstride;
-    const bool xpose = hasA && hasB && qstride == 2 && outB == outA + 1 && (nthreads & 31) == 0;    // warp-uniform
-    // the trip count is warp-uniform (first lane's q decides): every lane takes part in the shuffles below
-    for (int q0 = tid; q0 - (tid & 31) < Q; q0 += 4 * nthreads) {
+    if (!ACC && hasA && hasB && qstride == 2 && outB == outA + 1 && (nthreads & 31) == 0) {
+        // Pair-major layout: (A, B) of 32 consecutive q are 1 KB contiguous.  A lane computes ONE of the two
+        // sequences (even lanes A, odd lanes B) of wave vector 16h + lane/2 of its group, so consecutive lanes hold
+        // consecutive 16-byte values: every warp store is one fully coalesced 512-byte run, no shuffles, no
+        // divergence; the pair of lanes that shares a wave vector reads the same two bins (shared-memory broadcast).
+        // Two groups (four outputs) are in flight per thread.
+        const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+        const bool par = lane & 1;
+        const int sub = lane >> 1;
+        const int ngroups = (Q + 31) >> 5;
+        const cplx* __restrict__ tw = par ? twB : twA;
+        for (int g0 = warp; g0 < ngroups; g0 += 2 * nwarps) {
+            int q[4];
+            unsigned o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                q[j] = (g0 + (j >> 1) * nwarps) * 32 + (j & 1) * 16 + sub;
+                o[j] = qo[imin(q[j], Q - 1)];
+            }
+            cplx C[4], D[4], w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                C[j] = W[o[j] & 0xffffu];
+                D[j] = W[o[j] >> 16];
+                if (TW) w[j] = __ldg(tw + (int64_t)imin(q[j], Q - 1) * n_unit);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // A = (0.5 (C.x + D.x), 0.5 (C.y - D.y)),  B = (0.5 (C.y + D.y), 0.5 (D.x - C.x))
+                const double a1 = par ? C[j].y : C[j].x, b1 = par ? D[j].y : D[j].x;
+                const double a2 = par ? D[j].x : C[j].y, b2 = par ? C[j].x : D[j].y;
+                cplx r = make_double2(0.5 * (a1 + b1), 0.5 * (a2 - b2));
+                if (TW) r = cmul(r, w[j]);
+                if (q[j] < Q) __stcs(outA + (int64_t)(q[j] - sub) * 2 + lane, r);
+            }
+        }
+        return;
+    }
+    for (int q0 = tid; q0 < Q; q0 += 4 * nthreads) {
         cplx wa[4], wb[4];
         if (TW) {
 #pragma unroll
@@ -144,25 +180,12 @@ __device__ __noinline__ void pf_epilogue(const PfUnit& u, int npad, int Q, int n
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int q = q0 + i * nthreads;
-            const unsigned o = qo[imin(q, Q - 1)];
-            const cplx C = W[o & 0xffffu], D = W[o >> 16];
-            cplx ra = make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y));
-            cplx rb = make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x));
-            if (TW) { ra = cmul(ra, wa[i]); rb = cmul(rb, wb[i]); }
-            if (!ACC && xpose) {
-                // pair-major layout: (A, B) of 32 consecutive q are 1 KB contiguous.  Exchange inside the warp so
-                // that consecutive lanes store consecutive 16-byte values: two fully coalesced 512-byte stores
-                // instead of two stores of half-filled sectors.
-                const int lane = tid & 31, qbase = q - lane;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int src = h * 16 + (lane >> 1);
-                    const double ax = __shfl_sync(0xffffffffu, ra.x, src), ay = __shfl_sync(0xffffffffu, ra.y, src);
-                    const double bx = __shfl_sync(0xffffffffu, rb.x, src), by = __shfl_sync(0xffffffffu, rb.y, src);
-                    if (qbase + src < Q)
-                        __stcs(outA + (int64_t)(qbase + h * 16) * 2 + lane, (lane & 1) ? make_double2(bx, by) : make_double2(ax, ay));
-                }
-            } else if (q < Q) {
+            if (q < Q) {
+                const unsigned o = qo[q];
+                const cplx C = W[o & 0xffffu], D = W[o >> 16];
+                cplx ra = make_double2(0.5 * (C.x + D.x), 0.5 * (C.y - D.y));
+                cplx rb = make_double2(0.5 * (C.y + D.y), 0.5 * (D.x - C.x));
+                if (TW) { ra = cmul(ra, wa[i]); rb = cmul(rb, wb[i]); }
                 if (ACC) {
                     if (hasA) ra = cadd(outA[q * qstride], ra);
                     if (hasB) rb = cadd(outB[q * qstride], rb);

@@ -248,20 +248,23 @@ class MeshPipeline:
         return recv.reshape(g * nch, s_loc, tc)
 
     # -- host-resident trajectory: chunked H2D copies overlapped with the projection ------------------
-    def run_from_host(self, velocity_host, chunk_frames=2048):
+    def run_from_host(self, velocity_host, chunk_frames=2048, stage_slots=8):
         """velocity_host: pinned (Tl, N, 3) float64 torch tensor on the host.  Frames are copied in
-        chunks on a side stream into a two-slot staging buffer while the previous chunk is being
-        projected and contracted; the spectra come back to the host as numpy."""
+        chunks on a side stream into a ring of ``stage_slots`` staging buffers while earlier chunks are being
+        projected and contracted; the spectra come back to the host as numpy.  The ring is deep enough to ride out
+        the spectrum launches that the streamed-window path inserts between chunks (a pair of windows of every series
+        keeps the SMs busy for tens of milliseconds, during which the copy engine must keep running)."""
         import torch
         be = self.be
         tl = velocity_host.shape[0]
         n = velocity_host.shape[1]
         send = be.empty((self.world, self.q_block * self.M, tl), np.complex128)
-        stage = [be.empty((min(chunk_frames, tl), n, 3), np.float64) for _ in range(2)]
+        nslots = max(2, min(int(stage_slots), (tl + chunk_frames - 1) // chunk_frames))
+        stage = [be.empty((min(chunk_frames, tl), n, 3), np.float64) for _ in range(nslots)]
         copy_stream = torch.cuda.Stream(device=be.device)
         main = torch.cuda.current_stream(be.device)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        ready = [torch.cuda.Event() for _ in range(nslots)]
+        freed = [torch.cuda.Event() for _ in range(nslots)]
         # single rank + FFT method: the spectra of a window start as soon as its frames have been contracted,
         # underneath the remaining host->device copies (windows go in pairs, the unit the kernel works in)
         stream_windows = self.world == 1 and self.algorithm in (2, 3, 4, 5)
@@ -272,14 +275,26 @@ class MeshPipeline:
             ws = self.ops.power_fft_begin(tl, n_series, self.dt, self.freq)
             done = 0
         starts = list(range(0, tl, chunk_frames))
-        for i, t0 in enumerate(starts):
-            slot = i % 2
+
+        def enqueue_copy(i):
+            # host -> staging slot on the copy stream; a slot is reused once the chunk that occupied it is contracted
+            slot, t0 = i % nslots, starts[i]
             t1 = min(t0 + chunk_frames, tl)
             with torch.cuda.stream(copy_stream):
-                if i >= 2:
+                if i >= nslots:
                     copy_stream.wait_event(freed[slot])
                 stage[slot][: t1 - t0].copy_(velocity_host[t0:t1], non_blocking=True)
                 ready[slot].record(copy_stream)
+
+        # copies are queued nslots - 1 chunks ahead of the kernels that consume them: the launch path blocks the host
+        # on the stream once per chunk (q-bin validation), which must not leave the copy engine idle
+        for j in range(min(nslots - 1, len(starts))):
+            enqueue_copy(j)
+        for i, t0 in enumerate(starts):
+            slot = i % nslots
+            t1 = min(t0 + chunk_frames, tl)
+            if i + nslots - 1 < len(starts):
+                enqueue_copy(i + nslots - 1)               # its slot was freed at the end of iteration i - 1
             main.wait_event(ready[slot])
             self.series(stage[slot][: t1 - t0], chunk_frames, out=send, t_offset=t0, t_total=tl)
             freed[slot].record(main)

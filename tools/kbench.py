@@ -105,6 +105,15 @@ if "fft" in which:
         t = timeit(lambda: ops.power_fft(xt, dt, freq, series_major=True), reps=3, warm=1)
         report(f"power_fft series-major T={Ts} S={S}", t, nbytes=16.0 * L * len(pieces) * S, extra=f"L={L} pieces={len(pieces)} series/s={S / t[0]:.1f}")
         del x, xt
+if "fft5b" in which:
+    # cfg 5-B: one window of the whole run, resolution 2^-17/dt (L = T = 131072, P = 2^18, 5244 frequencies)
+    Ts, S, dt5 = 131072, int(os.environ.get("KB_S5B", 296)), 0.001
+    f5b = np.arange(5244) * (1.0 / (Ts * dt5))
+    x = torch.randn((S, Ts), dtype=torch.complex128, device=dev)
+    t = timeit(lambda: ops.power_fft(x, dt5, f5b, series_major=True), reps=2, warm=1)
+    L, pieces = ops.fft_pieces(Ts, dt5, f5b)
+    report(f"power_fft cfg5-B T={Ts} S={S}", t, nbytes=16.0 * L * S, extra=f"L={L} pieces={len(pieces)} series/s={S / t[0]:.1f}")
+    del x
 if "mem" in which:
     for (Ts, S, m) in ((2500, 192, 1000), (131072, int(os.environ.get("KB_SM", 148)), 1000)):
         x = torch.randn((Ts, S), dtype=torch.complex128, device=dev)

@@ -11,12 +11,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     qb = torch.as_tensor(mm, device=ops.be.device)
     v = torch.randn((T, 2 * nc, 3), dtype=torch.float64, device=ops.be.device)
     for _ in range(2):
-        ops.project_commensurate(v, dims, [0, 1], 2, qb, None)
+        ops.project_commensurate(v, dims, [0, 1], 2, qb, None, pair_major=True)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(5):
-        ops.project_commensurate(v, dims, [0, 1], 2, qb, None)
+        ops.project_commensurate(v, dims, [0, 1], 2, qb, None, pair_major=True)
     b.record(); torch.cuda.synchronize()
     print("skip=%s threads=%s  %.3f ms" % (os.environ.get("DP_PF_SKIP", "0"), os.environ.get("DP_PF_THREADS", "auto"), a.elapsed_time(b) / 5), flush=True)
 else:
