@@ -110,7 +110,12 @@ __device__ __forceinline__ unsigned long long s2_slab_policy() {
     return 0;
 #else
     unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+#ifndef DP_S2_EVICT_FRAC
+#define DP_S2_EVICT_FRAC 1.0
+#endif
+#define DP_S2_STR2(x) #x
+#define DP_S2_STR(x) DP_S2_STR2(x)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, " DP_S2_STR(DP_S2_EVICT_FRAC) ";\n" : "=l"(pol));
     return pol;
 #endif
 }

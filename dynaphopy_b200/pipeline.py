@@ -12,6 +12,8 @@ one contiguous block per destination rank, every (q, s) series contiguous in tim
 spectrum kernel reads the received (source rank, series, time) blocks in place
 (``dp_power_fft_strided``), so there is no pack or unpack pass and every stage streams contiguous runs.
 """
+import os
+
 import numpy as np
 
 from . import ops as _ops
@@ -254,10 +256,12 @@ class MeshPipeline:
         projected and contracted; the spectra come back to the host as numpy.  The ring is deep enough to ride out
         the spectrum launches that the streamed-window path inserts between chunks (a pair of windows of every series
         keeps the SMs busy for tens of milliseconds, during which the copy engine must keep running)."""
+        import time
         import torch
         be = self.be
         tl = velocity_host.shape[0]
         n = velocity_host.shape[1]
+        h0 = time.perf_counter()
         send = be.empty((self.world, self.q_block * self.M, tl), np.complex128)
         nslots = max(2, min(int(stage_slots), (tl + chunk_frames - 1) // chunk_frames))
         stage = [be.empty((min(chunk_frames, tl), n, 3), np.float64) for _ in range(nslots)]
@@ -275,6 +279,8 @@ class MeshPipeline:
             ws = self.ops.power_fft_begin(tl, n_series, self.dt, self.freq)
             done = 0
         starts = list(range(0, tl, chunk_frames))
+        trace = [] if os.environ.get("DP_E2E_TRACE") else None      # development aid: copy-engine timeline
+        h1 = time.perf_counter()
 
         def enqueue_copy(i):
             # host -> staging slot on the copy stream; a slot is reused once the chunk that occupied it is contracted
@@ -283,8 +289,13 @@ class MeshPipeline:
             with torch.cuda.stream(copy_stream):
                 if i >= nslots:
                     copy_stream.wait_event(freed[slot])
+                if trace is not None:
+                    trace.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                    trace[-1][0].record(copy_stream)
                 stage[slot][: t1 - t0].copy_(velocity_host[t0:t1], non_blocking=True)
                 ready[slot].record(copy_stream)
+                if trace is not None:
+                    trace[-1][1].record(copy_stream)
 
         # copies are queued nslots - 1 chunks ahead of the kernels that consume them: the launch path blocks the host
         # on the stream once per chunk (q-bin validation), which must not leave the copy engine idle
@@ -305,12 +316,45 @@ class MeshPipeline:
                     self.ops.power_fft_windows(send, self.dt, self.freq, done, ready_now, ws, series_major=True)
                     done += ready_now
         del stage
+        if trace is not None:
+            h2 = time.perf_counter()
+            torch.cuda.synchronize()
+            h3 = time.perf_counter()
+            print("e2e host: setup %.1f ms, launch loop %.1f ms, drain %.1f ms" % ((h1 - h0) * 1e3, (h2 - h1) * 1e3, (h3 - h2) * 1e3))
+            t_end = torch.cuda.Event(enable_timing=True)
+            t_end.record(main)
+            t_end.synchronize()
+            busy = sum(a.elapsed_time(b) for a, b in trace)
+            gaps = [trace[k][1].elapsed_time(trace[k + 1][0]) for k in range(len(trace) - 1)]
+            print("e2e trace: copies %.1f ms busy, span %.1f ms, gaps > 0.5 ms: %s, tail after last copy %.1f ms" % (
+                busy, trace[0][0].elapsed_time(trace[-1][1]), [(k, round(g, 1)) for k, g in enumerate(gaps) if g > 0.5],
+                trace[-1][1].elapsed_time(t_end)), flush=True)
         if stream_windows:
             ps = self.ops.power_fft_finish(tl, n_series, self.dt, self.freq, ws)
-            return ps.cpu().numpy()
+            if trace is not None:
+                h4 = time.perf_counter()
+                out = self._to_host_pinned(ps)
+                print("e2e host: finish launch %.1f ms, D2H %.1f ms" % ((h4 - h3) * 1e3, (time.perf_counter() - h4) * 1e3), flush=True)
+                return out
+            return self._to_host_pinned(ps)
         blocks = self.exchange_series(send)
         ps = self.spectra_series(blocks)
-        return ps.cpu().numpy()
+        return self._to_host_pinned(ps)
+
+    def _to_host_pinned(self, ps):
+        """Device spectra -> numpy through a pinned host buffer kept on the pipeline (a pageable ``.cpu()`` of the
+        (F, S) array costs ~90 ms of page faults at cfg 5; the pinned copy runs at PCIe rate).  The returned array
+        aliases that buffer: it is valid until the next ``run_from_host`` call of this pipeline."""
+        import torch
+        if not torch.is_tensor(ps):
+            return np.asarray(ps)
+        buf = getattr(self, "_host_out", None)
+        if buf is None or buf.shape != ps.shape or buf.dtype != ps.dtype:
+            buf = torch.empty(ps.shape, dtype=ps.dtype, pin_memory=True)
+            self._host_out = buf
+        buf.copy_(ps, non_blocking=True)
+        torch.cuda.current_stream(ps.device).synchronize()
+        return buf.numpy()
 
 
 def _dist_ready():
