@@ -45,6 +45,9 @@ FREQ = np.arange(0, 40.05, 0.05)
 CHUNK = 1024             # frames generated / copied per chunk
 
 
+FP64_PEAK_TOPS = 18.3     # measured fp64 lane-ops/s (tools/micro/fp64_rate.cu); x2 flop for FMA
+
+
 def workload(frames):
     cell = np.eye(3) * A_LAT
     nc = int(np.prod(DIMS))
@@ -318,6 +321,30 @@ def run_ours(args):
     peak_bin = int(torch.argmax(ps[:, 0]).item())
     checksum = float(ps.sum().item())
 
+    # ---- the other two spectrum methods of the selector on a bounded sample of the SAME series (not in the timed
+    # region; the metric names "mode spectra/s" per algorithm): maximum entropy (m = 1000) and direct correlation
+    methods = None
+    if world == 1 and not args.skip_methods:
+        def timed(fn):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) * 1e-3, out
+        ns_c, ns_m = 128, 148
+        x = send[0, :ns_m, :].t().contiguous()                      # (T, S) time-major, the reference's layout
+        t_c, _ = timed(lambda: ops.power_correlation(x[:, :ns_c], DT, FREQ, 10, 1, 1))
+        t_m, _ = timed(lambda: ops.power_mem(x, DT, FREQ, 1000))
+        fl_c = 4.0 * tl * tl / 10 * ns_c
+        methods = {
+            "fft": {"series_per_s": wl["Q"] * wl["M"] / (np.mean(stage_ms["spectra"]) * 1e-3), "sample": "all series (timed region)"},
+            "correlation": {"series_per_s": ns_c / t_c, "sample": "%d series, step 10, method 1" % ns_c,
+                            "fp64_TFLOPs": fl_c / t_c / 1e12, "frac_of_fp64_peak": fl_c / t_c / 1e12 / (2 * FP64_PEAK_TOPS),
+                            "full_job_extrapolated_s": wl["Q"] * wl["M"] / (ns_c / t_c)},
+            "mem": {"series_per_s": ns_m / t_m, "sample": "%d series, 1000 coefficients" % ns_m,
+                    "full_job_extrapolated_s": wl["Q"] * wl["M"] / (ns_m / t_m)},
+        }
+        del x
+
     # ---- end to end through the host-facing call (pinned host trajectory) -----------------------------
     e2e = None
     if not args.skip_e2e:
@@ -394,7 +421,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(wl, frames, world),
             "mode_spectra_per_s": wl["Q"] * wl["M"] / (ms_per_step * 1e-3),
-            "stages": stages, "roofline": roofline, "gpu_launches": int(launches),
+            "stages": stages, "spectra_methods": methods, "roofline": roofline, "gpu_launches": int(launches),
             "result_check": {"peak_bin_series0": peak_bin, "peak_freq_THz": float(FREQ[peak_bin]), "checksum": checksum}}
     if e2e:
         line["e2e"] = e2e
@@ -429,6 +456,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=131072, help="total frames (default: the full 2^17 workload)")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-methods", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=1024)  # <= 1024 (one generator chunk)
     ap.add_argument("--cpu-q", type=int, default=4)

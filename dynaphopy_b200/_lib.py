@@ -44,6 +44,7 @@ SIGNATURES = {
     "dp_power_mem": (_I, [_P, _L, _I, _L, _D, _P, _I, _I, _D, _I, _P, _P, _Z, _P]),
     "dp_power_correlation_workspace_bytes": (_Z, [_L, _I, _I, _I]),
     "dp_power_correlation": (_I, [_P, _L, _I, _L, _D, _P, _I, _I, _I, _I, _D, _P, _P, _Z, _P]),
+    "dp_spectra_peaks": (_I, [_P, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     "dp_fft_c2c_workspace_bytes": (_Z, [_I, _I]),
     "dp_fft_c2c": (_I, [_P, _P, _I, _I, _I, _P, _Z, _P]),
 }

@@ -333,6 +333,32 @@ class Ops:
                       int(integration_method), int(weight), float(scale), be.ptr(out), be.ptr(ws), nbytes, be.stream())
         return out
 
+    def spectra_peaks(self, spectra, sets=None, want_average=True):
+        """(F, S) spectra -> (averaged (F, S) or None, peak_bin (S,), peak_height (S,)).  ``sets``: list of lists of
+        series indices (degenerate sets, analysis/fitting/__init__.py:17-39); every series must be in exactly one."""
+        be = self.be
+        ps = be.asarray(spectra, np.float64)
+        F, S = be.shape(ps)
+        d_ptr = d_mem = d_sid = None
+        n_sets = 0
+        if sets is not None:
+            ptr = np.zeros(len(sets) + 1, dtype=np.int32)
+            ptr[1:] = np.cumsum([len(g) for g in sets])
+            mem = np.concatenate([np.asarray(g, dtype=np.int32) for g in sets]) if len(sets) else np.zeros(0, np.int32)
+            sid = np.full(S, -1, dtype=np.int32)
+            for k, g in enumerate(sets):
+                sid[np.asarray(g, dtype=int)] = k
+            if mem.size != S or (sid < 0).any() or mem.min() < 0 or mem.max() >= S:
+                raise ValueError("degenerate sets must partition the series")
+            d_ptr, d_mem, d_sid = be.asarray(ptr, np.int32), be.asarray(mem, np.int32), be.asarray(sid, np.int32)
+            n_sets = len(sets)
+        avg = be.empty((F, S), np.float64) if (want_average and sets is not None) else None
+        bins = be.empty((S,), np.int32)
+        heights = be.empty((S,), np.float64)
+        self.lib.call("dp_spectra_peaks", be.ptr(ps), F, S, be.ptr(d_ptr), be.ptr(d_mem), be.ptr(d_sid), n_sets,
+                      be.ptr(avg), be.ptr(bins), be.ptr(heights), be.stream())
+        return avg, bins, heights
+
     def fft_pieces(self, T, dt, frequency_range, max_pieces=1 << 16):
         """Window list of the FFT method (host query; power_spectrum/__init__.py:33-51)."""
         f = _host(frequency_range, np.float64)

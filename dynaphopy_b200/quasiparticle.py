@@ -187,3 +187,67 @@ class Quasiparticle:
             parts = [self._spectrum(vm[:, :, k]) for k in range(vm.shape[2])]
             self._power_spectrum_partials = np.sum(parts, axis=0)
         return self._power_spectrum_partials
+
+    # -- whole commensurate mesh in one pass (the q loop of get_commensurate_points_data, :1130-1174) --------
+    def get_commensurate_points_spectra(self, eigenvectors, frequencies=None, com_points=None, use_degeneracy=None,
+                                        cutoff=1e-4):
+        """Power spectra of EVERY commensurate q point at once, ready for the fitting stage.
+
+        The reference loops over the commensurate points one q at a time (set_reduced_q_vector -> get_vc -> get_vq ->
+        get_power_spectrum_phonon -> phonon_fitting_analysis).  Here all q are projected from one pass over the
+        trajectory (``MeshPipeline``), the spectra of all Q*M modes are computed by the selected algorithm, and the
+        degenerate-set average plus the np.max / np.argmax initial guess of ``phonon_fitting_analysis``
+        (analysis/fitting/__init__.py:36-61) are taken on the device.  Lorentzian fitting stays in scipy.
+
+        eigenvectors: (Q, M, n_p, 3) in the arrangement of ``get_eigenvectors`` for every q of ``com_points``
+        frequencies:  (Q, M) harmonic frequencies (needed for the degenerate sets), or None
+        com_points:   (Q, 3) reduced q; default: all commensurate points of the MD supercell
+        Returns a dict: q_points (Q,3), power_spectra (Q,F,M), averaged (Q,F,M) or None, peak_bin (Q,M),
+        guess_position (Q,M), guess_height (Q,M), degenerate_sets (list per q)."""
+        from . import pipeline
+        from .fitting import degenerate_sets
+        from .ops import to_host
+        dyn = self.dynamic
+        st = dyn.structure
+        sc = dyn.get_supercell_matrix()
+        if com_points is None:
+            com_points = st.get_commensurate_points(sc)
+        com_points = np.atleast_2d(np.asarray(com_points, dtype=float))
+        q_cart = np.array([np.dot(q, 2.0 * np.pi * np.linalg.inv(st.get_primitive_cell()).T) for q in com_points])   # :167-169
+        n_prim = st.get_number_of_primitive_atoms()
+        M = 3 * n_prim
+        Q = len(com_points)
+        eig = np.asarray(eigenvectors, dtype=complex).reshape(Q, M, M)
+        plan = pipeline.CommensuratePlan(st.get_cell(), sc, dyn.positions_supercell(), st.get_masses(supercell=sc),
+                                         st.get_atom_type_index(supercell=sc), n_prim, q_cart)
+        if not (plan.usable() and plan.commensurate.all()):
+            raise ValueError("the batched path needs q points commensurate with a diagonal MD supercell")
+        if use_degeneracy is None:
+            use_degeneracy = bool(self.parameters.use_symmetry) and frequencies is not None
+        freq = np.asarray(self.get_frequency_range(), dtype=float)
+        pipe = pipeline.MeshPipeline(plan, eig, freq, dyn.get_time_step_average(), ops=dyn.ops,
+                                     algorithm=self.parameters.power_spectra_algorithm,
+                                     mem_coefficients=self.parameters.number_of_coefficients_mem,
+                                     correlation_step=self.parameters.correlation_function_step,
+                                     integration_method=self.parameters.integration_method,
+                                     correlation_weight=1 if getattr(self.parameters, "correlation_weight",
+                                                                     "reference") == "intended" else 0)
+        ps = pipe.run(dyn.velocity_device)                                  # (F, Q*M) on the device
+        sets_q, sets_flat = [], None
+        if use_degeneracy:
+            fr = np.asarray(frequencies, dtype=float).reshape(Q, M)
+            sets_q = [degenerate_sets(fr[i], cutoff=cutoff) for i in range(Q)]
+            sets_flat = [[i * M + j for j in g] for i, sq in enumerate(sets_q) for g in sq]
+        avg, bins, heights = dyn.ops.spectra_peaks(ps, sets_flat)
+        F = freq.size
+        bins_h = to_host(bins).reshape(Q, M)
+        out = {
+            "q_points": com_points,
+            "power_spectra": to_host(ps).reshape(F, Q, M).transpose(1, 0, 2),
+            "averaged": None if avg is None else to_host(avg).reshape(F, Q, M).transpose(1, 0, 2),
+            "peak_bin": bins_h,
+            "guess_position": freq[bins_h],
+            "guess_height": to_host(heights).reshape(Q, M),
+            "degenerate_sets": sets_q,
+        }
+        return out

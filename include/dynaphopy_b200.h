@@ -257,6 +257,24 @@ size_t dp_fft_c2c_workspace_bytes(int n, int batch);
 int dp_fft_c2c(const double* in, double* out, int n, int batch, int direction, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Hand-off to the fitting stage: degenerate-set average + initial guess for every series.
+ * Replaces: degenerate_sets / average_phonon and the np.max / np.argmax guess of
+ *           phonon_fitting_analysis (dynaphopy/analysis/fitting/__init__.py:17-39, 60-61),
+ *           run per mode inside the q loop of get_commensurate_points_data
+ *           (dynaphopy/__init__.py:1130-1174).  Lorentzian fitting stays in scipy.
+ *   spectra     [dev] F x S (the selector's output layout)
+ *   set_ptr     [dev] n_sets + 1 offsets into set_members, or NULL (no averaging)
+ *   set_members [dev] series indices grouped by degenerate set (reference order), or NULL
+ *   series_set  [dev] S: set of each series, or NULL
+ *   averaged    [dev] F x S averaged spectra, or NULL
+ *   peak_bin    [dev] S   np.argmax of the (averaged) spectrum
+ *   peak_height [dev] S   np.max
+ * ------------------------------------------------------------------------------------ */
+int dp_spectra_peaks(const double* spectra, int F, int S, const int* set_ptr, const int* set_members,
+                     const int* series_set, int n_sets, double* averaged, int* peak_bin,
+                     double* peak_height, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,3 +119,39 @@ def test_dynamics_displacement_statistics_vs_reference(kops, tag):
     # the reference's rel_traj check is a difference of O(10) numbers compared at 1e-9: only meaningful to ~1e-14 absolute
     rel_traj = np.array([np.average(ap.real - traj, axis=0).real for traj in g[tag + "_trajectory"]])
     assert np.abs(rel_traj - g[tag + "_rel_traj"]).max() < 1e-13
+
+
+def test_commensurate_points_batch_matches_q_loop(kops, monkeypatch):
+    """Quasiparticle.get_commensurate_points_spectra (all q in one pass) against the reference-style loop over q
+    (set_reduced_q_vector -> get_power_spectrum_phonon, dynaphopy/__init__.py:1130-1174) on the same object."""
+    from dynaphopy_b200.quasiparticle import Quasiparticle
+    from dynaphopy_b200.parameters import Parameters
+    from dynaphopy_b200.fitting import degenerate_sets
+    _patch_default_ops(monkeypatch, kops)
+    g = golden("cubic2_232")
+    Parameters().reset()
+    dyn = _dynamics(g, kops)
+    calc = Quasiparticle(dyn)
+    calc.parameters.frequency_range = g["freq"]
+    calc.parameters.use_symmetry = True
+    calc.select_power_spectra_algorithm(2)
+    com = dyn.structure.get_commensurate_points(dyn.get_supercell_matrix())
+    assert com.shape == (12, 3)
+    rng = np.random.default_rng(3)
+    eig = np.stack([np.linalg.qr(rng.normal(size=(6, 6)) + 1j * rng.normal(size=(6, 6)))[0].T.reshape(6, 2, 3) for _ in com])
+    fr = np.tile(np.array([0.0, 0.0, 0.0, 5.0, 5.0, 9.0]), (len(com), 1))
+    data = calc.get_commensurate_points_spectra(eig, frequencies=fr, com_points=com)
+    assert data["power_spectra"].shape == (12, g["freq"].size, 6)
+    for i, q in enumerate(com):
+        calc.set_reduced_q_vector(q)
+        calc.set_eigenvectors(eig[i], frequencies=fr[i])
+        ps = calc.get_power_spectrum_phonon()
+        assert relerr(data["power_spectra"][i], ps) < TOL
+        sets = degenerate_sets(fr[i])
+        assert sets == data["degenerate_sets"][i] == [[0, 1, 2], [3, 4], [5]]
+        for j in range(6):
+            members = [s for s in sets if j in s][0]
+            ref = np.average([data["power_spectra"][i][:, k] for k in members], axis=0)
+            assert np.array_equal(data["averaged"][i][:, j], ref)
+            assert data["guess_position"][i, j] == g["freq"][np.argmax(ref)]
+            assert data["guess_height"][i, j] == np.max(ref)

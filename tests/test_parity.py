@@ -467,3 +467,36 @@ def test_power_fft_incremental_windows(kops):
         assert relerr(out, ref) < 1e-13
         if split == [2, 2, 1]:
             assert np.array_equal(out, ref)                  # same pairing as the one-shot call: bitwise
+
+
+def test_spectra_peaks_degenerate_average_and_guess(kops):
+    """dp_spectra_peaks against analysis/fitting/__init__.py:17-39, 60-61 (degenerate_sets / average_phonon /
+    np.max + np.argmax), restated with numpy exactly as the reference writes them."""
+    from dynaphopy_b200.fitting import degenerate_sets
+    rng = np.random.default_rng(41)
+    F, Q, M = 157, 5, 6
+    ps = rng.random((F, Q * M)) ** 4
+    ps[40, 3] = ps[90, 3] = 7.0                # tie: the first maximum wins (np.argmax)
+    ps[11, 8] = np.nan                         # NaN wins np.max / np.argmax
+    ps[50, 8] = np.nan
+    freqs = np.array([[0, 0, 0, 3.1, 3.1 + 5e-5, 9.0], [1, 2, 3, 4, 5, 6], [2, 2, 2, 2, 2, 2], [1, 5, 1, 5, 1, 5],
+                      [0.0, 0.00009, 0.00018, 7, 8, 8]])
+    sets_q = [degenerate_sets(f) for f in freqs]
+    assert sets_q[0] == [[0, 1, 2], [3, 4], [5]] and sets_q[4] == [[0, 1, 2], [3], [4, 5]]    # chained membership
+    flat = [[i * M + j for j in g] for i, sq in enumerate(sets_q) for g in sq]
+    avg, bins, heights = (to_np(a) for a in kops.spectra_peaks(ps, flat))
+    for i in range(Q):
+        for j in range(M):
+            members = [g for g in sets_q[i] if j in g][0]
+            ref = np.average([ps[:, i * M + k] for k in members], axis=0)           # average_phonon
+            col = i * M + j
+            assert np.array_equal(avg[:, col], ref, equal_nan=True)
+            assert bins[col] == np.argmax(ref)
+            assert np.array_equal(heights[col], np.max(ref), equal_nan=True)
+    # without sets: plain guess per series, no averaged output
+    avg0, bins0, heights0 = kops.spectra_peaks(ps)
+    assert avg0 is None
+    assert np.array_equal(to_np(bins0), np.argmax(ps, axis=0))
+    assert np.array_equal(to_np(heights0), np.max(ps, axis=0), equal_nan=True)
+    with pytest.raises(ValueError):
+        kops.spectra_peaks(ps, flat[:-1])
