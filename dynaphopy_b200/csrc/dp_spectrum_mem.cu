@@ -11,8 +11,12 @@
 // are fixed-order trees (no atomics) so results are run-to-run reproducible.
 // Stage 2 (mem_eval_kernel): P(f) = dt * sum_parts xms / |1 - sum_k d_k z^k|^2 per (series, f).
 #include <cmath>
+#include <cstdlib>
 
 #include "dp_common.cuh"
+#ifndef DP_EMUL
+#include <cooperative_groups.h>
+#endif
 
 namespace dp {
 
@@ -123,6 +127,188 @@ __global__ void __launch_bounds__(BURG_THREADS) burg_kernel(BurgParams p) {
     }
 }
 
+#ifndef DP_EMUL
+// ---- long series: one thread-block CLUSTER per (series, part), the prediction-error arrays never leave the SMs ----
+// When 16*(N-1) bytes do not fit one CTA's shared memory the single-CTA kernel streams both arrays through L2/HBM
+// once per order (32*(N-1) bytes x m orders per part: 8.4 GB per series at N = 2^17, m = 1000).  Here a cluster of
+// BC_CTAS CTAs splits the time axis into contiguous blocks: a thread owns E consecutive samples, the forward errors
+// f live in its REGISTERS, the backward errors b in shared memory (row pitch E+1: conflict-free), and one order is
+//   sweep (registers + shared memory; the one neighbour sample a thread needs comes from a parity-double-buffered
+//   edge array, across CTAs through distributed shared memory) -> warp/CTA partial sums -> partials pushed into
+//   every peer's shared memory -> ONE cluster barrier -> every CTA adds the BC_CTAS partials in rank order.
+// Element arithmetic is the single-CTA kernel's (explicit round-to-nearest mul/sub, reference operation order).
+namespace cg = cooperative_groups;
+constexpr int BC_CTAS = 8;                       // portable cluster size
+constexpr int BC_THREADS = 512;
+constexpr int BC_WARPS = BC_THREADS / 32;
+
+struct BurgClusterSmem {
+    double red_w[2 * BC_WARPS];                  // per-warp partial (num | den)
+    double cl_red[2][BC_CTAS][2];                // [order parity][source rank] (num, den), written by the peers
+    double edge_in[2][2];                        // [order parity] (f, b) of the first sample of the NEXT rank
+    double fb0[2][BC_THREADS][2];                // [order parity][thread] (f, b) of the thread's first sample
+};
+
+template <int E>
+__global__ void __launch_bounds__(BC_THREADS, 1) burg_cluster_kernel(BurgParams p) {
+    DP_DYNSMEM(double, sm);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = p.N, m = p.m, len = N - 1;
+    BurgClusterSmem* cs = reinterpret_cast<BurgClusterSmem*>(sm);
+    double* d_a = sm + (sizeof(BurgClusterSmem) + 7) / 8;
+    double* d_b = d_a + m;
+    double* bs = d_b + m + (size_t)tid * (E + 1);          // this thread's row of backward errors
+    const int per_cta = BC_THREADS * E;
+    const int j0 = rank * per_cta + tid * E;               // first sample owned by this thread
+    BurgClusterSmem* peer[BC_CTAS];
+#pragma unroll
+    for (int r = 0; r < BC_CTAS; r++) peer[r] = cluster.map_shared_rank(cs, r);
+    const int ncl = gridDim.x / BC_CTAS, cl = blockIdx.x / BC_CTAS;
+
+    // sum of (a, b) over the whole cluster for the reduction round `par`; also delivers the first sample of this
+    // CTA (e0f, e0b) to the previous rank.  One cluster barrier.
+    auto cluster_sum2 = [&](double& a, double& b, int par, double e0f, double e0b) {
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) { cs->red_w[warp] = a; cs->red_w[BC_WARPS + warp] = b; }
+        __syncthreads();
+        if (tid < BC_CTAS) {
+            double sa = 0.0, sb = 0.0;
+#pragma unroll
+            for (int w = 0; w < BC_WARPS; w++) { sa += cs->red_w[w]; sb += cs->red_w[BC_WARPS + w]; }
+            peer[tid]->cl_red[par][rank][0] = sa;
+            peer[tid]->cl_red[par][rank][1] = sb;
+        }
+        if (tid == 0 && rank > 0) { peer[rank - 1]->edge_in[par][0] = e0f; peer[rank - 1]->edge_in[par][1] = e0b; }
+        cluster.sync();
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int r = 0; r < BC_CTAS; r++) { sa += cs->cl_red[par][r][0]; sb += cs->cl_red[par][r][1]; }
+        a = sa; b = sb;
+    };
+
+    for (int unit = cl; unit < p.nunits; unit += ncl) {
+        const int gu = p.unit0 + unit;
+        const double* x = p.series + (size_t)(gu >> 1) * 2 + (gu & 1);
+        const int64_t xs = p.ld * 2;
+        // ---- init: f[j] = x[j+1], b[j] = x[j+2] (x[N] := 0) ----
+        double f[E];
+        double pw = 0.0, num = 0.0, den = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int j = j0 + e;
+            double fj = 0.0, bj = 0.0;
+            if (j < len) {
+                fj = __ldg(x + (int64_t)(j + 1) * xs);
+                bj = (j + 2 < N) ? __ldg(x + (int64_t)(j + 2) * xs) : 0.0;
+                pw = fma(fj, fj, pw);
+                num = fma(fj, bj, num);
+                den = fma(fj, fj, fma(bj, bj, den));
+            }
+            f[e] = fj; bs[e] = bj;
+        }
+        double dummy = 0.0;
+        cluster_sum2(pw, dummy, 0, 0.0, 0.0);
+        double xms = pw / (double)N;
+        cs->fb0[1][tid][0] = f[0]; cs->fb0[1][tid][1] = bs[0];        // edges for order k = 1 (parity 1)
+        double* dprev = d_a;
+        double* dcur = d_b;
+        bool dead = false;
+        for (int k = 1; k <= m; k++) {
+            const int par = k & 1;
+            cluster_sum2(num, den, par, f[0], bs[0]);
+            if (fabs(den) < 1.0e-6) { dead = true; break; }          // c/mem.c:229 (uniform over the cluster)
+            const double c = __ddiv_rn(__dmul_rn(2.0, num), den);
+            xms = __dmul_rn(xms, __dsub_rn(1.0, __dmul_rn(c, c)));
+            for (int a = tid; a < k - 1; a += BC_THREADS)
+                dcur[a] = __dsub_rn(dprev[a], __dmul_rn(c, dprev[k - 2 - a]));
+            if (tid == 0) dcur[k - 1] = c;
+            { double* t = dprev; dprev = dcur; dcur = t; }
+            if (k == m) break;
+            // ---- sweep: update to order k, accumulate the order k+1 inner products ----
+            const int cnt_new = N - k - 1;
+            double fnx, bnx;                                          // old (f, b) of sample j0 + E
+            if (tid + 1 < BC_THREADS) { fnx = cs->fb0[par][tid + 1][0]; bnx = cs->fb0[par][tid + 1][1]; }
+            else if (rank + 1 < BC_CTAS) { fnx = cs->edge_in[par][0]; bnx = cs->edge_in[par][1]; }
+            else { fnx = 0.0; bnx = 0.0; }
+            num = 0.0; den = 0.0;
+            // the element updates keep the reference's two roundings (mul, then sub); the inner products are summed in
+            // a different order than the reference's serial loop anyway, so they use fused multiply-adds
+            if (j0 + E <= cnt_new) {                                  // whole block valid (all but one warp per order)
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const double fo = f[e], bo = bs[e];
+                    const double fn = (e + 1 < E) ? f[e + 1] : fnx;
+                    const double bn = (e + 1 < E) ? bs[e + 1] : bnx;
+                    const double f2 = __dsub_rn(fo, __dmul_rn(c, bo));
+                    const double b2 = __dsub_rn(bn, __dmul_rn(c, fn));
+                    f[e] = f2; bs[e] = b2;
+                    num = fma(f2, b2, num);
+                    den = fma(f2, f2, fma(b2, b2, den));
+                }
+            } else if (j0 < cnt_new + 1) {                             // block straddles the end of the valid range
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const double fo = f[e], bo = bs[e];
+                    const double fn = (e + 1 < E) ? f[e + 1] : fnx;
+                    const double bn = (e + 1 < E) ? bs[e + 1] : bnx;
+                    double f2 = __dsub_rn(fo, __dmul_rn(c, bo));
+                    double b2 = __dsub_rn(bn, __dmul_rn(c, fn));
+                    if (j0 + e >= cnt_new) { f2 = 0.0; b2 = 0.0; }
+                    f[e] = f2; bs[e] = b2;
+                    num = fma(f2, b2, num);
+                    den = fma(f2, f2, fma(b2, b2, den));
+                }
+            }                                                          // else: block already retired (all zeros)
+            cs->fb0[par ^ 1][tid][0] = f[0]; cs->fb0[par ^ 1][tid][1] = bs[0];
+        }
+        __syncthreads();
+        if (dead) xms = 0.0;
+        if (rank == 0) {
+            for (int a = tid; a < m; a += BC_THREADS) p.coef[(size_t)gu * m + a] = dead ? 0.0 : dprev[a];
+            if (tid == 0) p.xms[gu] = xms;
+        }
+        cluster.sync();                           // nobody starts the next unit while a peer still reads this one's edges
+    }
+}
+
+static size_t burg_cluster_smem(int E, int m) {
+    return (sizeof(BurgClusterSmem) + 7) / 8 * 8 + (2 * (size_t)m + (size_t)BC_THREADS * (E + 1)) * sizeof(double);
+}
+
+// smallest per-thread block that covers the series, or 0 when the cluster form does not apply
+static int burg_cluster_E(int64_t T, int m) {
+    const int64_t len = T - 1;
+    for (int E : {8, 16, 32})
+        if ((int64_t)BC_CTAS * BC_THREADS * E >= len && burg_cluster_smem(E, m) <= 220 * 1024) return E;
+    return 0;
+}
+
+template <int E>
+static cudaError_t launch_burg_cluster(const BurgParams& p, cudaStream_t st) {
+    auto k = burg_cluster_kernel<E>;
+    const size_t smem = burg_cluster_smem(E, p.m);
+    cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = BC_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(BC_CTAS);
+    int ncl = 0;
+    e = cudaOccupancyMaxActiveClusters(&ncl, (const void*)k, &cfg);
+    if (e != cudaSuccess) return e;
+    if (ncl < 1) return cudaErrorLaunchOutOfResources;
+    ncl = imin(ncl, p.nunits);
+    cfg.gridDim = dim3((unsigned)(ncl * BC_CTAS));
+    count_launch();
+    return cudaLaunchKernelEx(&cfg, k, p);
+}
+#endif  // !DP_EMUL
+
 // P(f) for every (series, frequency).  z^k through sincos(k*theta) with theta = arg(exp(i delta)),
 // the quantity glibc's cpow(z, k) = cexp(k * clog(z)) uses (c/mem.c:186-195).
 __global__ void __launch_bounds__(256)
@@ -215,7 +401,18 @@ int dp_power_mem(const double* series, int64_t T, int S, int64_t ld, double dt, 
     p.slabs = lay.smem_mode ? nullptr : (double*)(ws + lay.off_slabs);
     p.coef = (double*)(ws + lay.off_coef);
     p.xms = (double*)(ws + lay.off_xms);
-    if (lay.smem_mode) {
+#ifndef DP_EMUL
+    const int cluster_E = (lay.smem_mode || getenv("DP_MEM_NO_CLUSTER")) ? 0 : dp::burg_cluster_E(T, coefficients);
+#else
+    const int cluster_E = 0;
+#endif
+    if (cluster_E) {
+#ifndef DP_EMUL
+        cudaError_t e = cluster_E == 8 ? dp::launch_burg_cluster<8>(p, st)
+                        : cluster_E == 16 ? dp::launch_burg_cluster<16>(p, st) : dp::launch_burg_cluster<32>(p, st);
+        DP_CUDA_OK(e);
+#endif
+    } else if (lay.smem_mode) {
         auto k = dp::burg_kernel<true>;
         DP_CUDA_OK(DP_SET_SMEM(k, lay.smem_bytes));
         DP_LAUNCH(k, dim3(lay.slots), dim3(dp::BURG_THREADS), lay.smem_bytes, st, p);

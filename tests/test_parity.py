@@ -372,6 +372,25 @@ def test_power_mem_vs_oracle(kops):
         kops.power_mem(x[: m + 1], 0.002, f, m)
 
 
+@pytest.mark.gpu
+def test_power_mem_long_series_cluster(cuda_ops):
+    """Series too long for one CTA's shared memory: the thread-block-cluster Burg kernel (f in registers, b in
+    shared memory, one cluster barrier per order) for its three block sizes, against the oracle."""
+    rng = np.random.default_rng(43)
+    f = np.arange(0, 40.0, 0.25)
+    for nt, m, ns in ((20001, 64, 3), (40000, 200, 2), (65537, 100, 2), (131072, 1000, 2), (131073, 300, 1), (100003, 50, 20)):
+        x = _series(rng, nt, ns, 0.001)
+        if ns > 1:
+            x[:, -1] = x[:, -1].real                                  # skipped part (xms == 0)
+        pm = to_np(cuda_ops.power_mem(x, 0.001, f, m))
+        ref = port.mem_spectra(x, 0.001, f, m)
+        assert relerr(pm, ref) < TOL, (nt, m)
+        assert np.array_equal(pm.argmax(0), ref.argmax(0))
+    # beyond the cluster's capacity (8 x 512 x 32 samples): the streaming single-CTA kernel
+    x = _series(rng, 140000, 1, 0.001)
+    assert relerr(cuda_ops.power_mem(x, 0.001, f, 30), port.mem_spectra(x, 0.001, f, 30)) < TOL
+
+
 def test_power_correlation_vs_oracle(kops):
     cuda = is_cuda(kops)
     nt, ns = (2500, 6) if cuda else (777, 2)
