@@ -244,13 +244,23 @@ def run_ours(args):
 
     stage_ms = {"project": [], "contract": [], "exchange": [], "spectra": []}
     CH = 4096                                        # frames per projection/contraction chunk (vc chunk: 2 GB)
+    use_peers = peer_stores = False
     if world == 1:
         send = torch.empty((1, pipe.q_block * pipe.M, tl), dtype=torch.complex128, device=dev)
-    else:                                            # two send slots, chunked receive blocks (source rank, chunk)
+    else:
         assert tl % CH == 0
         send = None
-        send2 = torch.empty((2, world, pipe.q_block * pipe.M, CH), dtype=torch.complex128, device=dev)
-        recv = torch.empty((world, tl // CH, pipe.q_block * pipe.M, CH), dtype=torch.complex128, device=dev)
+        # preferred: the contraction kernel stores every block straight into the destination rank's receive buffer
+        # (symmetric memory over NVLink); fallback: two send slots + chunked asynchronous NCCL all-to-all
+        use_peers = pipe.peer_exchange_setup(tl // CH, CH)
+        peer_stores = use_peers and pipe.peer_mode() == "stores"
+        if use_peers:
+            recv = pipe._peer["recv"]
+            peer_ptrs = pipe._peer["ptrs"]
+            send2 = None if peer_stores else torch.empty((2, world, pipe.q_block * pipe.M, CH), dtype=torch.complex128, device=dev)
+        else:
+            send2 = torch.empty((2, world, pipe.q_block * pipe.M, CH), dtype=torch.complex128, device=dev)
+            recv = torch.empty((world, tl // CH, pipe.q_block * pipe.M, CH), dtype=torch.complex128, device=dev)
 
     def step(record):
         """One pass of the hot path over the rank's frames: [project chunk -> contract chunk into the
@@ -259,6 +269,8 @@ def run_ours(args):
         projection of the following chunks and "exchange" is only what remains exposed at the end."""
         evs = []
         pending = [None, None]
+        if world > 1 and use_peers:
+            pipe.peer_begin()                        # device barrier: the peers have finished reading the previous step's blocks
         for ci, t0 in enumerate(range(0, tl, CH)):
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a.record()
@@ -269,6 +281,18 @@ def run_ours(args):
                 ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send, t_offset=t0, t_total=tl,
                                           pair_major=True)
                 c.record()
+            elif use_peers and peer_stores:              # the contraction kernel stores into the peers' receive buffers
+                off = ((rank * (tl // CH) + ci) * pipe.q_block * pipe.M * CH) * 16
+                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, t_total=CH, pair_major=True,
+                                          block_ptrs=[peer_ptrs[dst] + off for dst in range(world)])
+                c.record()
+            elif use_peers:                              # local send slot, copy engines push the blocks over NVLink
+                slot = ci % 2
+                pipe.peer_wait_slot(slot)
+                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, t_total=CH, pair_major=True,
+                                          block_ptrs=pipe.peer_block_ptrs(send2[slot], ci))
+                c.record()
+                pipe.peer_push(send2[slot], ci, slot)
             else:
                 slot = ci % 2
                 if pending[slot] is not None:
@@ -285,6 +309,8 @@ def run_ours(args):
         for w in pending:
             if w is not None:
                 w.wait()
+        if world > 1 and use_peers:
+            pipe.peer_end()                          # own copies done + device barrier: every rank's blocks have landed
         blocks = send if world == 1 else recv.reshape(world * (tl // CH), pipe.q_block * pipe.M, CH)
         e3 = torch.cuda.Event(enable_timing=True); e3.record()
         ps = pipe.spectra_series(blocks)
@@ -351,17 +377,19 @@ def run_ours(args):
         del v, send
         if world > 1:
             del send2, recv
+        del ps
         torch.cuda.empty_cache()
         vh = torch.empty((tl, wl["n_atoms"], 3), dtype=torch.float64, pin_memory=True)
         for t0 in range(0, tl, CHUNK):
             vh[t0:t0 + CHUNK].copy_(gen_chunk_torch(torch, dev, wl, t_lo + t0, t_lo + t0 + CHUNK))
         torch.cuda.synchronize()
-        pipe.run_from_host(vh, chunk_frames=2048)                        # warm-up
+        e2e_chunk = 2048 if world == 1 else CH                           # N > 1: the receive-buffer geometry of the timed steps
+        pipe.run_from_host(vh, chunk_frames=e2e_chunk)                   # warm-up
         barrier()
         es = max(1, min(args.steps, 2))
         t0 = time.perf_counter()
         for _ in range(es):
-            ps_host = pipe.run_from_host(vh, chunk_frames=2048)
+            ps_host = pipe.run_from_host(vh, chunk_frames=e2e_chunk)
         barrier()
         dt_e2e = (time.perf_counter() - t0) / es
         if world > 1:
@@ -393,7 +421,12 @@ def run_ours(args):
     for k in ("project", "contract", "spectra"):
         ach = bytes_stage[k] / (mean[k] * 1e-3) / 1e9 if mean[k] > 0 else 0.0
         stages[k] = {"kernel": kernels[k], "ms": mean[k], "achieved_GBps": ach, "frac_of_hbm": ach / hbm}
-    stages["exchange"] = {"kernel": "nccl all_to_all per chunk, asynchronous (exposed remainder)" if world > 1 else "none",
+    stages["exchange"] = {"kernel": ("fused into project_phonon_series_kernel: peer stores over NVLink into the destination's "
+                                     "receive buffer (exposed: the closing device barrier)" if (world > 1 and use_peers and peer_stores) else
+                                     "copy engines push each contracted chunk into the peers' receive buffers (symmetric memory "
+                                     "over NVLink) underneath the following chunks; exposed remainder + device barrier"
+                                     if (world > 1 and use_peers) else
+                                     "nccl all_to_all per chunk, asynchronous (exposed remainder)") if world > 1 else "none",
                           "ms": mean["exchange"]}
     # DRAM traffic of the dominant kernels from `ncu --set full` captures of smaller launches of the same
     # kernels (profiles/r01_ncu_*.jsonl), scaled linearly to this launch: bytes per series / per frame

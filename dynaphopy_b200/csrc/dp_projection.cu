@@ -147,12 +147,18 @@ project_phonon_kernel(const cplx* vc, const cplx* __restrict__ eig, int64_t T, i
 // so the eigenvector reads are broadcasts) and written as runs of PS_TT consecutive time samples.
 constexpr int PS_TT = 32;
 constexpr int PS_QT_MAX = 16;       // wave vectors per CTA (fewer for wide M: shared-memory budget)
+constexpr int PS_MAX_BLOCKS = 16;   // destination blocks with their own base pointer (ranks of one NVSwitch domain)
+
+// Per-destination output bases: block g = q / q_block is written at p[g] instead of out + g*q_block*M*T_total.
+// The pointers may be PEER device memory mapped over NVLink: the contraction then IS the exchange step (its
+// 512-byte runs of consecutive time samples go straight into the destination rank's receive buffer).
+struct PsBlocks { cplx* p[PS_MAX_BLOCKS]; int n; };
 
 template <int MT>   // MT > 0: compile-time M (inputs kept in registers); 0: any M
 __global__ void __launch_bounds__(256)
 project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig, int64_t T, int Q, int Mdyn,
                              int q_block, int qt, int vc_pairs, int64_t t_offset, int64_t T_total,
-                             cplx* __restrict__ out) {
+                             cplx* __restrict__ out, const __grid_constant__ PsBlocks blocks) {
     DP_DYNSMEM(cplx, sm);
     const int M = MT > 0 ? MT : Mdyn;
     const int pitch = qt * M + 1;                   // odd: conflict-free column reads
@@ -187,7 +193,8 @@ project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict
         const int q = q0 + qq;
         const cplx* row = in + lane * pitch + qq * M;
         const cplx* e = es + qq * M * M;
-        cplx* dst = out + ((int64_t)(q / q_block) * q_block * M + (int64_t)(q % q_block) * M) * T_total + t_offset + t;
+        cplx* dst = (blocks.n > 0 ? blocks.p[q / q_block] : out + (int64_t)(q / q_block) * q_block * M * T_total) +
+                    (int64_t)(q % q_block) * M * T_total + t_offset + t;
         if (MT > 0) {
             cplx a[MT > 0 ? MT : 1];
 #pragma unroll
@@ -320,17 +327,32 @@ int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int
     return dp_project_phonon_series_ex(vc, DP_VC_ROWS, eig, T, Q, M, q_block, t_offset, T_total, out, stream);
 }
 
-int dp_project_phonon_series_ex(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M, int q_block,
-                                int64_t t_offset, int64_t T_total, double* out, void* stream) {
+static int project_phonon_series_impl(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M,
+                                      int q_block, int64_t t_offset, int64_t T_total, double* out,
+                                      double* const* block_out, int n_blocks, void* stream) {
     DP_REQUIRE(vc_layout == DP_VC_ROWS || (vc_layout == DP_VC_PAIRS && M % 2 == 0), DP_ERR_INVALID,
                "dp_project_phonon_series: bad vc_layout %d (the pair-major layout needs an even M)", vc_layout);
     const int vc_pairs = vc_layout == DP_VC_PAIRS;
-    DP_REQUIRE((T == 0 || (vc && out)) && eig, DP_ERR_INVALID, "dp_project_phonon_series: null pointer");
+    DP_REQUIRE((T == 0 || (vc && (out || block_out))) && eig, DP_ERR_INVALID, "dp_project_phonon_series: null pointer");
     DP_REQUIRE(vc != out, DP_ERR_INVALID, "dp_project_phonon_series: cannot run in place (the output is transposed)");
     DP_REQUIRE(q_block > 0 && Q % q_block == 0, DP_ERR_INVALID, "dp_project_phonon_series: q_block=%d must divide Q=%d", q_block, Q);
     DP_REQUIRE(T >= 0 && Q > 0 && M > 0 && M % 3 == 0, DP_ERR_INVALID, "dp_project_phonon_series: bad sizes (M must be 3*n_prim)");
     DP_REQUIRE(t_offset >= 0 && t_offset + T <= T_total, DP_ERR_INVALID, "dp_project_phonon_series: frames [%lld, %lld) outside the series length %lld",
                (long long)t_offset, (long long)(t_offset + T), (long long)T_total);
+    dp::PsBlocks blocks;
+    blocks.n = 0;
+    for (int g = 0; g < dp::PS_MAX_BLOCKS; g++) blocks.p[g] = nullptr;
+    if (block_out) {
+        DP_REQUIRE(n_blocks == Q / q_block && n_blocks <= dp::PS_MAX_BLOCKS, DP_ERR_INVALID,
+                   "dp_project_phonon_series_peers: %d block pointers for Q/q_block = %d blocks (at most %d)", n_blocks,
+                   Q / q_block, dp::PS_MAX_BLOCKS);
+        for (int g = 0; g < n_blocks; g++) {
+            DP_REQUIRE(block_out[g] != nullptr && (const double*)block_out[g] != vc, DP_ERR_INVALID,
+                       "dp_project_phonon_series_peers: bad pointer for block %d", g);
+            blocks.p[g] = (dp::cplx*)block_out[g];
+        }
+        blocks.n = n_blocks;
+    }
     if (T == 0) return DP_OK;
     const size_t per_q = ((size_t)dp::PS_TT * M + (size_t)M * M) * sizeof(dp::cplx);
     const int qt = (int)dp::imax<size_t>(1, dp::imin<size_t>(dp::PS_QT_MAX, (size_t)(72 * 1024) / per_q));
@@ -345,7 +367,7 @@ int dp_project_phonon_series_ex(const double* vc, int vc_layout, const double* e
         auto k = dp::project_phonon_series_kernel<MT>;                                                            \
         DP_CUDA_OK(DP_SET_SMEM(k, smem));                                                                         \
         DP_LAUNCH(k, grid, dim3(256), smem, st, (const dp::cplx*)vc, (const dp::cplx*)eig, T, Q, M, q_block,     \
-                  qt, vc_pairs, t_offset, T_total, (dp::cplx*)out);                                                             \
+                  qt, vc_pairs, t_offset, T_total, (dp::cplx*)out, blocks);                                       \
     } while (0)
     if (M == 6) DP_PS_LAUNCH(6);
     else if (M == 12) DP_PS_LAUNCH(12);
@@ -353,6 +375,20 @@ int dp_project_phonon_series_ex(const double* vc, int vc_layout, const double* e
 #undef DP_PS_LAUNCH
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
+}
+
+int dp_project_phonon_series_ex(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M, int q_block,
+                                int64_t t_offset, int64_t T_total, double* out, void* stream) {
+    DP_REQUIRE(T == 0 || out, DP_ERR_INVALID, "dp_project_phonon_series: null pointer");
+    return project_phonon_series_impl(vc, vc_layout, eig, T, Q, M, q_block, t_offset, T_total, out, nullptr, 0, stream);
+}
+
+int dp_project_phonon_series_peers(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M,
+                                   int q_block, int64_t t_offset, int64_t T_total, double* const* block_out,
+                                   int n_blocks, void* stream) {
+    DP_REQUIRE(block_out, DP_ERR_INVALID, "dp_project_phonon_series_peers: null pointer");
+    return project_phonon_series_impl(vc, vc_layout, eig, T, Q, M, q_block, t_offset, T_total, nullptr, block_out,
+                                      n_blocks, stream);
 }
 
 }  // extern "C"

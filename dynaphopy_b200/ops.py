@@ -203,9 +203,11 @@ class Ops:
         return out.reshape(T, Q, M) if (inplace and qb == Q) else out
 
     def project_phonon_series(self, vc, eigenvectors, q_block=None, out=None, t_offset=0, t_total=None,
-                              pair_major=False):
+                              pair_major=False, block_ptrs=None):
         """vc (T,Q,n_p,3)|(T,Q,M) -> series-major vq: ``out[g, qq*M + s, t_offset + t]`` with q = g*q_block + qq,
-        shape (Q/q_block, q_block*M, t_total).  ``out`` lets a long trajectory be contracted chunk by chunk."""
+        shape (Q/q_block, q_block*M, t_total).  ``out`` lets a long trajectory be contracted chunk by chunk.
+        ``block_ptrs``: one device address per block g (possibly peer memory of rank g): block g is written there as a
+        (q_block*M, t_total) matrix instead of into ``out`` -- the contraction fused with the exchange step."""
         be = self.be
         vc = be.asarray(vc, np.complex128)
         if pair_major:                                   # (T, M/2, Q, 2) from project_commensurate(pair_major=True)
@@ -218,6 +220,11 @@ class Ops:
         assert be.shape(e)[0] == Q and int(np.prod(be.shape(e)[1:])) == M * M, "eigenvector shape mismatch"
         qb = Q if q_block is None else int(q_block)
         t_total = T if t_total is None else int(t_total)
+        if block_ptrs is not None:
+            ptrs = (ctypes.c_void_p * len(block_ptrs))(*[int(a) for a in block_ptrs])
+            self.lib.call("dp_project_phonon_series_peers", be.ptr(vc), int(bool(pair_major)), be.ptr(e), T, Q, M, qb,
+                          int(t_offset), t_total, ptrs, len(block_ptrs), be.stream())
+            return None
         if out is None:
             out = be.empty((Q // qb, qb * M, t_total), np.complex128)
         else:

@@ -161,14 +161,14 @@ class MeshPipeline:
         raise ValueError("Power spectrum algorithm number not found")
 
     # -- series-major path (the one run() uses) ---------------------------------------------------------
-    def series(self, velocity_local, chunk_frames=4096, out=None, t_offset=0, t_total=None):
+    def series(self, velocity_local, chunk_frames=4096, out=None, t_offset=0, t_total=None, block_ptrs=None):
         """Local frames -> series-major contracted series ``(G, (Q/G)*M, Tl)``: block g is the contiguous
         message for rank g, every (q, s) series is contiguous in time.  Projection and contraction run chunk
         by chunk so that only one chunk of ``vc`` is ever materialised."""
         be = self.be
         tl = be.shape(velocity_local)[0]
         t_total = tl if t_total is None else t_total
-        if out is None:
+        if out is None and block_ptrs is None:
             out = be.empty((self.world, self.q_block * self.M, t_total), np.complex128)
         for t0 in range(0, tl, chunk_frames):
             t1 = min(t0 + chunk_frames, tl)
@@ -182,9 +182,146 @@ class MeshPipeline:
                 vc = self.project(velocity_local[t0:t1])
                 eig = self.d_eig
             self.ops.project_phonon_series(vc, eig, q_block=self.q_block, out=out, t_offset=t_offset + t0,
-                                           t_total=t_total, pair_major=pm)
+                                           t_total=t_total, pair_major=pm, block_ptrs=block_ptrs)
             del vc
         return out
+
+    # -- exchange fused into the contraction: peer receive buffers over NVLink ---------------------------------
+    def peer_exchange_setup(self, n_chunks, chunk_frames):
+        """Allocate this rank's receive buffer ``(G, n_chunks, S_loc, Tc)`` in symmetric memory and map every peer's
+        buffer (torch.distributed._symmetric_memory: CUDA IPC / fabric handles over NVLink).  Afterwards
+        ``series_exchanged`` lets the contraction kernel of every rank store block g straight into rank g's buffer
+        (``dp_project_phonon_series_peers``) -- no all-to-all, no send buffer, no SMs spent on a copy kernel.
+        Returns False (and leaves the NCCL path in place) when symmetric memory is not available."""
+        if self.world == 1:
+            return False
+        key = (int(n_chunks), int(chunk_frames))
+        if getattr(self, "_peer", None) is not None and self._peer["key"] == key:
+            return True
+        try:
+            import torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            if dist.get_backend(self.group) != "nccl" or os.environ.get("DP_NO_PEER_EXCHANGE"):
+                return False
+            dev = self.be.device
+            s_loc = self.q_block * self.M
+            shape = (self.world, int(n_chunks), s_loc, int(chunk_frames))
+            flat = symm.empty(int(np.prod(shape)) * 2, dtype=torch.float64, device=dev)
+            group = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm.rendezvous(flat, group)
+            recv = torch.view_as_complex(flat.view(*shape, 2))
+            self._peer = {"key": key, "flat": flat, "hdl": hdl, "recv": recv, "ptrs": [int(p) for p in hdl.buffer_ptrs]}
+            return True
+        except Exception as exc:                                   # no P2P mapping on this box: keep the NCCL all-to-all
+            print("peer exchange unavailable (%s): using the NCCL all-to-all" % (exc,), flush=True)
+            self._peer = None
+            return False
+
+    # Three ways to move a contracted chunk to its destination ranks, selected by DP_PEER_MODE (measured on 2 and 8
+    # B200s, DESIGN.md section 5):
+    #   "dma"    (default) the contraction writes a local two-slot send buffer at HBM speed; copy engines push every
+    #            block into the destination's receive buffer (peer pointers from symmetric memory) on side streams,
+    #            underneath the projection of the following chunks; no SM is spent on the exchange
+    #   "stores" the contraction kernel itself stores into the peers' buffers (dp_project_phonon_series_peers)
+    #   NCCL     chunked asynchronous all_to_all (series_exchanged), when symmetric memory is unavailable
+    def peer_mode(self):
+        return os.environ.get("DP_PEER_MODE", "dma")
+
+    def peer_begin(self):
+        """Start of a step: device-side barrier (the peers have finished reading the previous step's blocks)."""
+        import torch
+        pr = self._peer
+        pr["hdl"].barrier(channel=0)
+        if "streams" not in pr:
+            dev = self.be.device
+            pr["streams"] = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(self.world - 1, 4)))]
+            pr["slot_free"] = [None, None]
+            nch, tc = pr["key"]
+            s_loc = self.q_block * self.M
+            # receive buffer of every rank as a (G, n_chunks, S_loc, Tc, 2) float64 view
+            pr["views"] = [pr["hdl"].get_buffer(r, (self.world, nch, s_loc, tc, 2), torch.float64) for r in range(self.world)]
+        pr["slot_free"] = [None, None]
+
+    def peer_wait_slot(self, slot):
+        """The kernels that refill send slot ``slot`` wait (on the device) until its previous blocks have left."""
+        import torch
+        evs = self._peer["slot_free"][slot]
+        if evs:
+            main = torch.cuda.current_stream(self.be.device)
+            for e in evs:
+                main.wait_event(e)
+
+    def peer_block_ptrs(self, send_slot, ci):
+        """Destination of every block of chunk ``ci`` in "dma" mode: this rank's own block goes straight into its
+        receive buffer (no local copy), the others into the send slot the copy engines read."""
+        pr = self._peer
+        nch, tc = pr["key"]
+        s_loc = self.q_block * self.M
+        off = ((self.rank * nch + ci) * s_loc * tc) * 16
+        return [pr["ptrs"][dst] + off if dst == self.rank else int(send_slot[dst].data_ptr()) for dst in range(self.world)]
+
+    def peer_push(self, send_slot, ci, slot):
+        """Queue the copies of one contracted chunk ``send_slot`` (G, S_loc, Tc) into block (rank, ci) of every
+        destination's receive buffer: copy engines over NVLink, several streams so that more than one engine runs."""
+        import torch
+        pr = self._peer
+        main = torch.cuda.current_stream(self.be.device)
+        done = torch.cuda.Event()
+        done.record(main)
+        src = torch.view_as_real(send_slot)
+        evs = []
+        for k, st in enumerate(pr["streams"]):
+            st.wait_event(done)
+        for j in range(self.world - 1):
+            dst = (self.rank + 1 + j) % self.world            # staggered: at any time every rank targets a different peer
+            st = pr["streams"][j % len(pr["streams"])]
+            with torch.cuda.stream(st):
+                pr["views"][dst][self.rank, ci].copy_(src[dst], non_blocking=True)
+        for st in pr["streams"]:
+            e = torch.cuda.Event()
+            e.record(st)
+            evs.append(e)
+        pr["slot_free"][slot] = evs
+
+    def peer_end(self):
+        """End of the exchange: all copies of this rank are done, then the device-side barrier (everybody's are)."""
+        import torch
+        main = torch.cuda.current_stream(self.be.device)
+        for evs in self._peer["slot_free"]:
+            for e in evs or []:
+                main.wait_event(e)
+        self._peer["hdl"].barrier(channel=1)
+
+    def series_exchanged_peers(self, velocity_local, chunk_frames=4096):
+        """Time-sharded frames -> received (G*n_chunks, S_loc, Tc) time blocks over peer memory: chunk c of this rank
+        lands in block (rank, c) of every destination's buffer.  Two device-side barriers per step (symmetric-memory
+        signal pads, stream ordered, the host never blocks)."""
+        be = self.be
+        tl = be.shape(velocity_local)[0]
+        assert tl % chunk_frames == 0, "local frame count must be a multiple of the chunk length"
+        nch, tc, g, s_loc = tl // chunk_frames, chunk_frames, self.world, self.q_block * self.M
+        assert self._peer is not None and self._peer["key"] == (nch, tc), "peer_exchange_setup first"
+        ptrs = self._peer["ptrs"]
+        stores = self.peer_mode() == "stores"
+        self.peer_begin()
+        if not stores:
+            send = self._peer.get("send")
+            if send is None:
+                send = self._peer["send"] = be.empty((2, g, s_loc, tc), np.complex128)
+        for c in range(nch):
+            if stores:
+                off = ((self.rank * nch + c) * s_loc * tc) * 16      # bytes: block (source rank, chunk) of a receive buffer
+                self.series(velocity_local[c * tc:(c + 1) * tc], chunk_frames, t_total=tc,
+                            block_ptrs=[ptrs[dst] + off for dst in range(g)])
+            else:
+                slot = c % 2
+                self.peer_wait_slot(slot)
+                self.series(velocity_local[c * tc:(c + 1) * tc], chunk_frames, t_total=tc,
+                            block_ptrs=self.peer_block_ptrs(send[slot], c))
+                self.peer_push(send[slot], c, slot)
+        self.peer_end()
+        return self._peer["recv"].reshape(g * nch, s_loc, tc)
 
     def exchange_series(self, send):
         """The one all-to-all on the series-major layout: (G, S_loc, Tl) -> (G, S_loc, Tl) where block g now
@@ -209,6 +346,8 @@ class MeshPipeline:
     def run(self, velocity_local, chunk_frames=4096):
         """Whole step on device-resident local frames; returns the (F, S_local) spectra of this rank."""
         if self.world > 1 and self.be.shape(velocity_local)[0] % chunk_frames == 0 and hasattr(velocity_local, "device"):
+            if self.peer_exchange_setup(self.be.shape(velocity_local)[0] // chunk_frames, chunk_frames):
+                return self.spectra_series(self.series_exchanged_peers(velocity_local, chunk_frames))
             return self.spectra_series(self.series_exchanged(velocity_local, chunk_frames))
         send = self.series(velocity_local, chunk_frames)
         blocks = self.exchange_series(send)
@@ -262,7 +401,18 @@ class MeshPipeline:
         tl = velocity_host.shape[0]
         n = velocity_host.shape[1]
         h0 = time.perf_counter()
-        send = be.empty((self.world, self.q_block * self.M, tl), np.complex128)
+        # multi-rank: the contraction of every chunk stores straight into the peers' receive buffers when symmetric
+        # memory is available (no send buffer, no all-to-all); otherwise one all-to-all at the end
+        peers = self.world > 1 and tl % chunk_frames == 0 and self.peer_exchange_setup(tl // chunk_frames, chunk_frames)
+        send = None if peers else be.empty((self.world, self.q_block * self.M, tl), np.complex128)
+        if peers:
+            nch, s_loc = tl // chunk_frames, self.q_block * self.M
+            stores = self.peer_mode() == "stores"
+            self.peer_begin()
+            if not stores:
+                send2 = self._peer.get("send")
+                if send2 is None:
+                    send2 = self._peer["send"] = be.empty((2, self.world, s_loc, chunk_frames), np.complex128)
         nslots = max(2, min(int(stage_slots), (tl + chunk_frames - 1) // chunk_frames))
         stage = [be.empty((min(chunk_frames, tl), n, 3), np.float64) for _ in range(nslots)]
         copy_stream = torch.cuda.Stream(device=be.device)
@@ -307,7 +457,17 @@ class MeshPipeline:
             if i + nslots - 1 < len(starts):
                 enqueue_copy(i + nslots - 1)               # its slot was freed at the end of iteration i - 1
             main.wait_event(ready[slot])
-            self.series(stage[slot][: t1 - t0], chunk_frames, out=send, t_offset=t0, t_total=tl)
+            if peers and stores:
+                off = ((self.rank * nch + i) * s_loc * chunk_frames) * 16
+                self.series(stage[slot][: t1 - t0], chunk_frames, t_total=chunk_frames,
+                            block_ptrs=[p + off for p in self._peer["ptrs"]])
+            elif peers:
+                self.peer_wait_slot(i % 2)
+                self.series(stage[slot][: t1 - t0], chunk_frames, t_total=chunk_frames,
+                            block_ptrs=self.peer_block_ptrs(send2[i % 2], i))
+                self.peer_push(send2[i % 2], i, i % 2)
+            else:
+                self.series(stage[slot][: t1 - t0], chunk_frames, out=send, t_offset=t0, t_total=tl)
             freed[slot].record(main)
             if stream_windows:
                 complete = sum(1 for p in pieces if p[1] <= t1)
@@ -337,7 +497,11 @@ class MeshPipeline:
                 print("e2e host: finish launch %.1f ms, D2H %.1f ms" % ((h4 - h3) * 1e3, (time.perf_counter() - h4) * 1e3), flush=True)
                 return out
             return self._to_host_pinned(ps)
-        blocks = self.exchange_series(send)
+        if peers:
+            self.peer_end()
+            blocks = self._peer["recv"].reshape(self.world * nch, s_loc, chunk_frames)
+        else:
+            blocks = self.exchange_series(send)
         ps = self.spectra_series(blocks)
         return self._to_host_pinned(ps)
 

@@ -182,6 +182,16 @@ int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int
 int dp_project_phonon_series_ex(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M,
                                 int q_block, int64_t t_offset, int64_t T_total, double* out, void* stream);
 
+/* Contraction FUSED with the exchange step of the multi-GPU path: block g = q / q_block is
+ * written at block_out[g] + ((q % q_block)*M + s) * T_total + t_offset + t instead of into one array.  The pointers
+ * may be peer device memory of the other ranks of an NVLink/NVSwitch domain (mapped with CUDA IPC / symmetric
+ * memory): the kernel's 512-byte runs then go straight into the destination rank's receive buffer and no
+ * all-to-all is needed.  block_out is a HOST array of n_blocks = Q / q_block (<= 16) device pointers.  The caller
+ * orders the accesses across ranks (a barrier before reuse of the receive buffers and after the last chunk). */
+int dp_project_phonon_series_peers(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M,
+                                   int q_block, int64_t t_offset, int64_t T_total, double* const* block_out,
+                                   int n_blocks, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A7  power spectrum, FFT method (selector keys 2 and 3).
  * Replaces: get_fft_numpy_spectra / _numpy_power / _division_of_data

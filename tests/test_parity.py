@@ -519,3 +519,24 @@ def test_spectra_peaks_degenerate_average_and_guess(kops):
     assert np.array_equal(to_np(heights0), np.max(ps, axis=0), equal_nan=True)
     with pytest.raises(ValueError):
         kops.spectra_peaks(ps, flat[:-1])
+
+
+def test_project_phonon_series_peer_blocks(kops):
+    """dp_project_phonon_series_peers: every destination block at its own base pointer (peer receive buffers on a
+    multi-GPU box) holds exactly what the single-array send layout holds for that block."""
+    rng = np.random.default_rng(47)
+    T, Q, M, qb = 70, 12, 6, 3
+    vc = rng.normal(size=(T, Q, M)) + 1j * rng.normal(size=(T, Q, M))
+    eig = rng.normal(size=(Q, M, M)) + 1j * rng.normal(size=(Q, M, M))
+    t_total, t_off = 100, 20
+    ref = to_np(kops.project_phonon_series(vc, eig, q_block=qb, t_offset=t_off, t_total=t_total,
+                                           out=kops.be.asarray(np.zeros((Q // qb, qb * M, t_total), complex), np.complex128)))
+    blocks = [kops.be.asarray(np.zeros((qb * M, t_total), complex), np.complex128) for _ in range(Q // qb)]
+    assert kops.project_phonon_series(vc, eig, q_block=qb, t_offset=t_off, t_total=t_total,
+                                      block_ptrs=[kops.be.ptr(b).value for b in blocks]) is None
+    for g, b in enumerate(blocks):
+        assert np.array_equal(to_np(b), ref[g])
+    assert np.abs(ref[:, :, t_off:t_off + T]).min() > 0 and not ref[:, :, :t_off].any()
+    from dynaphopy_b200._lib import DpError
+    with pytest.raises(DpError, match="block pointers"):
+        kops.project_phonon_series(vc, eig, q_block=qb, t_total=T, block_ptrs=[kops.be.ptr(blocks[0]).value])
