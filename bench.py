@@ -203,7 +203,8 @@ def config_dict(wl, frames, gpus):
                         "7 windows of 20000)",
             "atoms": wl["n_atoms"], "frames": frames, "q_points": wl["Q"], "modes_per_q": wl["M"],
             "series": wl["Q"] * wl["M"], "frequencies": len(FREQ), "dt_ps": DT,
-            "sharding": f"time-block x{gpus}" + (" + all-to-all (NCCL)" if gpus > 1 else ""),
+            "sharding": f"time-block x{gpus}" + (" (4096-frame blocks dealt cyclically to the ranks) + one exchange over NVLink "
+                                                   "peer memory (copy engines; NCCL all-to-all fallback)" if gpus > 1 else ""),
             "l2_policy": "inputs (32 GB velocities, 64 GB projected series) far exceed the 126 MB L2"}
 
 
@@ -232,9 +233,19 @@ def run_ours(args):
     assert pipe.fold_twiddle        # primitive cell: the projection twiddle rides on the eigenvectors
 
     # ---- device-resident inputs -------------------------------------------------------------------
+    CH = 4096                                        # frames per projection/contraction chunk (vc chunk: 2 GB)
+    # N > 1: chunk-cyclic time sharding (chunk j of the trajectory lives on rank j % N), so that the spectra of finished
+    # windows overlap the rest of the exchange; --sharding blocks keeps one contiguous time block per rank
+    cyclic = world > 1 and args.sharding == "cyclic"
     v = torch.empty((tl, wl["n_atoms"], 3), dtype=torch.float64, device=dev)
-    for t0 in range(0, tl, CHUNK):
-        v[t0:t0 + CHUNK] = gen_chunk_torch(torch, dev, wl, t_lo + t0, t_lo + t0 + CHUNK)
+    if cyclic:
+        assert tl % CH == 0
+        for c, (g0, g1) in enumerate(pipe.cyclic_chunks(frames, CH)):
+            for t0 in range(0, CH, CHUNK):
+                v[c * CH + t0:c * CH + t0 + CHUNK] = gen_chunk_torch(torch, dev, wl, g0 + t0, g0 + t0 + CHUNK)
+    else:
+        for t0 in range(0, tl, CHUNK):
+            v[t0:t0 + CHUNK] = gen_chunk_torch(torch, dev, wl, t_lo + t0, t_lo + t0 + CHUNK)
     torch.cuda.synchronize()
 
     def barrier():
@@ -243,10 +254,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     stage_ms = {"project": [], "contract": [], "exchange": [], "spectra": []}
-    CH = 4096                                        # frames per projection/contraction chunk (vc chunk: 2 GB)
+    span_ms = []
     use_peers = peer_stores = False
     if world == 1:
         send = torch.empty((1, pipe.q_block * pipe.M, tl), dtype=torch.complex128, device=dev)
+    elif cyclic:
+        send = send2 = recv = None
+        use_peers = pipe.peer_exchange_setup(tl // CH, CH)
     else:
         assert tl % CH == 0
         send = None
@@ -267,6 +281,14 @@ def run_ours(args):
         series-major send buffer (-> asynchronous all-to-all of the chunk when N > 1)]* -> FFT spectra.
         Stage times are CUDA-event sums; with N > 1 the exchange runs on NCCL's stream underneath the
         projection of the following chunks and "exchange" is only what remains exposed at the end."""
+        if cyclic:
+            rec = {}
+            ps = pipe.run_cyclic(v, CH, record=rec if record else None)
+            if record:
+                for k in stage_ms:
+                    stage_ms[k].append(rec.get(k, 0.0))
+                span_ms.append(rec.get("span", 0.0))
+            return ps
         evs = []
         pending = [None, None]
         if world > 1 and use_peers:
@@ -428,6 +450,13 @@ def run_ours(args):
                                      if (world > 1 and use_peers) else
                                      "nccl all_to_all per chunk, asynchronous (exposed remainder)") if world > 1 else "none",
                           "ms": mean["exchange"]}
+    if cyclic:
+        stages["exchange"]["kernel"] = ("copy engines push each contracted chunk into the peers' receive buffers (symmetric memory over "
+                                        "NVLink); chunk-cyclic sharding: the spectra of finished windows run on a second stream "
+                                        "underneath the later rounds; ms = last contraction end -> last round landed on every rank"
+                                        if use_peers else "all_to_all per round (no symmetric memory)")
+        stages["overlap"] = {"span_ms": statistics.mean(span_ms) if span_ms else None,
+                             "note": "stage times are CUDA-event sums per stream; spectra overlap projection/contraction/exchange"}
     # DRAM traffic of the dominant kernels from `ncu --set full` captures of smaller launches of the same
     # kernels (profiles/r01_ncu_*.jsonl), scaled linearly to this launch: bytes per series / per frame
     ncu_traffic = {"spectra": (1.901760e9 + 1.569485e9) / 296.0 * s_loc,              # 296 series captured
@@ -490,6 +519,8 @@ def main():
     ap.add_argument("--frames", type=int, default=131072, help="total frames (default: the full 2^17 workload)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-methods", action="store_true")
+    ap.add_argument("--sharding", default="cyclic", choices=["cyclic", "blocks"],
+                    help="N > 1: chunk-cyclic time sharding with overlapped spectra (default) or one time block per rank")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=1024)  # <= 1024 (one generator chunk)
     ap.add_argument("--cpu-q", type=int, default=4)

@@ -161,7 +161,7 @@ class MeshPipeline:
         raise ValueError("Power spectrum algorithm number not found")
 
     # -- series-major path (the one run() uses) ---------------------------------------------------------
-    def series(self, velocity_local, chunk_frames=4096, out=None, t_offset=0, t_total=None, block_ptrs=None):
+    def series(self, velocity_local, chunk_frames=4096, out=None, t_offset=0, t_total=None, block_ptrs=None, mark=None):
         """Local frames -> series-major contracted series ``(G, (Q/G)*M, Tl)``: block g is the contiguous
         message for rank g, every (q, s) series is contiguous in time.  Projection and contraction run chunk
         by chunk so that only one chunk of ``vc`` is ever materialised."""
@@ -181,6 +181,8 @@ class MeshPipeline:
                 pm = False
                 vc = self.project(velocity_local[t0:t1])
                 eig = self.d_eig
+            if mark is not None:
+                mark()                                   # between projection and contraction (stage timing)
             self.ops.project_phonon_series(vc, eig, q_block=self.q_block, out=out, t_offset=t_offset + t0,
                                            t_total=t_total, pair_major=pm, block_ptrs=block_ptrs)
             del vc
@@ -235,7 +237,8 @@ class MeshPipeline:
         pr["hdl"].barrier(channel=0)
         if "streams" not in pr:
             dev = self.be.device
-            pr["streams"] = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(self.world - 1, 4)))]
+            nst = int(os.environ.get("DP_PEER_STREAMS", self.world - 1))       # one stream (copy engine) per destination
+            pr["streams"] = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(self.world - 1, nst)))]
             pr["slot_free"] = [None, None]
             nch, tc = pr["key"]
             s_loc = self.q_block * self.M
@@ -261,11 +264,14 @@ class MeshPipeline:
         off = ((self.rank * nch + ci) * s_loc * tc) * 16
         return [pr["ptrs"][dst] + off if dst == self.rank else int(send_slot[dst].data_ptr()) for dst in range(self.world)]
 
-    def peer_push(self, send_slot, ci, slot):
+    def peer_push(self, send_slot, ci, slot, views=None, index=None):
         """Queue the copies of one contracted chunk ``send_slot`` (G, S_loc, Tc) into block (rank, ci) of every
-        destination's receive buffer: copy engines over NVLink, several streams so that more than one engine runs."""
+        destination's receive buffer: copy engines over NVLink, several streams so that more than one engine runs.
+        ``views`` / ``index``: another geometry of the same buffers (chunk-cyclic: block (ci, rank))."""
         import torch
         pr = self._peer
+        views = pr["views"] if views is None else views
+        index = (self.rank, ci) if index is None else index
         main = torch.cuda.current_stream(self.be.device)
         done = torch.cuda.Event()
         done.record(main)
@@ -277,7 +283,7 @@ class MeshPipeline:
             dst = (self.rank + 1 + j) % self.world            # staggered: at any time every rank targets a different peer
             st = pr["streams"][j % len(pr["streams"])]
             with torch.cuda.stream(st):
-                pr["views"][dst][self.rank, ci].copy_(src[dst], non_blocking=True)
+                views[dst][index[0], index[1]].copy_(src[dst], non_blocking=True)
         for st in pr["streams"]:
             e = torch.cuda.Event()
             e.record(st)
@@ -322,6 +328,119 @@ class MeshPipeline:
                 self.peer_push(send[slot], c, slot)
         self.peer_end()
         return self._peer["recv"].reshape(g * nch, s_loc, tc)
+
+    # -- chunk-cyclic time sharding: the spectra of finished windows run underneath the rest of the exchange -------
+    def cyclic_chunks(self, total_frames, chunk_frames):
+        """Global frame ranges owned by this rank under chunk-cyclic sharding, in local order: chunk j of the
+        trajectory belongs to rank j % G.  After round c (every rank has pushed its c-th chunk) the frames
+        [0, (c+1)*G*chunk) are complete on every rank, so spectrum windows finish progressively instead of all at
+        the end (contiguous blocks per rank deliver the last sample of EVERY window in the last round)."""
+        g = self.world
+        nch = total_frames // (g * chunk_frames)
+        assert nch * g * chunk_frames == total_frames, "frames must be a multiple of ranks * chunk"
+        return [((c * g + self.rank) * chunk_frames, (c * g + self.rank + 1) * chunk_frames) for c in range(nch)]
+
+    def run_cyclic(self, velocity_local, chunk_frames=4096, record=None):
+        """Whole step on device-resident frames held chunk-cyclically (``cyclic_chunks``): per round project ->
+        contract -> push (copy engines, peer memory); on a second stream, as soon as a round has landed on every rank
+        (device barrier), the FFT spectra of the windows it completed.  Returns the (F, S_local) spectra.
+        ``record``: optional dict that receives CUDA-event stage times in ms."""
+        import torch
+        import torch.distributed as dist
+        be = self.be
+        tl = be.shape(velocity_local)[0]
+        g, tc, s_loc = self.world, chunk_frames, self.q_block * self.M
+        nch = tl // tc
+        assert nch * tc == tl, "local frame count must be a multiple of the chunk length"
+        T = tl * g
+        fft = self.algorithm in (2, 3, 4, 5)
+        cuda = hasattr(velocity_local, "device") and getattr(velocity_local, "is_cuda", False)
+        peers = g > 1 and cuda and self.peer_exchange_setup(nch, tc)
+        if fft:
+            _, pieces = self.ops.fft_pieces(T, self.dt, self.freq)
+            pieces = [p for i, p in enumerate(pieces) if i == 0 or p != pieces[i - 1]]      # distinct windows
+            if getattr(self, "_cyc_ws", None) is None or self._cyc_ws[0] != (T, s_loc):
+                self._cyc_ws = ((T, s_loc), self.ops.power_fft_begin(T, s_loc, self.dt, self.freq))
+            ws = self._cyc_ws[1]
+        done = 0
+
+        def windows_after(frames_complete, blocks):
+            nonlocal done
+            complete = sum(1 for p in pieces if p[1] <= frames_complete)
+            ready = (complete - done) // 2 * 2 if complete < len(pieces) else complete - done
+            if ready > 0:
+                self.ops.power_fft_windows(blocks, self.dt, self.freq, done, ready, ws, series_major=True)
+                done += ready
+
+        if not peers:
+            # single rank, CPU test back-end, or no symmetric memory: one all-to-all per round, same data movement
+            recv = be.empty((nch * g, s_loc, tc), np.complex128)
+            for c in range(nch):
+                send = self.series(velocity_local[c * tc:(c + 1) * tc], tc, t_total=tc)          # (G, S_loc, Tc)
+                if g > 1:
+                    as_t = (lambda x: x) if torch.is_tensor(send) else torch.from_numpy
+                    st, rt = as_t(send), as_t(recv)
+                    tmp = torch.empty_like(st)
+                    dist.all_to_all_single(torch.view_as_real(tmp), torch.view_as_real(st), group=self.group)
+                    rt[c * g:(c + 1) * g] = tmp
+                else:
+                    recv[c:c + 1] = send
+                if fft:
+                    windows_after((c + 1) * g * tc, recv)
+            if fft:
+                return self.ops.power_fft_finish(T, s_loc, self.dt, self.freq, ws)
+            return self.spectra_series(recv)
+
+        pr = self._peer
+        self.peer_begin()
+        if "cyc_views" not in pr:
+            pr["cyc_views"] = [pr["hdl"].get_buffer(r, (nch, g, s_loc, tc, 2), torch.float64) for r in range(g)]
+            pr["cyc_recv"] = torch.view_as_complex(pr["flat"].view(nch * g, s_loc, tc, 2))
+            pr["spec_stream"] = torch.cuda.Stream(device=be.device)
+        send = pr.get("send")
+        if send is None:
+            send = pr["send"] = be.empty((2, g, s_loc, tc), np.complex128)
+        recv, spec = pr["cyc_recv"], pr["spec_stream"]
+        main = torch.cuda.current_stream(be.device)
+        spec.wait_stream(main)
+        ev = []
+        for c in range(nch):
+            slot = c % 2
+            a, m, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            self.peer_wait_slot(slot)
+            a.record(main)
+            own = pr["ptrs"][self.rank] + ((c * g + self.rank) * s_loc * tc) * 16
+            self.series(velocity_local[c * tc:(c + 1) * tc], tc, t_total=tc, mark=lambda: m.record(main),
+                        block_ptrs=[own if dst == self.rank else int(send[slot][dst].data_ptr()) for dst in range(g)])
+            b.record(main)
+            self.peer_push(send[slot], c, slot, views=pr["cyc_views"], index=(c, self.rank))
+            with torch.cuda.stream(spec):
+                spec.wait_event(b)                                   # own block (written by the contraction kernel)
+                for e in pr["slot_free"][slot]:
+                    spec.wait_event(e)                               # own pushes of this round
+                pr["hdl"].barrier(channel=1)                         # ... and everybody else's
+                if fft:
+                    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0.record(spec)
+                    windows_after((c + 1) * g * tc, recv)
+                    s1.record(spec)
+                    ev.append((a, m, b, s0, s1))
+                else:
+                    ev.append((a, m, b, None, None))
+        main.wait_stream(spec)
+        if fft:
+            ps = self.ops.power_fft_finish(T, s_loc, self.dt, self.freq, ws)
+        else:
+            ps = self.spectra_series(recv)
+        if record is not None:
+            torch.cuda.synchronize()
+            record["project"] = sum(a.elapsed_time(m) for a, m, _, _, _ in ev)
+            record["contract"] = sum(m.elapsed_time(b) for _, m, b, _, _ in ev)
+            if fft:
+                record["spectra"] = sum(s0.elapsed_time(s1) for _, _, _, s0, s1 in ev)      # overlapped with later rounds
+                record["exchange"] = max(0.0, ev[-1][2].elapsed_time(ev[-1][3]))              # last round: contraction end -> landed everywhere
+                record["span"] = ev[0][0].elapsed_time(ev[-1][4])
+        return ps
 
     def exchange_series(self, send):
         """The one all-to-all on the series-major layout: (G, S_loc, Tl) -> (G, S_loc, Tl) where block g now

@@ -64,6 +64,8 @@ def test_mesh_pipeline_single_rank(kops):
     ps = to_np(pipe.run(c["v"], chunk_frames=24))
     assert relerr(ps, c["ref_ps"]) < 1e-10
     assert np.array_equal(ps.argmax(0), c["ref_ps"].argmax(0))
+    ps_c = to_np(pipe.run_cyclic(c["v"], chunk_frames=16))                # one rank: chunk-cyclic == contiguous
+    assert relerr(ps_c, c["ref_ps"]) < 1e-10
     for alg, ref in ((1, port.mem_spectra(c["ref_vq"].reshape(64, -1)[:, :6], c["dt"], c["freq"], 10)),):
         pipe1 = pipeline.MeshPipeline(c["plan"], c["eig"], c["freq"], c["dt"], ops=kops, algorithm=alg, mem_coefficients=10)
         assert relerr(to_np(pipe1.spectra(to_np(vq)[:, :6])), ref) < 1e-10
@@ -142,6 +144,42 @@ def test_time_sharded_all_to_all_gloo(tmp_path, world):
         assert relerr(series, ref_series) < 1e-10
         ps = np.load(tmp_path / f"ps{r}.npy")
         assert relerr(ps, c["ref_ps"][:, r * qb * 6:(r + 1) * qb * 6]) < 1e-10
+
+
+def _rank_cyclic(rank, world, port_no, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["DP_EMUL_THREADS"] = "2"
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
+    from emul import emul_ops
+    from dynaphopy_b200 import pipeline
+    c = make_case(nt=768, seed=7)
+    pipe = pipeline.MeshPipeline(c["plan"], c["eig"], c["freq"], c["dt"], ops=emul_ops(), algorithm=2)
+    chunks = pipe.cyclic_chunks(768, 96)
+    assert chunks[0] == (rank * 96, rank * 96 + 96) and len(chunks) == 768 // (world * 96)
+    v_local = np.concatenate([c["v"][a:b] for a, b in chunks])
+    ps = pipe.run_cyclic(v_local, chunk_frames=96)
+    np.save(os.path.join(out_dir, f"psc{rank}.npy"), np.asarray(ps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_chunk_cyclic_sharding_gloo(tmp_path):
+    """Chunk-cyclic time sharding (round c completes frames [0, (c+1)*G*chunk) on every rank; the spectra of finished
+    windows are launched round by round): 2 ranks, 4 rounds, 4 overlapping windows of 250 samples == oracle."""
+    import torch.multiprocessing as mp
+    world = 2
+    port_no = 29900 + os.getpid() % 90
+    mp.spawn(_rank_cyclic, args=(world, port_no, str(tmp_path)), nprocs=world, join=True)
+    c = make_case(nt=768, seed=7)
+    assert len(set(map(tuple, port.division_of_data(c["freq"][1] - c["freq"][0], 768, c["dt"])))) == 4
+    qb = 24 // world
+    for r in range(world):
+        ps = np.load(tmp_path / f"psc{r}.npy")
+        ref = c["ref_ps"][:, r * qb * 6:(r + 1) * qb * 6]
+        assert relerr(ps, ref) < 1e-10
+        assert np.array_equal(ps.argmax(0), ref.argmax(0))
 
 
 @pytest.mark.gpu
