@@ -93,5 +93,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 int sm_count();
+// small host array -> device through kernel parameters (never blocks the host; see dp_core.cu)
+int upload_small(void* dst, const void* src, size_t bytes, cudaStream_t st);
 
 }  // namespace dp

@@ -40,6 +40,30 @@ int sm_count() {
 #endif
 }
 
+// Small host arrays -> device WITHOUT blocking the host: the bytes travel as kernel parameters (1 KB per launch).
+// cudaMemcpyAsync from pageable memory synchronises the host with the stream before it starts, which serialises a
+// caller that wants to queue work ahead of the device (MeshPipeline.run_cyclic, run_from_host).
+struct UploadChunk { unsigned int w[256]; };
+
+__global__ void __launch_bounds__(256) upload_chunk_kernel(unsigned int* __restrict__ dst, UploadChunk c, int nwords) {
+    if ((int)threadIdx.x < nwords) dst[threadIdx.x] = c.w[threadIdx.x];
+}
+
+int upload_small(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    DP_REQUIRE(bytes % 4 == 0 && ((size_t)dst & 3) == 0, DP_ERR_INVALID, "upload_small: 4-byte granularity");
+    const unsigned int* s = (const unsigned int*)src;
+    size_t words = bytes / 4;
+    for (size_t o = 0; o < words; o += 256) {
+        UploadChunk c;
+        const int n = (int)imin<size_t>(256, words - o);
+        memcpy(c.w, s + o, (size_t)n * 4);
+        auto k = upload_chunk_kernel;
+        DP_LAUNCH(k, dim3(1), dim3(256), 0, st, (unsigned int*)dst + o, c, n);
+        DP_CUDA_OK(cudaGetLastError());
+    }
+    return DP_OK;
+}
+
 }  // namespace dp
 
 extern "C" {

@@ -359,10 +359,10 @@ int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_
             if (rc) return rc;
         }
     }
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_starts, pl.starts.data(), pl.starts.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-#ifndef DP_EMUL
-    DP_CUDA_OK(cudaStreamSynchronize(st));   // plan vectors are host temporaries
-#endif
+    // window starts travel as kernel parameters: this entry point never blocks the host, so a caller can queue the
+    // spectra of finished windows behind work that has not run yet
+    rc = dp::upload_small(ws + lay.off_starts, pl.starts.data(), pl.starts.size() * sizeof(int), st);
+    if (rc) return rc;
     double* spec = (double*)(ws + lay.off_spec);
     const int64_t items = (int64_t)S * (pl.use_v2 ? (n_windows + 1) / 2 : n_windows);
     const int grid = (int)dp::imin<int64_t>(items, lay.nslots);

@@ -367,7 +367,7 @@ class MeshPipeline:
         def windows_after(frames_complete, blocks):
             nonlocal done
             complete = sum(1 for p in pieces if p[1] <= frames_complete)
-            ready = (complete - done) // 2 * 2 if complete < len(pieces) else complete - done
+            ready = complete - done              # every finished window now (pairs + possibly one single): start early
             if ready > 0:
                 self.ops.power_fft_windows(blocks, self.dt, self.freq, done, ready, ws, series_major=True)
                 done += ready
@@ -440,6 +440,9 @@ class MeshPipeline:
                 record["spectra"] = sum(s0.elapsed_time(s1) for _, _, _, s0, s1 in ev)      # overlapped with later rounds
                 record["exchange"] = max(0.0, ev[-1][2].elapsed_time(ev[-1][3]))              # last round: contraction end -> landed everywhere
                 record["span"] = ev[0][0].elapsed_time(ev[-1][4])
+                if os.environ.get("DP_CYCLIC_TRACE") and self.rank == 0:      # development aid: per-round timeline (ms)
+                    t0 = ev[0][0]
+                    print("cyclic trace:", [tuple(round(t0.elapsed_time(x), 2) for x in e) for e in ev], flush=True)
         return ps
 
     def exchange_series(self, send):
