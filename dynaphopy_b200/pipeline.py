@@ -367,7 +367,11 @@ class MeshPipeline:
         def windows_after(frames_complete, blocks):
             nonlocal done
             complete = sum(1 for p in pieces if p[1] <= frames_complete)
-            ready = complete - done              # every finished window now (pairs + possibly one single): start early
+            # windows go in pairs (the unit the kernel works in: a single costs 0.65 of a pair); everything at the end;
+            # and with few rounds (exchange-bound, many ranks) the very first window alone, to start early
+            ready = complete - done
+            if complete < len(pieces) and not (done == 0 and nch <= len(pieces)):
+                ready = ready // 2 * 2
             if ready > 0:
                 self.ops.power_fft_windows(blocks, self.dt, self.freq, done, ready, ws, series_major=True)
                 done += ready
