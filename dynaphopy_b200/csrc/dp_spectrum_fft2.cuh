@@ -76,10 +76,18 @@ struct S2Smem {
     cplx* fine;     // [256] w_P^j
     cplx* coarse;   // [256] w_P^(256 j)
     cplx* E;        // S2_WARPS * SUBFFT_EWARP_MAX      exchange slabs (pass 4: the column tile)
+    cplx* PF;       // S2_WARPS * 512                   per-warp landing zone of the NEXT tile (cp.async, passes 1-3)
 };
+// Measured (B200, cfg 5-A): 138.4 ms with the cp.async pipeline vs 129.7 ms without -- the passes are limited by
+// LSU / L2-port throughput (LSU wavefronts 50 %), not by exposed load latency, and the extra shared-memory round trip
+// costs more than the overlap buys.  Kept as a build option (-DDP_S2_PREFETCH=1) for other window lengths.
+#ifndef DP_S2_PREFETCH
+#define DP_S2_PREFETCH 0
+#endif
+constexpr size_t S2_PF_ELEMS = DP_S2_PREFETCH ? (size_t)S2_WARPS * 512 : 0;
 constexpr size_t S2_E_ELEMS = S2_WARPS * SUBFFT_EWARP_MAX > 2 * S2_NP_MAX * S2_CPITCH ? S2_WARPS * SUBFFT_EWARP_MAX
                                                                                   : 2 * S2_NP_MAX * S2_CPITCH;
-constexpr size_t S2_SMEM_BYTES = (size_t)(6 * 256 + S2_E_ELEMS) * sizeof(cplx);
+constexpr size_t S2_SMEM_BYTES = (size_t)(6 * 256 + S2_E_ELEMS + S2_PF_ELEMS) * sizeof(cplx);
 
 // carve the CTA's dynamic shared memory; done inside every pass (from the __shared__ symbol itself) so
 // that the compiler sees shared-space pointers and emits LDS/STS instead of generic loads
@@ -87,6 +95,7 @@ __device__ __forceinline__ S2Smem s2_carve(cplx* smem) {
     S2Smem sm;
     sm.T1 = smem; sm.T2 = smem + 256; sm.T2f = smem + 512; sm.Ts = smem + 768;
     sm.fine = smem + 1024; sm.coarse = smem + 1280; sm.E = smem + 1536;
+    sm.PF = smem + 1536 + S2_E_ELEMS;
     return sm;
 }
 #define S2_SMEM_HERE() DP_DYNSMEM(cplx, s2_smem_base_); const S2Smem sm = s2_carve(s2_smem_base_)
@@ -143,6 +152,39 @@ __device__ __forceinline__ void s2_st_slab(cplx* ptr, cplx v, unsigned long long
 #endif
 }
 
+
+// ---- software pipeline of passes 1-3: the NEXT tile of a warp travels global -> shared memory with cp.async while
+// the current one is transformed; a lane copies exactly the 16 values it will load into registers (slot r*32 + lane:
+// conflict-free), so no cross-lane synchronisation is involved.  Zero fill for samples beyond the window.
+__device__ __forceinline__ unsigned long long s2_stream_policy() {
+#ifdef DP_EMUL
+    return 0;
+#else
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+#endif
+}
+__device__ __forceinline__ void s2_cp16(cplx* dst_smem, const cplx* src, bool valid, unsigned long long pol) {
+#ifdef DP_EMUL
+    *dst_smem = valid ? *src : make_double2(0.0, 0.0);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(d), "l"(src), "r"(sz), "l"(pol) : "memory");
+#endif
+}
+__device__ __forceinline__ void s2_cp_commit() {
+#ifndef DP_EMUL
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void s2_cp_wait() {
+#ifndef DP_EMUL
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
 // ---- pass 1: window -> column FFTs -> A -----------------------------------------------------------
 // LAYOUT 0: time axis contiguous (stride_t == 1, no blocks) -- plain pointer arithmetic in the unrolled loads;
 // 1: contiguous power-of-two time blocks (the all-to-all's receive layout); 2: anything else.
@@ -175,10 +217,39 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
                 w[i * C::R1 + a] = val;
             }
     };
+#if DP_S2_PREFETCH
+    cplx* PB = sm.PF + (size_t)warp * 512 + lane;
+    const unsigned long long spol = s2_stream_policy();
+    auto prefetch_tile = [&](int tile) {
+        const int col = tile * C::NS + seq;
+#pragma unroll
+        for (int i = 0; i < C::NB1; i++)
+#pragma unroll
+            for (int a = 0; a < C::R1; a++) {
+                const int idx = (a * C::R2 + g + C::TG * i) * n2 + col;
+                const bool ok = idx < L;
+                const int t = t0 + (ok ? idx : 0);
+                const cplx* src;
+                if (LAYOUT == 0) src = x + t;
+                else if (LAYOUT == 1) { const int b = t >> tb_shift; src = x + (int64_t)b * tb_stride + (t - (b << tb_shift)); }
+                else src = x + s2_time_offset(p, t);
+                s2_cp16(PB + (i * C::R1 + a) * 32, src, ok, spol);
+            }
+        s2_cp_commit();
+    };
+    if (warp < ntiles) prefetch_tile(warp);
+#endif
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int col = tile * C::NS + seq;
         cplx v[16];
+#if DP_S2_PREFETCH
+        s2_cp_wait();
+#pragma unroll
+        for (int r = 0; r < 16; r++) v[r] = PB[r * 32];
+        if (tile + S2_WARPS < ntiles) prefetch_tile(tile + S2_WARPS);
+#else
         load_tile(tile, v);
+#endif
         sub_dit<C>(v, E, sm.T1, g);
         // four-step twiddle w_P^(col*kk), kk = k1 + R1*k2: geometric in k2
         const cplx ratio = tw2level(sm.fine, sm.coarse, col * C::R1);
@@ -216,11 +287,30 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 #pragma unroll
             for (int a = 0; a < C::R1; a++) w[i * C::R1 + a] = s2_ld_slab(Ar + a * C::R2 + g + C::TG * i, pol);
     };
+#if DP_S2_PREFETCH
+    cplx* PB = sm.PF + (size_t)warp * 512 + lane;
+    auto prefetch_tile = [&](int tile) {
+        const cplx* Ar = A + (size_t)(tile * C::NS + seq) * n2;
+#pragma unroll
+        for (int i = 0; i < C::NB1; i++)
+#pragma unroll
+            for (int a = 0; a < C::R1; a++) s2_cp16(PB + (i * C::R1 + a) * 32, Ar + a * C::R2 + g + C::TG * i, true, pol);
+        s2_cp_commit();
+    };
+    if (warp < ntiles) prefetch_tile(warp);
+#endif
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int row = tile * C::NS + seq;
         cplx* __restrict__ Ar = A + (size_t)row * n2;
         cplx v[16];
+#if DP_S2_PREFETCH
+        s2_cp_wait();
+#pragma unroll
+        for (int r = 0; r < 16; r++) v[r] = PB[r * 32];
+        if (tile + S2_WARPS < ntiles) prefetch_tile(tile + S2_WARPS);
+#else
         load_tile(tile, v);
+#endif
         double sa[16];
         double* __restrict__ Srow = Sr + (size_t)row * n2;
         if (MODE == 2) {                       // |X_a|^2 of the partner window, requested before the butterflies
@@ -283,10 +373,30 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
 #pragma unroll
             for (int a = 0; a < C::R1; a++) w[i * C::R1 + a] = s2_ld_slab(A + (size_t)(a * C::R2 + g + C::TG * i) * n2 + col, pol);
     };
+#if DP_S2_PREFETCH
+    cplx* PB = sm.PF + (size_t)warp * 512 + lane;
+    auto prefetch_tile = [&](int tile) {
+        const int col = tile * C::NS + seq;
+#pragma unroll
+        for (int i = 0; i < C::NB1; i++)
+#pragma unroll
+            for (int a = 0; a < C::R1; a++)
+                s2_cp16(PB + (i * C::R1 + a) * 32, A + (size_t)(a * C::R2 + g + C::TG * i) * n2 + col, true, pol);
+        s2_cp_commit();
+    };
+    if (warp < ntiles) prefetch_tile(warp);
+#endif
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int col = tile * C::NS + seq;
         cplx v[16];
+#if DP_S2_PREFETCH
+        s2_cp_wait();
+#pragma unroll
+        for (int r = 0; r < 16; r++) v[r] = PB[r * 32];
+        if (tile + S2_WARPS < ntiles) prefetch_tile(tile + S2_WARPS);
+#else
         load_tile(tile, v);
+#endif
         sub_dit<C>(v, E, sm.T1, g);
         __syncwarp();          // every lane of the warp has its column in registers before rows are overwritten
 #pragma unroll
