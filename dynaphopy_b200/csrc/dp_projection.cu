@@ -154,6 +154,19 @@ constexpr int PS_MAX_BLOCKS = 16;   // destination blocks with their own base po
 // 512-byte runs of consecutive time samples go straight into the destination rank's receive buffer).
 struct PsBlocks { cplx* p[PS_MAX_BLOCKS]; int n; };
 
+__device__ __forceinline__ void ps_cp16(cplx* dst_smem, const cplx* src) {
+#ifdef DP_EMUL
+    *dst_smem = *src;
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void ps_cp_wait_all() {
+#ifndef DP_EMUL
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
 template <int MT>   // MT > 0: compile-time M (inputs kept in registers); 0: any M
 __global__ void __launch_bounds__(256)
 project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig, int64_t T, int Q, int Mdyn,
@@ -175,6 +188,16 @@ project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict
             if (t0 + f < T) val = __ldcs(vc + ((t0 + f) * Q + q0) * M + j);
             in[f * pitch + j] = val;
         }
+    } else if (MT > 0 && nq == PS_QT_MAX && t0 + PS_TT <= T) {
+        // full tile, compile-time M: shifts instead of divisions, and the 16-byte elements travel global -> shared
+        // memory with cp.async (no register staging, 12 copies in flight per thread)
+        constexpr int np2 = MT > 0 ? MT / 2 : 1, run = PS_QT_MAX * 2;       // (MT == 0 never takes this branch)
+#pragma unroll
+        for (int e = tid; e < PS_TT * np2 * run; e += 256) {
+            const int f = e / (np2 * run), r = e % (np2 * run), pr = r / run, w = r % run;
+            ps_cp16(in + f * pitch + (w >> 1) * MT + pr * 2 + (w & 1), vc + (((t0 + f) * np2 + pr) * Q + q0) * 2 + w);
+        }
+        ps_cp_wait_all();
     } else {                       // vc[t][slot pair][q][2]: runs of nq*2 contiguous values per (frame, pair)
         const int np2 = M / 2, run = nq * 2;
         for (int e = tid; e < PS_TT * np2 * run; e += nthreads) {
