@@ -29,17 +29,42 @@ namespace dp {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // pencil pc: base = (pc % A)*sa + (pc / A)*sb, elements at base + i*st
+// The last decimation-in-time stage is done here rather than inside PencilDft<N>::run: the R sub-transforms read
+// their inputs straight from shared memory and the final butterflies store straight back, so only the N intermediate
+// values are live (2N doubles instead of the 4N-6N of the out-of-place codelet, which spilled for N >= 16 under the
+// 96-register budget of two CTAs per SM).
 template <int N>
 __device__ __noinline__ void axis_pass_n(int npencil, int A, int sa, int sb, int st, int tid, int nthreads) {
     DP_DYNSMEM(cplx, W);             // the transform is the CTA's dynamic shared memory: keep the address space visible
+    constexpr int R = PencilDft<N>::R, M = PencilDft<N>::M;
     for (int pc = tid; pc < npencil; pc += nthreads) {
         const int base = (pc % A) * sa + (pc / A) * sb;
-        cplx in[N], out[N];
+        if constexpr (M == 1) {
+            cplx t[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) in[i] = W[base + i * st];
-        PencilDft<N>::run(in, out);
+            for (int i = 0; i < N; i++) t[i] = W[base + i * st];
+            pencil_bfly<N>(t);
 #pragma unroll
-        for (int i = 0; i < N; i++) W[base + i * st] = out[i];
+            for (int i = 0; i < N; i++) W[base + i * st] = t[i];
+        } else {
+            cplx sub[R][M];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                cplx g[M];
+#pragma unroll
+                for (int mm = 0; mm < M; mm++) g[mm] = W[base + (mm * R + r) * st];
+                PencilDft<M>::run(g, sub[r]);
+            }
+#pragma unroll
+            for (int k = 0; k < M; k++) {
+                cplx t[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) t[r] = (r == 0 || k == 0) ? sub[r][k] : cmul(sub[r][k], root_const(N, r * k));
+                pencil_bfly<R>(t);
+#pragma unroll
+                for (int u = 0; u < R; u++) W[base + (k + M * u) * st] = t[u];
+            }
+        }
     }
 }
 
