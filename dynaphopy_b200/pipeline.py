@@ -192,8 +192,9 @@ class MeshPipeline:
     def peer_exchange_setup(self, n_chunks, chunk_frames):
         """Allocate this rank's receive buffer ``(G, n_chunks, S_loc, Tc)`` in symmetric memory and map every peer's
         buffer (torch.distributed._symmetric_memory: CUDA IPC / fabric handles over NVLink).  Afterwards
-        ``series_exchanged`` lets the contraction kernel of every rank store block g straight into rank g's buffer
-        (``dp_project_phonon_series_peers``) -- no all-to-all, no send buffer, no SMs spent on a copy kernel.
+        ``series_exchanged_peers`` / ``run_cyclic`` / ``run_from_host`` move every contracted block into the destination
+        rank's buffer without a collective: copy engines ("dma") or the contraction kernel's own stores ("stores",
+        ``dp_project_phonon_series_peers``), see ``peer_mode``.
         Returns False (and leaves the NCCL path in place) when symmetric memory is not available."""
         if self.world == 1:
             return False
@@ -277,7 +278,7 @@ class MeshPipeline:
         done.record(main)
         src = torch.view_as_real(send_slot)
         evs = []
-        for k, st in enumerate(pr["streams"]):
+        for st in pr["streams"]:
             st.wait_event(done)
         for j in range(self.world - 1):
             dst = (self.rank + 1 + j) % self.world            # staggered: at any time every rank targets a different peer
