@@ -199,3 +199,41 @@ def test_run_from_host_streams(cuda_ops):
         for i, q in enumerate(c["plan"].q_cart)], axis=1).reshape(96, -1), c["dt"], c["freq"])
     assert relerr(ps, ref) < 1e-10
     assert relerr(ps, to_np(pipe.run(c["v"]))) < 1e-13
+
+
+@pytest.mark.gpu
+def test_full_mesh_parseval_unitarity_linearity(cuda_ops):
+    """BASELINE cfg 5 geometry at full width (10 240 atoms, all 5120 commensurate q, 6 modes), where the oracle is out
+    of reach: size-independent properties of the path.  (1) Parseval of the lattice DFT over the full mesh:
+    sum_q |vc[t,q,p,k]|^2 = sum_cells m_p v[t,cell,p,k]^2.  (2) The contraction with unitary eigenvectors preserves
+    the norm per (t, q).  (3) The whole projection + contraction is linear in the velocities.  (4) The series-major
+    pipeline output is the transpose of the time-major one."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from dynaphopy_b200 import pipeline
+    dev = cuda_ops.be.device
+    wl = bench.workload(1024)
+    plan = pipeline.CommensuratePlan(wl["cell"], bench.DIMS, wl["pos"], wl["mass"], wl["typ"], wl["n_prim"], wl["q_cart"])
+    assert plan.usable() and plan.commensurate.all()
+    eig = bench.random_unitary_eigenvectors(torch, dev, wl["Q"], wl["M"])
+    pipe = pipeline.MeshPipeline(plan, eig, bench.FREQ, bench.DT, ops=cuda_ops, algorithm=2)
+    nt = 256
+    v1 = bench.gen_chunk_torch(torch, dev, wl, 0, nt)
+    v2 = torch.randn(v1.shape, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    vc = pipe.project(v1)                                                   # (T, Q, n_p, 3), twiddles and sqrt(m) applied
+    lhs = (vc.real ** 2 + vc.imag ** 2).sum(dim=1)                          # (T, n_p, 3)
+    mass = torch.as_tensor(wl["mass"], device=dev).reshape(1, 2, -1, 1)
+    rhs = (mass * v1.reshape(nt, 2, -1, 3) ** 2).sum(dim=2)
+    assert float(((lhs - rhs).abs().max() / rhs.abs().max()).item()) < 1e-12
+    n_vc = (vc.real ** 2 + vc.imag ** 2).sum(dim=(2, 3))                    # (T, Q)
+    vq = pipe.contract(vc.clone())                                          # (T, Q*M) time-major, in place on the copy
+    vq = vq.reshape(nt, wl["Q"], wl["M"])
+    n_vq = (vq.real ** 2 + vq.imag ** 2).sum(dim=2)
+    assert float(((n_vq - n_vc).abs().max() / n_vc.abs().max()).item()) < 1e-12
+    s1 = pipe.series(v1, chunk_frames=128)                                  # (1, Q*M, T) series-major, folded twiddle path
+    assert float(((s1[0].t().reshape(nt, wl["Q"], wl["M"]) - vq).abs().max() / vq.abs().max()).item()) < 1e-11
+    a, b = 0.75, -1.5
+    s2 = pipe.series(v2, chunk_frames=128)
+    s12 = pipe.series(a * v1 + b * v2, chunk_frames=128)
+    assert float(((s12 - (a * s1 + b * s2)).abs().max() / s12.abs().max()).item()) < 1e-12
