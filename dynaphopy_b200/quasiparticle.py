@@ -24,6 +24,8 @@ class Quasiparticle:
         self._power_spectrum_direct = None
         self._power_spectrum_partials = None
         self._parameters = Parameters()
+        self._harmonic_provider = None             # q_reduced -> (eigenvectors (M, n_p, 3), frequencies (M,))
+        self._star_provider = None                 # q_reduced -> list of symmetry-equivalent reduced q points
         self.crop_trajectory(last_steps)
 
     # -- state -----------------------------------------------------------------------------------------
@@ -122,13 +124,31 @@ class Quasiparticle:
         self._vq = None
         self._power_spectrum_phonon = None
 
+    def set_harmonic_provider(self, provider):
+        """Callable ``q_reduced -> (eigenvectors (M, n_p, 3), frequencies (M,))`` standing in for
+        ``pho_interface.obtain_eigenvectors_and_frequencies`` (dynaphopy/__init__.py:172-186): with it the eigenvectors
+        follow ``set_reduced_q_vector`` lazily, exactly as in the reference."""
+        self._harmonic_provider = provider
+
+    def set_star_provider(self, provider):
+        """Callable ``q_reduced -> [q_reduced, ...]`` standing in for
+        ``pho_interface.get_equivalent_q_points_by_symmetry`` (used at dynaphopy/__init__.py:727-728)."""
+        self._star_provider = provider
+
+    def _harmonic(self):
+        if self._eigenvectors is None and self._harmonic_provider is not None:
+            e, f = self._harmonic_provider(np.array(self.parameters.reduced_q_vector, dtype=float))
+            self._eigenvectors, self._frequencies = np.asarray(e, dtype=complex), (None if f is None else np.asarray(f))
+
     def get_eigenvectors(self):
+        self._harmonic()
         if self._eigenvectors is None:
             raise RuntimeError("eigenvectors come from phonopy in the reference (dynaphopy/__init__.py:172-186); "
                                "inject them with set_eigenvectors()")
         return self._eigenvectors
 
     def get_frequencies(self):
+        self._harmonic()
         return self._frequencies
 
     # -- projections -----------------------------------------------------------------------------------------
@@ -152,10 +172,26 @@ class Quasiparticle:
         fn = power_spectrum_functions[self.parameters.power_spectra_algorithm][0]
         return fn(columns, self.dynamic, self.parameters)
 
-    def get_power_spectrum_phonon(self):                                     # :721-746 (no symmetry star: phonopy)
+    def get_power_spectrum_phonon(self):                                     # :721-746
         if self._power_spectrum_phonon is None:
             print("Calculating phonon projection power spectra")
-            self._power_spectrum_phonon = self._spectrum(self.get_vq())
+            if self.parameters.use_symmetry and self._star_provider is not None and self._harmonic_provider is not None:
+                # star of q (:725-739).  The reference loops over the equivalent points (projection, contraction and
+                # spectra one q at a time); here the whole star is projected in one pass over the trajectory and all
+                # n_star * M spectra come from one launch.  np.average over the members in the reference's order.
+                initial = np.array(self.get_reduced_q_vector(), dtype=float)
+                star = [np.array(q, dtype=float) for q in self._star_provider(initial)]
+                to_cart = 2.0 * np.pi * np.linalg.inv(self.dynamic.structure.get_primitive_cell()).T
+                vc = projection.project_onto_wave_vectors(self.dynamic, np.array([np.dot(q, to_cart) for q in star]),
+                                                          project_on_atom=self.parameters.project_on_atom)
+                eig = np.array([np.asarray(self._harmonic_provider(q)[0], dtype=complex) for q in star])
+                ops = self.dynamic.ops
+                vq = ops.project_phonon(vc, eig)                                         # (T, n_star, M) on the device
+                nt, ns, m = ops.be.shape(vq)
+                ps = self._spectrum(vq.reshape(nt, ns * m))                              # (F, n_star * M)
+                self._power_spectrum_phonon = np.average([ps[:, i * m:(i + 1) * m] for i in range(ns)], axis=0)
+            else:
+                self._power_spectrum_phonon = self._spectrum(self.get_vq())
         return self._power_spectrum_phonon
 
     def get_power_spectrum_wave_vector(self):                                # :748-779

@@ -155,3 +155,41 @@ def test_commensurate_points_batch_matches_q_loop(kops, monkeypatch):
             assert np.array_equal(data["averaged"][i][:, j], ref)
             assert data["guess_position"][i, j] == g["freq"][np.argmax(ref)]
             assert data["guess_height"][i, j] == np.max(ref)
+
+
+def test_star_of_q_average_matches_loop(kops, monkeypatch):
+    """use_symmetry: get_power_spectrum_phonon averages the spectra over the symmetry-equivalent q points
+    (dynaphopy/__init__.py:725-739).  phonopy's star and eigenvectors are injected; the batched evaluation (one
+    projection pass, one spectrum launch for the whole star) must equal the reference's loop over the members."""
+    from dynaphopy_b200.quasiparticle import Quasiparticle
+    from dynaphopy_b200.parameters import Parameters
+    _patch_default_ops(monkeypatch, kops)
+    g = golden("cubic2_232")
+    Parameters().reset()
+    calc = Quasiparticle(_dynamics(g, kops))
+    calc.parameters.frequency_range = g["freq"]
+    calc.select_power_spectra_algorithm(2)
+    qs = [np.array(q, dtype=float) for q in g["q_reduced"][1:4]]          # three commensurate points play the star
+
+    def harmonic(q):
+        i = [k for k, qq in enumerate(g["q_reduced"]) if np.allclose(qq, q)][0]
+        return g["eigenvectors"][i], np.arange(6.0)
+
+    calc.set_harmonic_provider(harmonic)
+    # the loop of the reference, member by member, without symmetry
+    calc.parameters.use_symmetry = False
+    looped = []
+    for q in qs:
+        calc.set_reduced_q_vector(q)
+        assert relerr(calc.get_eigenvectors(), harmonic(q)[0]) == 0          # lazily fetched for the current q
+        looped.append(calc.get_power_spectrum_phonon())
+    # with symmetry: star provider + batched evaluation
+    calc.parameters.use_symmetry = True
+    calc.set_star_provider(lambda q: qs)
+    calc.set_reduced_q_vector(qs[0])
+    calc.power_spectra_clear()
+    ps = calc.get_power_spectrum_phonon()
+    assert ps.shape == looped[0].shape
+    assert relerr(ps, np.average(looped, axis=0)) < 1e-12
+    assert np.array_equal(calc.get_reduced_q_vector(), qs[0])
+    assert calc.get_power_spectrum_phonon() is ps                            # cached until q or the algorithm changes
