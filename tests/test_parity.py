@@ -540,3 +540,28 @@ def test_project_phonon_series_peer_blocks(kops):
     from dynaphopy_b200._lib import DpError
     with pytest.raises(DpError, match="block pointers"):
         kops.project_phonon_series(vc, eig, q_block=qb, t_total=T, block_ptrs=[kops.be.ptr(blocks[0]).value])
+
+
+def test_small_and_ragged_shapes_of_the_reductions(kops):
+    """Edge shapes of the two reduction kernels: fewer frames than one time split, atom counts that do not fill a
+    CTA, fewer frequencies than a warp, a single series, all-equal and all-NaN spectra."""
+    rng = np.random.default_rng(53)
+    cell = np.diag([5.0, 6.0, 7.0])
+    i, j = np.triu_indices(3)
+    for nt, na in ((1, 1), (3, 5), (17, 257), (40, 300)):
+        pos = rng.random((na, 3)) @ cell
+        tr = pos[None] + rng.normal(scale=0.2, size=(nt, na, 3)) + rng.integers(-1, 2, size=(nt, na, 3)) @ cell
+        u = np.stack([port.atomic_displacements(tr[:, a, :], pos[a], cell) for a in range(na)], axis=1)
+        ref = np.concatenate([u.sum(0), (u[:, :, i] * u[:, :, j]).sum(0)], axis=1)
+        sums = to_np(kops.displacement_moments(tr, pos, cell))
+        assert np.abs(sums - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1e-300), (nt, na)
+    for F, S in ((1, 1), (5, 3), (31, 2), (33, 70)):
+        ps = rng.random((F, S))
+        _, bins, heights = kops.spectra_peaks(ps)
+        assert np.array_equal(to_np(bins), ps.argmax(0)) and np.array_equal(to_np(heights), ps.max(0))
+    flat = np.full((40, 2), 3.0)                      # all equal: the first bin wins
+    flat[:, 1] = np.nan                               # all NaN: bin 0, NaN height
+    _, bins, heights = kops.spectra_peaks(flat)
+    assert list(to_np(bins)) == [0, 0]
+    h = to_np(heights)
+    assert h[0] == 3.0 and np.isnan(h[1])
