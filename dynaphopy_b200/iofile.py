@@ -1,0 +1,104 @@
+"""Trajectory ingest with the reference's parser interface (dynaphopy/interface/iofile/trajectory_parsers.py), the text
+conversion done natively by all host threads (``dp_lammps_scan`` / ``dp_lammps_read``) into ONE (T, N, ndim) float64
+buffer -- pinned when a CUDA device is present, so that ``MeshPipeline.run_from_host`` / the ``Dynamics`` device
+accessors can stream it without another host copy.
+
+    read_lammps_trajectory(file_name, structure, time_step, limit_number_steps, last_steps, initial_cut, end_cut,
+                           memmap, template) -> Dynamics                      (trajectory_parsers.py:135-352)
+
+Differences from the reference, all of representation only: the array is real float64 (the reference stores
+complex128 with zero imaginary part) and ``memmap`` is accepted but unnecessary (no Python list of frames is built).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from .dynamics import Dynamics
+
+
+def _host_buffer(shape, pinned):
+    if pinned:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.empty(shape, dtype=np.float64)
+
+
+def lammps_supercell(bounds, bound_cols, structure, number_of_dimensions=3):
+    """Cell of the dump and the rotation onto the unit-cell orientation (trajectory_parsers.py:217-277)."""
+    bounds = np.array(bounds, dtype=float).reshape(3, 3)[:, :bound_cols]
+    if bounds.shape[1] == 2:
+        bounds = np.append(bounds, np.array([0, 0, 0])[None].T, axis=1)
+    xy, xz, yz = bounds[0, 2], bounds[1, 2], bounds[2, 2]
+    xlo = bounds[0, 0] - np.min([0.0, xy, xz, xy + xz])
+    xhi = bounds[0, 1] - np.max([0.0, xy, xz, xy + xz])
+    ylo = bounds[1, 0] - np.min([0.0, yz])
+    yhi = bounds[1, 1] - np.max([0.0, yz])
+    zlo, zhi = bounds[2, 0], bounds[2, 1]
+    supercell = np.array([[xhi - xlo, xy, xz], [0, yhi - ylo, yz], [0, 0, zhi - zlo]]).T
+    supercell = supercell[:number_of_dimensions, :number_of_dimensions]
+
+    def unit_matrix(matrix):
+        return np.array([np.array(row) / np.linalg.norm(row) for row in matrix])
+
+    transformation_mat = np.dot(np.linalg.inv(unit_matrix(structure.get_cell())), unit_matrix(supercell)).T
+    return np.dot(supercell, transformation_mat), transformation_mat
+
+
+def read_lammps_trajectory(file_name, structure=None, time_step=None, limit_number_steps=10000000, last_steps=None,
+                           initial_cut=1, end_cut=None, memmap=False, template=None, pinned=True, threads=0, ops=None):
+    lib = _lib.load()
+    if not os.path.isfile(file_name):                                   # :162-164
+        print('Trajectory file does not exist!')
+        raise SystemExit
+    if time_step is None:                                               # :167-170
+        print('Warning! LAMMPS trajectory file does not contain time step information')
+        print('Using default: 0.001 ps')
+        time_step = 0.001
+    print("Reading LAMMPS trajectory")
+    number_of_dimensions = 3 if structure is None else structure.get_number_of_dimensions()
+    n_frames, n_atoms, cols = ctypes.c_int64(0), ctypes.c_int(0), ctypes.c_int(0)
+    bounds = np.zeros(9)
+    labels = ctypes.create_string_buffer(512)
+    lib.call("dp_lammps_scan", os.fsencode(file_name), ctypes.byref(n_frames), ctypes.byref(n_atoms),
+             bounds.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cols), labels, 512)
+    n_total, n_atoms = int(n_frames.value), int(n_atoms.value)
+    if structure is not None and n_atoms % structure.get_number_of_cell_atoms() != 0:       # :214-216
+        print('Warning: Number of atoms not matching, check LAMMPS output file')
+    supercell, transformation_mat = lammps_supercell(bounds, int(cols.value), structure, number_of_dimensions)
+    # frames are counted from 1; [initial_cut, end_cut] inclusive, and the "security routine" that stops after
+    # limit_number_steps + initial_cut + 1 frames (:318-324)
+    first = max(int(initial_cut), 1)
+    last = n_total
+    if end_cut is not None:
+        last = min(last, int(end_cut))
+    last = min(last, int(limit_number_steps) + int(initial_cut) + 1)
+    if int(limit_number_steps) + int(initial_cut) + 1 < n_total and (end_cut is None or end_cut > last):
+        print("Warning! maximum number of steps reached! No more steps will be read")
+    count = max(last - first + 1, 0)
+    data = _host_buffer((count, n_atoms, number_of_dimensions), pinned)
+    steps = np.empty(count)
+    if count:
+        lib.call("dp_lammps_read", os.fsencode(file_name), first - 1, count, n_atoms, number_of_dimensions,
+                 data.ctypes.data_as(ctypes.c_void_p), steps.ctypes.data_as(ctypes.c_void_p), int(threads))
+    if template is not None:                                            # :304-306
+        data[...] = data[:, np.argsort(template), :]
+    if not np.array_equal(transformation_mat, np.identity(number_of_dimensions)):
+        for i in range(count):                                          # frame by frame like the reference (:309)
+            data[i] = np.dot(data[i], transformation_mat)
+    time = steps * time_step
+    if last_steps is not None and not memmap:                           # :326-332
+        data = data[-last_steps:, :, :]
+        time = time[-last_steps:]
+    lammps_labels = labels.value
+    if b'vx vy' in lammps_labels:                                       # :335-349
+        return Dynamics(structure=structure, velocity=data, time=time, supercell=supercell, memmap=memmap, ops=ops)
+    if b'x y' in lammps_labels:
+        return Dynamics(structure=structure, trajectory=data, time=time, supercell=supercell, memmap=memmap, ops=ops)
+    print('LAMMPS parsing error. Data not recognized: {}'.format(lammps_labels))
+    raise SystemExit

@@ -285,6 +285,24 @@ int dp_spectra_peaks(const double* spectra, int F, int S, const int* set_ptr, co
                      const int* series_set, int n_sets, double* averaged, int* peak_bin,
                      double* peak_height, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Trajectory ingest (host only): LAMMPS text dump -> (T, N, ndim) doubles.
+ * Replaces: the per-line Python parsing of read_lammps_trajectory
+ *           (dynaphopy/interface/iofile/trajectory_parsers.py:135-352).  Same conventions: frames
+ *           counted at every "TIMESTEP" marker, the first ndim columns of every atom line, cell
+ *           and atom count from the first BOX BOUNDS / NUMBER OF ATOMS blocks.
+ * dp_lammps_scan: n_frames (complete frames), n_atoms, bounds[3][3] row-major (lo, hi, tilt; only
+ *   bound_cols = 2 or 3 columns are present), labels = the last "ITEM: ATOMS ..." line
+ *   (position or velocity dump is decided from it: ' x y' / ' vx vy', :335-349).
+ * dp_lammps_read: frames [first_frame, first_frame + n_frames) (0-based) into `out` [host,
+ *   caller-owned, e.g. pinned], their TIMESTEP values into `timesteps` (or NULL); n_threads <= 0:
+ *   all host threads.  Conversion with strtod (correctly rounded, as Python's float()).
+ * ------------------------------------------------------------------------------------ */
+int dp_lammps_scan(const char* path, int64_t* n_frames, int* n_atoms, double* bounds, int* bound_cols,
+                   char* labels, int labels_len);
+int dp_lammps_read(const char* path, int64_t first_frame, int64_t n_frames, int n_atoms, int ndim,
+                   double* out, double* timesteps, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -294,3 +294,41 @@ def time_step_average(time):
     for i in range(n - 1):
         acc += (time[i + 1] - time[i]) / (n - 1)
     return np.round(acc, decimals=8)
+
+
+# ----------------------------------------------------------------------------------
+# (f)4  LAMMPS dump parsing (interface/iofile/trajectory_parsers.py:135-352), line by line like the reference
+# ----------------------------------------------------------------------------------
+def read_lammps_frames(file_name, number_of_dimensions=3, initial_cut=1, end_cut=None):
+    """(frames (T,N,ndim), TIMESTEP values (T,), bounds rows, labels) with the reference's marker logic."""
+    with open(file_name, "rb") as f:
+        lines = f.read().split(b"\n")
+    frames, steps, bounds, labels, natoms = [], [], None, None, None
+    counter, i = 0, 0
+    while True:
+        while i < len(lines) and b"TIMESTEP" not in lines[i]:
+            i += 1
+        if i >= len(lines):
+            break
+        counter += 1
+        step = float(lines[i + 1])
+        if natoms is None:
+            j = next(k for k, l in enumerate(lines) if b"NUMBER OF ATOMS" in l)
+            natoms = int(lines[j + 1])
+        if bounds is None:
+            j = next(k for k, l in enumerate(lines) if b"BOX BOUNDS" in l)
+            bounds = [[float(x) for x in lines[j + 1 + r].split()] for r in range(3)]
+        while i < len(lines) and b"ITEM: ATOMS" not in lines[i]:
+            i += 1
+        if i >= len(lines):
+            break
+        labels = lines[i]
+        i += 1
+        if initial_cut > counter:
+            continue
+        frames.append([[float(x) for x in lines[i + a].split()[0:number_of_dimensions]] for a in range(natoms)])
+        steps.append(step)
+        i += natoms
+        if end_cut is not None and end_cut <= counter:
+            break
+    return np.array(frames, dtype=float), np.array(steps), bounds, labels

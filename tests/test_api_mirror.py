@@ -2,6 +2,8 @@
 of the kernels, driven the way the reference's own scripts and unit tests drive it
 (unittest/Si_test.py:29-41: build a Dynamics, make a Quasiparticle, set q, select the algorithm, read the
 spectra), and compared with what the REFERENCE returned for the same inputs (tests/golden)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -193,3 +195,80 @@ def test_star_of_q_average_matches_loop(kops, monkeypatch):
     assert relerr(ps, np.average(looped, axis=0)) < 1e-12
     assert np.array_equal(calc.get_reduced_q_vector(), qs[0])
     assert calc.get_power_spectrum_phonon() is ps                            # cached until q or the algorithm changes
+
+
+def _write_dump(path, frames, steps, bounds_lines, labels, extra_cols=0, rng=None):
+    with open(path, "w") as f:
+        for fr, st in zip(frames, steps):
+            f.write("ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n%d\n" % (st, fr.shape[0]))
+            f.write("ITEM: BOX BOUNDS xy xz yz pp pp pp\n" + "\n".join(bounds_lines) + "\n")
+            f.write("ITEM: ATOMS " + labels + " \n")
+            for row in fr:
+                cols = ["%.10f" % v for v in row] + ["%d" % rng.integers(0, 9) for _ in range(extra_cols)]
+                f.write("   " + "   ".join(cols) + " \n")
+
+
+def test_lammps_ingest_synthetic(tmp_path):
+    """dp_lammps_scan / dp_lammps_read + the read_lammps_trajectory mirror on dumps written here: positions with a
+    tilted box and extra columns, a velocity dump, frame ranges, atom template, and the reference's error paths;
+    checked against a line-by-line restatement of the reference's parser (oracle/port.py)."""
+    from oracle import port
+    from dynaphopy_b200 import iofile
+    from dynaphopy_b200._lib import DpError
+    from dynaphopy_b200.structure import Structure
+    rng = np.random.default_rng(61)
+    cell = np.array([[4.0, 0.0, 0.0], [0.4, 4.1, 0.0], [0.3, 0.2, 3.9]])           # rows: lattice vectors (LAMMPS triclinic)
+    st = Structure(cell=cell, positions=np.array([[0.0, 0, 0], [2.0, 2.0, 2.0]]), masses=[28.0855, 69.723])
+    sc = np.diag([2, 2, 2]) @ cell
+    xy, xz, yz = sc[1, 0], sc[2, 0], sc[2, 1]
+    bounds = ["%.8f %.8f %.8f" % (min(0, xy, xz, xy + xz), sc[0, 0] + max(0, xy, xz, xy + xz), xy),
+              "%.8f %.8f %.8f" % (min(0, yz), sc[1, 1] + max(0, yz), xz), "%.8f %.8f %.8f" % (0.0, sc[2, 2], yz)]
+    frames = [rng.normal(scale=3.0, size=(16, 3)) for _ in range(9)]
+    steps = [1000 + 5 * i for i in range(9)]
+    pos_dump = str(tmp_path / "pos.lammpstrj")
+    _write_dump(pos_dump, frames, steps, bounds, "x y z ix iy", extra_cols=2, rng=rng)
+    ref, ref_steps, _, ref_labels = port.read_lammps_frames(pos_dump, 3, initial_cut=2, end_cut=7)
+    dyn = iofile.read_lammps_trajectory(pos_dump, st, time_step=0.002, initial_cut=2, end_cut=7, pinned=False)
+    assert ref.shape == (6, 16, 3) and b"x y" in ref_labels
+    sc_ref, tmat = iofile.lammps_supercell(np.array([[float(x) for x in l.split()] for l in bounds]).ravel(), 3, st)
+    assert np.allclose(sc_ref, sc, atol=1e-6)
+    assert np.array_equal(dyn.trajectory, np.array([np.dot(fr, tmat) for fr in ref]))
+    assert np.array_equal(dyn.get_time(), ref_steps * 0.002)
+    assert dyn._velocity is None
+    # whole file, atom template (argsort reordering), last_steps crop
+    template = rng.permutation(16)
+    dyn2 = iofile.read_lammps_trajectory(pos_dump, st, time_step=0.002, template=template, last_steps=4, pinned=False, threads=3)
+    full, _, _, _ = port.read_lammps_frames(pos_dump, 3)
+    assert np.array_equal(dyn2.trajectory, np.array([np.dot(fr[np.argsort(template)], tmat) for fr in full])[-4:])
+    # velocity dump
+    vel_dump = str(tmp_path / "vel.lammpstrj")
+    _write_dump(vel_dump, frames[:3], steps[:3], bounds, "vx vy vz", rng=rng)
+    dyn3 = iofile.read_lammps_trajectory(vel_dump, st, pinned=False)                  # default time step warning path
+    assert dyn3._velocity is not None and dyn3._velocity.shape == (3, 16, 3)
+    # error behaviour: missing file -> exit(); truncated frame -> "Error reading step"; unknown columns -> exit()
+    with pytest.raises(SystemExit):
+        iofile.read_lammps_trajectory(str(tmp_path / "nope"), st)
+    text = open(pos_dump).read().split("\n")
+    open(pos_dump, "w").write("\n".join(text[:-6]))
+    with pytest.raises(DpError, match="Error reading step 9"):
+        iofile.read_lammps_trajectory(pos_dump, st, pinned=False)
+    assert iofile.read_lammps_trajectory(pos_dump, st, end_cut=8, pinned=False).trajectory.shape == (8, 16, 3)
+    odd = str(tmp_path / "odd.lammpstrj")
+    _write_dump(odd, frames[:1], steps[:1], bounds, "fx fy fz", rng=rng)
+    with pytest.raises(SystemExit):
+        iofile.read_lammps_trajectory(odd, st, pinned=False)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/unittest/Si_data/si.lammpstrj"), reason="reference data not mounted")
+def test_lammps_ingest_matches_reference_parser():
+    """The dump the reference's own reading test uses (unittest/reading_test.py:64-70): bit-identical to what the
+    reference's parser returned (tests/golden/reading_test.npz was written by it)."""
+    from dynaphopy_b200 import iofile
+    from dynaphopy_b200.structure import Structure
+    g = golden("reading_test")
+    st = Structure(cell=g["unit_cell"], positions=g["unit_pos"], masses=g["unit_masses"], primitive_matrix=g["prim_matrix"])
+    dyn = iofile.read_lammps_trajectory("/root/reference/unittest/Si_data/si.lammpstrj", st, initial_cut=3, end_cut=14,
+                                        time_step=0.001, pinned=False)
+    assert np.array_equal(dyn.trajectory, g["lammps_trajectory"])
+    assert np.array_equal(dyn.get_supercell(), g["lammps_supercell"])
+    assert dyn.get_time_step_average() == float(g["lammps_time_step"])
