@@ -48,6 +48,8 @@ SIGNATURES = {
     "dp_spectra_peaks": (_I, [_P, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P]),
     "dp_lammps_scan": (_I, [_c.c_char_p, _P, _P, _P, _P, _c.c_char_p, _I]),
     "dp_lammps_read": (_I, [_c.c_char_p, _L, _L, _I, _I, _P, _P, _I]),
+    "dp_xdatcar_scan": (_I, [_c.c_char_p, _P, _P, _P]),
+    "dp_xdatcar_read": (_I, [_c.c_char_p, _L, _L, _I, _P, _P, _L, _I]),
     "dp_fft_c2c_workspace_bytes": (_Z, [_I, _I]),
     "dp_fft_c2c": (_I, [_P, _P, _I, _I, _I, _P, _Z, _P]),
 }

@@ -105,9 +105,118 @@ static long parse_frame(const char* p, const char* e, int natoms, int ndim, doub
     return -1;
 }
 
+// VASP XDATCAR (read_VASP_XDATCAR, trajectory_parsers.py:355-483): two header lines, three cell lines, one species
+// line, the atom counts; then "Direct configuration= k" followed by N lines of fractional coordinates.
+static int scan_xdatcar(const MappedFile& f, LammpsIndex* ix, int* n_atoms, double* cell) {
+    const char* b = f.p;
+    const char* e = f.p + f.n;
+    const char* l = b;
+    for (int i = 0; i < 2; i++) l = next_line(l, e);
+    for (int r = 0; r < 3; r++) {
+        const char* le = next_line(l, e);
+        const char* q = l;
+        for (int c = 0; c < 3; c++) {
+            char* endp = nullptr;
+            cell[r * 3 + c] = strtod(q, &endp);
+            DP_REQUIRE(endp != q && endp <= le, DP_ERR_INVALID, "XDATCAR: bad cell line %d", r + 1);
+            q = endp;
+        }
+        l = le;
+    }
+    l = next_line(l, e);                                   // species names
+    {
+        const char* le = next_line(l, e);
+        long total = 0;
+        const char* q = l;
+        while (q < le) {
+            char* endp = nullptr;
+            const long v = strtol(q, &endp, 10);
+            if (endp == q || endp > le) break;
+            total += v;
+            q = endp;
+        }
+        DP_REQUIRE(total > 0, DP_ERR_INVALID, "XDATCAR: no atom counts in the header");
+        *n_atoms = (int)total;
+        l = le;
+    }
+    const char* cur = l;
+    while (cur < e) {
+        const char* m = find_token(cur, e, "Direct configuration");
+        if (!m) break;
+        const char* le = next_line(m, e);
+        const char* eq = (const char*)memchr(m, '=', (size_t)(le - m));
+        DP_REQUIRE(eq != nullptr, DP_ERR_INVALID, "XDATCAR: no '=' in the configuration line of frame %zu", ix->timestep.size() + 1);
+        ix->timestep.push_back(strtod(eq + 1, nullptr));
+        ix->data_off.push_back((size_t)(le - b));
+        cur = le;
+    }
+    return DP_OK;
+}
+
+// frames [first, first + n) of an index -> out, all threads; error text names the first bad step (1-based)
+static int convert_frames(const MappedFile& f, const LammpsIndex& ix, int64_t first_frame, int64_t n_frames, int n_atoms,
+                          int ndim, double* out, int n_threads) {
+    const int nt = (int)imax<int64_t>(1, imin<int64_t>(n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency(), n_frames));
+    std::vector<long> bad_atom((size_t)nt, -1);
+    std::vector<int64_t> bad_frame((size_t)nt, -1);
+    auto work = [&](int w) {
+        for (int64_t i = w; i < n_frames; i += nt) {
+            const size_t off = ix.data_off[(size_t)(first_frame + i)];
+            const long r = parse_frame(f.p + off, f.p + f.n, n_atoms, ndim, out + (size_t)i * n_atoms * ndim);
+            if (r >= 0 && bad_frame[(size_t)w] < 0) { bad_frame[(size_t)w] = first_frame + i; bad_atom[(size_t)w] = r; }
+        }
+    };
+    std::vector<std::thread> team;
+    for (int w = 1; w < nt; w++) team.emplace_back(work, w);
+    work(0);
+    for (auto& t : team) t.join();
+    int64_t first_bad = -1;
+    long atom = -1;
+    for (int w = 0; w < nt; w++)
+        if (bad_frame[(size_t)w] >= 0 && (first_bad < 0 || bad_frame[(size_t)w] < first_bad)) { first_bad = bad_frame[(size_t)w]; atom = bad_atom[(size_t)w]; }
+    // the reference stops with "Error reading step N" (trajectory_parsers.py:312-315, 452-454)
+    DP_REQUIRE(first_bad < 0, DP_ERR_INVALID, "Error reading step %lld (atom line %ld)", (long long)(first_bad + 1), atom + 1);
+    return DP_OK;
+}
+
 }  // namespace dp
 
 extern "C" {
+
+int dp_xdatcar_scan(const char* path, int64_t* n_frames, int* n_atoms, double* cell) {
+    DP_REQUIRE(path && n_frames && n_atoms && cell, DP_ERR_INVALID, "dp_xdatcar_scan: null pointer");
+    dp::MappedFile f;
+    int rc = f.open_ro(path);
+    if (rc) return rc;
+    DP_REQUIRE(f.n > 0, DP_ERR_INVALID, "XDATCAR: empty file");
+    dp::LammpsIndex ix;
+    rc = dp::scan_xdatcar(f, &ix, n_atoms, cell);
+    if (rc) return rc;
+    *n_frames = (int64_t)ix.timestep.size();
+    return DP_OK;
+}
+
+int dp_xdatcar_read(const char* path, int64_t first_frame, int64_t n_frames, int n_atoms, double* out, double* steps,
+                    int64_t n_steps, int n_threads) {
+    DP_REQUIRE(path && (out || n_frames == 0), DP_ERR_INVALID, "dp_xdatcar_read: null pointer");
+    DP_REQUIRE(first_frame >= 0 && n_frames >= 0 && n_atoms > 0, DP_ERR_INVALID, "dp_xdatcar_read: bad sizes");
+    dp::MappedFile f;
+    int rc = f.open_ro(path);
+    if (rc) return rc;
+    DP_REQUIRE(f.n > 0, DP_ERR_INVALID, "XDATCAR: empty file");
+    dp::LammpsIndex ix;
+    int na = 0;
+    double cell[9];
+    rc = dp::scan_xdatcar(f, &ix, &na, cell);
+    if (rc) return rc;
+    DP_REQUIRE(first_frame + n_frames <= (int64_t)ix.timestep.size(), DP_ERR_INVALID,
+               "dp_xdatcar_read: frames [%lld, %lld) requested, the file holds %zu", (long long)first_frame,
+               (long long)(first_frame + n_frames), ix.timestep.size());
+    // the configuration numbers of frames [0, n_steps): the reference keeps the time of the skipped frames too (:418)
+    if (steps)
+        for (int64_t i = 0; i < n_steps && i < (int64_t)ix.timestep.size(); i++) steps[i] = ix.timestep[(size_t)i];
+    return dp::convert_frames(f, ix, first_frame, n_frames, n_atoms, 3, out, n_threads);
+}
 
 int dp_lammps_scan(const char* path, int64_t* n_frames, int* n_atoms, double* bounds, int* bound_cols, char* labels,
                    int labels_len) {
@@ -177,27 +286,7 @@ int dp_lammps_read(const char* path, int64_t first_frame, int64_t n_frames, int 
                (long long)(first_frame + n_frames), ix.timestep.size());
     if (timesteps)
         for (int64_t i = 0; i < n_frames; i++) timesteps[i] = ix.timestep[(size_t)(first_frame + i)];
-    const int nt = (int)dp::imax<int64_t>(1, dp::imin<int64_t>(n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency(), n_frames));
-    std::vector<long> bad_atom((size_t)nt, -1);
-    std::vector<int64_t> bad_frame((size_t)nt, -1);
-    auto work = [&](int w) {
-        for (int64_t i = w; i < n_frames; i += nt) {
-            const size_t off = ix.data_off[(size_t)(first_frame + i)];
-            const long r = dp::parse_frame(f.p + off, f.p + f.n, n_atoms, ndim, out + (size_t)i * n_atoms * ndim);
-            if (r >= 0 && bad_frame[(size_t)w] < 0) { bad_frame[(size_t)w] = first_frame + i; bad_atom[(size_t)w] = r; }
-        }
-    };
-    std::vector<std::thread> team;
-    for (int w = 1; w < nt; w++) team.emplace_back(work, w);
-    work(0);
-    for (auto& t : team) t.join();
-    int64_t first_bad = -1;
-    long atom = -1;
-    for (int w = 0; w < nt; w++)
-        if (bad_frame[(size_t)w] >= 0 && (first_bad < 0 || bad_frame[(size_t)w] < first_bad)) { first_bad = bad_frame[(size_t)w]; atom = bad_atom[(size_t)w]; }
-    // the reference stops with "Error reading step N" (trajectory_parsers.py:312-315)
-    DP_REQUIRE(first_bad < 0, DP_ERR_INVALID, "Error reading step %lld (atom line %ld)", (long long)(first_bad + 1), atom + 1);
-    return DP_OK;
+    return dp::convert_frames(f, ix, first_frame, n_frames, n_atoms, ndim, out, n_threads);
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@ accessors can stream it without another host copy.
 
     read_lammps_trajectory(file_name, structure, time_step, limit_number_steps, last_steps, initial_cut, end_cut,
                            memmap, template) -> Dynamics                      (trajectory_parsers.py:135-352)
+    read_VASP_XDATCAR(same arguments)            -> Dynamics                  (trajectory_parsers.py:355-483)
 
 Differences from the reference, all of representation only: the array is real float64 (the reference stores
 complex128 with zero imaginary part) and ``memmap`` is accepted but unnecessary (no Python list of frames is built).
@@ -102,3 +103,42 @@ def read_lammps_trajectory(file_name, structure=None, time_step=None, limit_numb
         return Dynamics(structure=structure, trajectory=data, time=time, supercell=supercell, memmap=memmap, ops=ops)
     print('LAMMPS parsing error. Data not recognized: {}'.format(lammps_labels))
     raise SystemExit
+
+
+def read_VASP_XDATCAR(file_name, structure=None, time_step=None, limit_number_steps=10000000, last_steps=None,
+                      initial_cut=1, end_cut=None, memmap=False, template=None, pinned=True, threads=0, ops=None):
+    lib = _lib.load()
+    if not os.path.isfile(file_name):                                   # :381-383
+        print('Trajectory file does not exist!')
+        raise SystemExit
+    if time_step is None:                                               # :386-389
+        print('Warning! XDATCAR file does not contain time step information')
+        print('Using default: 0.001 ps')
+        time_step = 0.001
+    print("Reading XDATCAR file")
+    n_frames, n_atoms = ctypes.c_int64(0), ctypes.c_int(0)
+    super_cell = np.zeros((3, 3))
+    lib.call("dp_xdatcar_scan", os.fsencode(file_name), ctypes.byref(n_frames), ctypes.byref(n_atoms),
+             super_cell.ctypes.data_as(ctypes.c_void_p))
+    n_total, n_atoms = int(n_frames.value), int(n_atoms.value)
+    first = max(int(initial_cut), 1)
+    last = n_total
+    if end_cut is not None:
+        last = min(last, int(end_cut))
+    last = min(last, int(limit_number_steps) + int(initial_cut) + 1)
+    if int(limit_number_steps) + int(initial_cut) + 1 < n_total and (end_cut is None or end_cut > last):
+        print("Warning! maximum number of steps reached! No more steps will be read")
+    count = max(last - first + 1, 0)
+    data = _host_buffer((count, n_atoms, 3), pinned)
+    # the reference appends the time of EVERY frame it passes, skipped ones included (:418 is before the cut at :429)
+    steps = np.empty(max(last, 0))
+    if count or steps.size:
+        lib.call("dp_xdatcar_read", os.fsencode(file_name), first - 1, count, n_atoms,
+                 data.ctypes.data_as(ctypes.c_void_p), steps.ctypes.data_as(ctypes.c_void_p), steps.size, int(threads))
+    if template is not None:                                            # :440-442
+        data[...] = data[:, np.argsort(template), :]
+    time = steps * time_step
+    if last_steps is not None and not memmap:                           # :472-474
+        data = data[-last_steps:, :, :]
+        time = time[-last_steps:]
+    return Dynamics(structure=structure, scaled_trajectory=data, time=time, supercell=super_cell, memmap=memmap, ops=ops)

@@ -303,6 +303,14 @@ int dp_lammps_scan(const char* path, int64_t* n_frames, int* n_atoms, double* bo
 int dp_lammps_read(const char* path, int64_t first_frame, int64_t n_frames, int n_atoms, int ndim,
                    double* out, double* timesteps, int n_threads);
 
+/* Same for VASP XDATCAR files (read_VASP_XDATCAR, trajectory_parsers.py:355-483): header cell (3 x 3, the scale
+ * line is ignored like in the reference), atom count = sum of the counts line, frames at every
+ * "Direct configuration= k" marker, fractional coordinates.  `steps` receives the configuration numbers of
+ * frames [0, n_steps) -- the reference keeps the times of the frames it skips. */
+int dp_xdatcar_scan(const char* path, int64_t* n_frames, int* n_atoms, double* cell);
+int dp_xdatcar_read(const char* path, int64_t first_frame, int64_t n_frames, int n_atoms, double* out,
+                    double* steps, int64_t n_steps, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,7 @@ def reading_test_case():
             if tag == "xdatcar":
                 template = io.check_atoms_order(fname, parser, st)
                 dyn = parser(fname, st, initial_cut=3, end_cut=14, time_step=ts, template=template)
+                out["xdatcar_template"] = np.array(template)
             else:
                 dyn = parser(fname, st, initial_cut=3, end_cut=14, time_step=ts)
             sc = dyn.get_supercell_matrix()
@@ -161,6 +162,7 @@ def reading_test_case():
             out[tag + "_relative"] = np.array(dyn.get_relative_trajectory()).real
             out[tag + "_mean_matrix"] = np.average(dyn.get_mean_displacement_matrix(), axis=0)
             out[tag + "_time_step"] = dyn.get_time_step_average()
+            out[tag + "_time"] = np.array(dyn.get_time())
             # dynamics.py:207-295 in full: per-type matrices, the average-position variant, average positions
             out[tag + "_mean_matrix_types"] = np.array(dyn.get_mean_displacement_matrix())
             dyn._mean_displacement_matrix = None

@@ -272,3 +272,55 @@ def test_lammps_ingest_matches_reference_parser():
     assert np.array_equal(dyn.trajectory, g["lammps_trajectory"])
     assert np.array_equal(dyn.get_supercell(), g["lammps_supercell"])
     assert dyn.get_time_step_average() == float(g["lammps_time_step"])
+
+
+def test_xdatcar_ingest_synthetic(tmp_path):
+    """dp_xdatcar_scan / dp_xdatcar_read + the read_VASP_XDATCAR mirror on a file written here (two species, several
+    frames): frame ranges, the reference's habit of keeping the times of skipped frames, template, truncation error."""
+    from dynaphopy_b200 import iofile
+    from dynaphopy_b200._lib import DpError
+    from dynaphopy_b200.structure import Structure
+    rng = np.random.default_rng(67)
+    cell = np.array([[8.0, 0.0, 0.0], [0.5, 8.2, 0.0], [0.0, 0.3, 7.8]])
+    st = Structure(cell=cell / 2, positions=np.array([[0.0, 0, 0], [2.0, 2.0, 2.0]]), masses=[28.0855, 69.723])
+    frames = [rng.random((16, 3)) for _ in range(7)]
+    path = str(tmp_path / "XDATCAR")
+    with open(path, "w") as f:
+        f.write("unknown system\n           1\n")
+        for row in cell:
+            f.write("  %12.6f %12.6f %12.6f\n" % tuple(row))
+        f.write("   Si   Ga\n   8   8\n")
+        for k, fr in enumerate(frames):
+            f.write("Direct configuration= %5d\n" % (k + 1))
+            for row in fr:
+                f.write("   %.8f  %.8f  %.8f\n" % tuple(row))
+    parsed = np.array([[[float("%.8f" % v) for v in row] for row in fr] for fr in frames])
+    dyn = iofile.read_VASP_XDATCAR(path, st, time_step=0.0005, initial_cut=2, end_cut=6, pinned=False, threads=2)
+    assert np.array_equal(dyn._scaled_trajectory, parsed[1:6])
+    assert np.array_equal(dyn.get_supercell(), np.array([[float("%12.6f" % v) for v in row] for row in cell]))
+    assert np.array_equal(dyn.get_time(), np.arange(1, 7) * 0.0005)                  # six times for five frames (:418 vs :429)
+    assert np.array_equal(np.asarray(dyn.trajectory), np.dot(parsed[1:6], dyn.get_supercell()))
+    template = rng.permutation(16)
+    dyn2 = iofile.read_VASP_XDATCAR(path, st, time_step=0.0005, template=template, last_steps=3, pinned=False)
+    assert np.array_equal(dyn2._scaled_trajectory, parsed[:, np.argsort(template)][-3:])
+    text = open(path).read().split("\n")
+    open(path, "w").write("\n".join(text[:-4]))
+    with pytest.raises(DpError, match="Error reading step 7"):
+        iofile.read_VASP_XDATCAR(path, st, pinned=False)
+    with pytest.raises(SystemExit):
+        iofile.read_VASP_XDATCAR(str(tmp_path / "nope"), st)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/unittest/Si_data/XDATCAR"), reason="reference data not mounted")
+def test_xdatcar_ingest_matches_reference_parser():
+    """unittest/reading_test.py:23-35: same file, same cuts and template -> bit-identical to the reference's parser."""
+    from dynaphopy_b200 import iofile
+    from dynaphopy_b200.structure import Structure
+    g = golden("reading_test")
+    st = Structure(cell=g["unit_cell"], positions=g["unit_pos"], masses=g["unit_masses"], primitive_matrix=g["prim_matrix"])
+    dyn = iofile.read_VASP_XDATCAR("/root/reference/unittest/Si_data/XDATCAR", st, initial_cut=3, end_cut=14,
+                                   time_step=0.0005, template=g["xdatcar_template"], pinned=False)
+    assert np.array_equal(np.asarray(dyn.trajectory), g["xdatcar_trajectory"])
+    assert np.array_equal(dyn.get_supercell(), g["xdatcar_supercell"])
+    assert np.array_equal(dyn.get_time(), g["xdatcar_time"])
+    assert dyn.get_time_step_average() == float(g["xdatcar_time_step"])
