@@ -142,3 +142,41 @@ def read_VASP_XDATCAR(file_name, structure=None, time_step=None, limit_number_st
         data = data[-last_steps:, :, :]
         time = time[-last_steps:]
     return Dynamics(structure=structure, scaled_trajectory=data, time=time, supercell=super_cell, memmap=memmap, ops=ops)
+
+
+# -- atom order of a trajectory file vs the order the kernels assume (interface/iofile/__init__.py:23-128) ------------
+def get_correct_arrangement(reference, structure):
+    """Template such that ``frame[np.argsort(template)]`` is in DynaPhoPy's supercell order
+    (i = u*N_cells + x + Nx*(y + Ny*z), atoms.py:139-156) -- same result as the reference's O(N^2) search
+    (nearest unit-cell atom with its folded metric, then nearest lattice point), computed per atom in O(N)."""
+    cell = np.asarray(structure.get_cell(), dtype=float)
+    scaled = np.dot(np.asarray(reference).real, np.linalg.inv(cell))
+    n_cell_atoms = structure.get_number_of_atoms()
+    n_super = scaled.shape[0]
+    dims = np.array(np.round(np.max(scaled, axis=0)), dtype=int)
+    unit_scaled = scaled - np.array(scaled, dtype=int)                        # truncation, like the reference (:56)
+    sp = np.dot(np.asarray(structure.get_positions(), dtype=float), np.linalg.inv(cell))
+    diff = np.abs(unit_scaled[:, None, :] - sp[None, :, :])                   # :62-66
+    diff[diff >= 0.5] -= 1.0
+    diff[diff < -0.5] += 1.0
+    unit_index = np.argmin(np.linalg.norm(diff, axis=2), axis=1)
+    lp = scaled - sp[unit_index]                                              # :91-98
+    for k in range(3):
+        hi = lp[:, k] > dims[k] - 0.5
+        lp[hi, k] -= dims[k]
+        lo = lp[:, k] < -0.5
+        lp[lo, k] += dims[k]
+    xyz = np.clip(np.round(lp).astype(int), 0, dims - 1)                      # nearest point of dynaphopy_order (:80,:100-101)
+    lattice = xyz[:, 0] + dims[0] * (xyz[:, 1] + dims[1] * xyz[:, 2])
+    template = lattice + unit_index * n_super / n_cell_atoms
+    if len(np.unique(template)) < len(template):                              # :122-125
+        print('template failed, auto-order will not be applied')
+        print('unique: {} / {}'.format(len(np.unique(template)), len(template)))
+        return range(len(template))
+    return template
+
+
+def check_atoms_order(filename, trajectory_reading_function, structure):
+    """interface/iofile/__init__.py:23-40: read the first frame and derive the template from it."""
+    trajectory = trajectory_reading_function(filename, structure=structure, initial_cut=0, end_cut=1)
+    return get_correct_arrangement(np.asarray(trajectory.trajectory)[0], structure)

@@ -332,3 +332,37 @@ def read_lammps_frames(file_name, number_of_dimensions=3, initial_cut=1, end_cut
         if end_cut is not None and end_cut <= counter:
             break
     return np.array(frames, dtype=float), np.array(steps), bounds, labels
+
+
+def get_correct_arrangement(reference, cell, scaled_positions):
+    """interface/iofile/__init__.py:43-128, the reference's O(N^2) search restated step by step."""
+    scaled_coordinates = [np.array(np.dot(c, np.linalg.inv(cell)).real, dtype=float) for c in reference]
+    number_of_cell_atoms = len(scaled_positions)
+    number_of_supercell_atoms = len(scaled_coordinates)
+    supercell_dim = np.array(np.round(np.max(scaled_coordinates, axis=0)), dtype=int)
+    unit = scaled_coordinates - np.array(scaled_coordinates, dtype=int)
+    atom_unit_cell_index = []
+    for coordinate in unit:
+        diff = np.abs(np.array([coordinate] * number_of_cell_atoms) - scaled_positions)
+        diff[diff >= 0.5] -= 1.0
+        diff[diff < -0.5] += 1.0
+        atom_unit_cell_index.append(np.argmin(np.linalg.norm(diff, axis=1)))
+    atom_unit_cell_index = np.array(atom_unit_cell_index)
+
+    def order(i, size):
+        return np.array([np.mod(i, size[0]), np.mod(i, size[0] * size[1]) // size[0],
+                         np.mod(i, size[0] * size[1] * size[2]) // (size[1] * size[0])])
+    original_conf = np.array([order(j, supercell_dim) for j in range(number_of_supercell_atoms)])
+    template = []
+    for i, coordinate in enumerate(scaled_coordinates):
+        lp = coordinate - scaled_positions[atom_unit_cell_index[i]]
+        for k in range(3):
+            if lp[k] > supercell_dim[k] - 0.5:
+                lp[k] = lp[k] - supercell_dim[k]
+            if lp[k] < -0.5:
+                lp[k] = lp[k] + supercell_dim[k]
+        comparison = np.array([lp] * number_of_supercell_atoms)
+        dm = comparison / supercell_dim[None, :].astype(float) - original_conf / supercell_dim[None, :].astype(float)
+        template.append(np.argmin(np.linalg.norm(dm, axis=1)) +
+                        atom_unit_cell_index[i] * number_of_supercell_atoms / number_of_cell_atoms)
+    return np.array(template)

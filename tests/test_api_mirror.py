@@ -324,3 +324,42 @@ def test_xdatcar_ingest_matches_reference_parser():
     assert np.array_equal(dyn.get_supercell(), g["xdatcar_supercell"])
     assert np.array_equal(dyn.get_time(), g["xdatcar_time"])
     assert dyn.get_time_step_average() == float(g["xdatcar_time_step"])
+
+
+def test_atom_order_template_vs_reference_search(tmp_path):
+    """get_correct_arrangement (O(N)) against the reference's O(N^2) search (restated in oracle/port.py) on shuffled,
+    thermally displaced supercells, and check_atoms_order end to end through the XDATCAR reader."""
+    from oracle import port
+    from dynaphopy_b200 import iofile
+    from dynaphopy_b200.structure import Structure
+    rng = np.random.default_rng(71)
+    cell = np.array([[4.0, 0.0, 0.0], [0.3, 4.2, 0.0], [0.0, 0.2, 3.9]])
+    unit = np.array([[0.1, 0.1, 0.1], [2.3, 2.6, 2.4], [0.3, 2.9, 1.2]])      # (the reference's supercell-size guess
+    # round(max(scaled)) needs an atom beyond the middle of the cell in every direction, and no exact half-cell pairs)
+    st = Structure(cell=cell, positions=unit, masses=[28.0855, 69.723, 15.999])
+    sp = unit @ np.linalg.inv(cell)
+    for dims in ((2, 2, 2), (3, 2, 4)):
+        pos = st.get_positions(supercell=dims) + rng.normal(scale=0.08, size=(3 * int(np.prod(dims)), 3))
+        perm = rng.permutation(len(pos))
+        shuffled = pos[perm]
+        template = np.asarray(iofile.get_correct_arrangement(shuffled, st))
+        assert np.array_equal(template, port.get_correct_arrangement(shuffled, cell, sp))
+        assert np.array_equal(shuffled[np.argsort(template)], pos)              # the readers' reordering (:304-306)
+    # end to end: an XDATCAR in shuffled order comes back in DynaPhoPy's order
+    dims = (2, 2, 2)
+    sc = np.diag(dims) @ cell
+    pos = st.get_positions(supercell=dims)
+    perm = rng.permutation(len(pos))
+    path = str(tmp_path / "XDATCAR")
+    with open(path, "w") as f:
+        f.write("shuffled\n 1\n")
+        for row in sc:
+            f.write("  %14.8f %14.8f %14.8f\n" % tuple(row))
+        f.write(" A B C\n 8 8 8\n")
+        for k in range(3):
+            f.write("Direct configuration= %5d\n" % (k + 1))
+            for row in (pos[perm] + 0.01 * k) @ np.linalg.inv(sc):
+                f.write("   %.10f  %.10f  %.10f\n" % tuple(row))
+    template = iofile.check_atoms_order(path, lambda *a, **k: iofile.read_VASP_XDATCAR(*a, pinned=False, **k), st)
+    dyn = iofile.read_VASP_XDATCAR(path, st, time_step=0.001, template=template, pinned=False)
+    assert np.abs(np.asarray(dyn.trajectory)[0] - pos).max() < 1e-8
