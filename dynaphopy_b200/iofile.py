@@ -180,3 +180,21 @@ def check_atoms_order(filename, trajectory_reading_function, structure):
     """interface/iofile/__init__.py:23-40: read the first frame and derive the template from it."""
     trajectory = trajectory_reading_function(filename, structure=structure, initial_cut=0, end_cut=1)
     return get_correct_arrangement(np.asarray(trajectory.trajectory)[0], structure)
+
+
+def get_trajectory_parser(file_name, bytes_to_check=1000000):
+    """interface/iofile/__init__.py:139-164: pick the reader from the keywords found at the head of the file (the
+    deprecated OUTCAR reader of the reference is not provided: such files return None here)."""
+    parsers_keywords = {'lammps_dump': {'function': read_lammps_trajectory,
+                                        'keywords': ['ITEM: TIMESTEP', 'ITEM: NUMBER OF ATOMS', 'ITEM: BOX BOUNDS']},
+                        'vasp_xdatcar': {'function': read_VASP_XDATCAR,
+                                         'keywords': ['Direct configuration', 'Direct configuration', '=']}}
+    if not os.path.isfile(file_name):
+        print(file_name + ' file does not exist')
+        raise SystemExit
+    with open(file_name, "rb") as f:
+        head = f.read(int(bytes_to_check))
+    for parser in parsers_keywords.values():
+        if all(head.find(keyword.encode()) >= 0 for keyword in parser['keywords']):
+            return parser['function']
+    return None

@@ -227,6 +227,7 @@ def test_lammps_ingest_synthetic(tmp_path):
     steps = [1000 + 5 * i for i in range(9)]
     pos_dump = str(tmp_path / "pos.lammpstrj")
     _write_dump(pos_dump, frames, steps, bounds, "x y z ix iy", extra_cols=2, rng=rng)
+    assert iofile.get_trajectory_parser(pos_dump) is iofile.read_lammps_trajectory
     ref, ref_steps, _, ref_labels = port.read_lammps_frames(pos_dump, 3, initial_cut=2, end_cut=7)
     dyn = iofile.read_lammps_trajectory(pos_dump, st, time_step=0.002, initial_cut=2, end_cut=7, pinned=False)
     assert ref.shape == (6, 16, 3) and b"x y" in ref_labels
@@ -360,6 +361,7 @@ def test_atom_order_template_vs_reference_search(tmp_path):
             f.write("Direct configuration= %5d\n" % (k + 1))
             for row in (pos[perm] + 0.01 * k) @ np.linalg.inv(sc):
                 f.write("   %.10f  %.10f  %.10f\n" % tuple(row))
+    assert iofile.get_trajectory_parser(path) is iofile.read_VASP_XDATCAR          # keyword sniffing (:139-164)
     template = iofile.check_atoms_order(path, lambda *a, **k: iofile.read_VASP_XDATCAR(*a, pinned=False, **k), st)
     dyn = iofile.read_VASP_XDATCAR(path, st, time_step=0.001, template=template, pinned=False)
     assert np.abs(np.asarray(dyn.trajectory)[0] - pos).max() < 1e-8
