@@ -365,3 +365,45 @@ def test_atom_order_template_vs_reference_search(tmp_path):
     template = iofile.check_atoms_order(path, lambda *a, **k: iofile.read_VASP_XDATCAR(*a, pinned=False, **k), st)
     dyn = iofile.read_VASP_XDATCAR(path, st, time_step=0.001, template=template, pinned=False)
     assert np.abs(np.asarray(dyn.trajectory)[0] - pos).max() < 1e-8
+
+
+def test_dump_to_spectrum_end_to_end(kops, monkeypatch, tmp_path):
+    """The whole drop-in path in one go, as a user of the reference would drive it: LAMMPS velocity dump -> native
+    reader -> Dynamics -> Quasiparticle (q, eigenvectors, FFT selector) -> phonon power spectra, against the oracle
+    fed with the numbers written to the file."""
+    from oracle import port
+    from dynaphopy_b200 import iofile
+    from dynaphopy_b200.quasiparticle import Quasiparticle
+    from dynaphopy_b200.parameters import Parameters
+    from dynaphopy_b200.structure import Structure
+    _patch_default_ops(monkeypatch, kops)
+    rng = np.random.default_rng(73)
+    cell = np.diag([4.0, 4.1, 3.9])
+    st = Structure(cell=cell, positions=np.array([[0.0, 0, 0], [2.0, 2.05, 1.95]]), masses=[28.0855, 69.723])
+    dims = (2, 2, 2)
+    nt, dt = 128, 0.002
+    v = rng.normal(size=(nt, 16, 3))
+    sc = np.diag(dims) @ cell
+    bounds = ["0.0 %.8f" % sc[0, 0], "0.0 %.8f" % sc[1, 1], "0.0 %.8f" % sc[2, 2]]
+    path = str(tmp_path / "vel.lammpstrj")
+    _write_dump(path, list(v), [100 + i for i in range(nt)], bounds, "vx vy vz", rng=rng)
+    v_file = np.array([[[float("%.10f" % x) for x in row] for row in fr] for fr in v])
+    Parameters().reset()
+    dyn = iofile.read_lammps_trajectory(path, st, time_step=dt, pinned=False, ops=kops)
+    assert dyn.get_time_step_average() == dt and np.array_equal(dyn.get_supercell_matrix(), dims)
+    calc = Quasiparticle(dyn)
+    calc.parameters.use_symmetry = False
+    calc.parameters.frequency_range = np.arange(0, 40.05, 2.5)
+    calc.select_power_spectra_algorithm(2)
+    q_red = np.array([0.5, 0.0, 0.5])
+    calc.set_reduced_q_vector(q_red)
+    eig = np.linalg.qr(rng.normal(size=(6, 6)) + 1j * rng.normal(size=(6, 6)))[0].T.reshape(6, 2, 3)
+    calc.set_eigenvectors(eig)
+    ps = calc.get_power_spectrum_phonon()
+    pos = st.get_positions(supercell=dims)
+    typ = st.get_atom_type_index(supercell=dims)
+    vm = port.velocity_mass_average(v_file, st.get_masses(supercell=dims))
+    vq = port.project_onto_phonon(port.project_onto_wave_vector(vm, pos, typ, 2, calc.get_q_vector()), eig)
+    ref = port.fft_spectra(vq, dt, calc.parameters.frequency_range)
+    assert relerr(ps, ref) < TOL
+    assert np.array_equal(ps.argmax(0), ref.argmax(0))
