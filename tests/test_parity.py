@@ -565,3 +565,46 @@ def test_small_and_ragged_shapes_of_the_reductions(kops):
     assert list(to_np(bins)) == [0, 0]
     h = to_np(heights)
     assert h[0] == 3.0 and np.isnan(h[1])
+
+
+def test_randomised_shapes_property(kops):
+    """Randomly drawn shapes (seeded) for the kernels whose index arithmetic depends on ragged sizes: decimated lag
+    sums (any T / step), per-destination contraction blocks (any T, Q, q_block, both vc layouts), degenerate-set
+    partitions."""
+    rng = np.random.default_rng(79)
+    f = np.array([0.5, 7.0, 21.0])
+    cuda = is_cuda(kops)
+    for _ in range(6 if cuda else 4):
+        nt = int(rng.integers(12, 1400 if cuda else 500))
+        step = int(rng.integers(1, 13))
+        x = _series(rng, nt, 2, 0.002)
+        for method in (1, 0):
+            ref = port.correlation_spectra(x, 0.002, f, step, method, "intended")
+            pc = to_np(kops.power_correlation(x, 0.002, f, step, method, 1))
+            if np.isnan(ref).any():
+                assert np.array_equal(np.isnan(pc), np.isnan(ref)), (nt, step)
+            else:
+                assert relerr(pc, ref) < TOL, (nt, step, method)
+    for _ in range(4):
+        M = int(rng.choice([3, 6, 12]))
+        nb = int(rng.integers(1, 5))
+        qb = int(rng.integers(1, 7))
+        Q, T = nb * qb, int(rng.integers(1, 90))
+        vc = rng.normal(size=(T, Q, M)) + 1j * rng.normal(size=(T, Q, M))
+        eig = rng.normal(size=(Q, M, M)) + 1j * rng.normal(size=(Q, M, M))
+        ref = np.einsum("tqj,qsj->qst", vc, np.conj(eig)).reshape(nb, qb * M, T)
+        blocks = [kops.be.asarray(np.zeros((qb * M, T), complex), np.complex128) for _ in range(nb)]
+        kops.project_phonon_series(vc, eig, q_block=qb, t_total=T, block_ptrs=[kops.be.ptr(b).value for b in blocks])
+        for g, b in enumerate(blocks):
+            assert relerr(to_np(b), ref[g]) < 1e-13, (T, Q, M, qb)
+    for _ in range(4):
+        F, S = int(rng.integers(1, 70)), int(rng.integers(1, 40))
+        ps = rng.random((F, S))
+        perm = rng.permutation(S)
+        cuts = np.sort(rng.choice(np.arange(1, S), size=min(S - 1, int(rng.integers(0, 6))), replace=False)) if S > 1 else []
+        sets = [list(map(int, g)) for g in np.split(perm, cuts)]
+        avg, bins, heights = (to_np(a) for a in kops.spectra_peaks(ps, sets))
+        for g in sets:
+            ref = np.average([ps[:, k] for k in g], axis=0)
+            for k in g:
+                assert np.array_equal(avg[:, k], ref) and bins[k] == ref.argmax() and heights[k] == ref.max()
