@@ -17,6 +17,7 @@ import numpy as np
 
 from . import _lib
 from .dynamics import Dynamics
+from .structure import Structure
 
 
 def _host_buffer(shape, pinned):
@@ -198,3 +199,41 @@ def get_trajectory_parser(file_name, bytes_to_check=1000000):
         if all(head.find(keyword.encode()) >= 0 for keyword in parser['keywords']):
             return parser['function']
     return None
+
+
+def read_from_file_structure_poscar(file_name, number_of_dimensions=3, masses=None):
+    """interface/iofile/__init__.py:268-328 (new and old style POSCAR, Direct or Cartesian coordinates).  The
+    reference looks the atomic masses up in its own periodic table (atoms.py:383-); this package carries no such table:
+    pass ``masses`` as ``{element: mass}`` or as one value per atom."""
+    if not os.path.isfile(file_name):
+        print('Structure file does not exist!')
+        raise SystemExit
+    print("Reading VASP POSCAR structure")
+    with open(file_name, 'r') as poscar_file:
+        data_lines = poscar_file.read().split('\n')
+    multiply = float(data_lines[1])
+    direct_cell = np.array([data_lines[i].split() for i in range(2, 2 + number_of_dimensions)], dtype=float)
+    direct_cell *= multiply
+    scaled_positions = None
+    positions = None
+    try:
+        number_of_types = np.array(data_lines[3 + number_of_dimensions].split(), dtype=int)
+        first, names = 8, data_lines[5].split()
+        coordinates_type = data_lines[4 + number_of_dimensions][0]
+    except ValueError:                                                  # old style: no element line (:306-321)
+        print("Reading old style POSCAR")
+        number_of_types = np.array(data_lines[5].split(), dtype=int)
+        first, names = 7, data_lines[0].split()
+        coordinates_type = data_lines[6][0]
+    coords = np.array([data_lines[first + k].split()[0:3] for k in range(np.sum(number_of_types))], dtype=float)
+    if coordinates_type in ('D', 'd'):
+        scaled_positions = coords
+    else:
+        positions = coords
+    atomic_types = [name for i, name in enumerate(names[:len(number_of_types)]) for _ in range(number_of_types[i])]
+    if masses is None:
+        raise ValueError("atomic masses are not stored in a POSCAR: pass masses={element: mass} (or one mass per atom)")
+    if isinstance(masses, dict):
+        masses = [masses[e] for e in atomic_types]
+    return Structure(cell=direct_cell, scaled_positions=scaled_positions, positions=positions, masses=masses,
+                     atomic_elements=atomic_types)

@@ -407,3 +407,39 @@ def test_dump_to_spectrum_end_to_end(kops, monkeypatch, tmp_path):
     ref = port.fft_spectra(vq, dt, calc.parameters.frequency_range)
     assert relerr(ps, ref) < TOL
     assert np.array_equal(ps.argmax(0), ref.argmax(0))
+
+
+def test_poscar_structure_reader(tmp_path):
+    from dynaphopy_b200 import iofile
+    cell = np.array([[5.4661639157319968, 0, 0], [0, 5.4661639157319968, 0], [0, 0, 5.4661639157319968]])
+    frac = np.array([[.875, .875, .875], [.875, .375, .375], [.125, .125, .125]])
+    new = str(tmp_path / "POSCAR")
+    with open(new, "w") as f:
+        f.write(" Si O\n   1.5\n" + "".join("  %.16f %.16f %.16f\n" % tuple(r) for r in cell) + "   Si O\n   2 1\nDirect\n")
+        f.write("".join("  %.16f  %.16f  %.16f\n" % tuple(r) for r in frac))
+    st = iofile.read_from_file_structure_poscar(new, masses={"Si": 28.0855, "O": 15.9994})
+    assert np.array_equal(st.get_cell(), cell * 1.5)
+    assert np.array_equal(st.get_positions(), np.dot(frac, cell * 1.5))
+    assert list(st.get_masses()) == [28.0855, 28.0855, 15.9994] and st.get_atomic_elements() == ["Si", "Si", "O"]
+    old = str(tmp_path / "POSCAR_old")                                   # old style: elements on the title line, Cartesian
+    with open(old, "w") as f:
+        f.write(" Si O\n   1.0\n" + "".join("  %.16f %.16f %.16f\n" % tuple(r) for r in cell) + "   2 1\nCartesian\n")
+        f.write("".join("  %.16f  %.16f  %.16f\n" % tuple(r) for r in frac @ cell))
+    st2 = iofile.read_from_file_structure_poscar(old, masses=[28.0855, 28.0855, 15.9994])
+    assert np.array_equal(st2.get_positions(), np.array([[float("%.16f" % v) for v in r] for r in frac @ cell]))
+    assert st2.get_atomic_elements() == ["Si", "Si", "O"]
+    with pytest.raises(SystemExit):
+        iofile.read_from_file_structure_poscar(str(tmp_path / "nope"), masses={})
+    with pytest.raises(ValueError, match="masses"):
+        iofile.read_from_file_structure_poscar(new)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/unittest/Si_data/POSCAR"), reason="reference data not mounted")
+def test_poscar_reader_matches_reference_structure():
+    from dynaphopy_b200 import iofile
+    g = golden("reading_test")
+    st = iofile.read_from_file_structure_poscar("/root/reference/unittest/Si_data/POSCAR", masses={"Si": 28.0855})
+    assert np.array_equal(st.get_cell(), g["unit_cell"]) and np.array_equal(st.get_positions(), g["unit_pos"])
+    assert np.array_equal(st.get_masses(), g["unit_masses"])
+    st.set_primitive_matrix(g["prim_matrix"])
+    assert np.array_equal(st.get_atom_type_index(), g["unit_atom_type"])
