@@ -443,3 +443,31 @@ def test_poscar_reader_matches_reference_structure():
     assert np.array_equal(st.get_masses(), g["unit_masses"])
     st.set_primitive_matrix(g["prim_matrix"])
     assert np.array_equal(st.get_atom_type_index(), g["unit_atom_type"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/unittest/Si_data"), reason="reference data not mounted")
+@pytest.mark.parametrize("fname,dt,tag", [("XDATCAR", 0.0005, "xdatcar"), ("si.lammpstrj", 0.001, "lammps")])
+def test_reading_test_of_the_reference_line_by_line(kops, fname, dt, tag):
+    """unittest/reading_test.py:11-102 rewritten against this package with the same calls in the same order:
+    structure from POSCAR, parser picked by keyword, atom-order template, trajectory with the same cuts, and the
+    reference's own assertions (time step, mean displacement matrix literals; the rel_traj literals are compared with
+    what the reference itself computed, they are differences of O(10) numbers at the 1e-9 level)."""
+    from dynaphopy_b200 import iofile as io
+    data = "/root/reference/unittest/Si_data/"
+    structure = io.read_from_file_structure_poscar(data + "POSCAR", masses={"Si": 28.0855})
+    structure.set_primitive_matrix([[0.0, 0.5, 0.5], [0.5, 0.0, 0.5], [0.5, 0.5, 0.0]])
+    parser = io.get_trajectory_parser(data + fname)
+    kw = dict(pinned=False, ops=kops)
+    if tag == "xdatcar":
+        template = io.check_atoms_order(data + fname, lambda *a, **k: parser(*a, pinned=False, **k), structure)
+        trajectory = parser(data + fname, structure, initial_cut=3, end_cut=14, time_step=dt, template=template, **kw)
+    else:
+        trajectory = parser(data + fname, structure, initial_cut=3, end_cut=14, time_step=dt, **kw)
+    g = golden("reading_test")
+    rel_traj = np.array([np.average(trajectory.average_positions().real - traj, axis=0).real
+                         for traj in np.asarray(trajectory.trajectory)])
+    assert np.abs(rel_traj - g[tag + "_rel_traj"]).max() < 1e-13
+    assert float(trajectory.get_time_step_average()) == float(dt)
+    mean_matrix = np.average(trajectory.get_mean_displacement_matrix(), axis=0)
+    assert np.allclose(mean_matrix, g[tag + "_mean_matrix_literal"], rtol=1e-3, atol=1.e-6)
+    assert np.allclose(mean_matrix, g[tag + "_mean_matrix"], rtol=1e-12, atol=0)
