@@ -16,6 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdynaphopy_b200.so")
 EMUL_DIR = os.path.join(ROOT, "tests", "_emul_build")
 EMUL_LIB = os.path.join(EMUL_DIR, "libdp_emul.so")
+OBJ_DIR = os.path.join(HERE, "_build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -44,19 +45,39 @@ def nvcc_path():
     return None
 
 
-def build_cuda(force=False, verbose=False):
-    """Compile every .cu for sm_100a into one shared library.  Returns the library path."""
-    if not force and not _stale(LIB):
+def build_cuda(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every .cu for sm_100a (one object per source, in parallel; objects are cached under
+    ``dynaphopy_b200/_build`` keyed on the flags) and link them into one shared library.  Returns the library path.
+    ``extra_flags`` / ``out``: alternative builds of the same library for experiments (``DYNAPHOPY_B200_LIB``)."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    out = LIB if out is None else out
+    if not force and not extra_flags and out == LIB and not _stale(LIB):
         return LIB
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libdynaphopy_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", LIB]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
-    return LIB
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
+    tag = hashlib.sha1(" ".join(flags).encode()).hexdigest()[:10]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [d for d in _deps() if not d.endswith(".cu")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, "%s.%s.o" % (os.path.basename(src)[:-3], tag))
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            subprocess.check_call(cmd, env=env)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, _sources()))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + objs + ["-o", out],
+                          env=env)
+    return out
 
 
 def build_emulator(force=False):

@@ -89,7 +89,8 @@ class MeshPipeline:
     """All q of a mesh at once, optionally time-sharded over the ranks of a torch.distributed group."""
 
     def __init__(self, plan, eigenvectors, frequency_range, dt, ops=None, group=None, algorithm=2,
-                 mem_coefficients=1000, correlation_step=10, integration_method=1, correlation_weight=0):
+                 mem_coefficients=1000, correlation_step=10, integration_method=1, correlation_weight=0,
+                 project_on_atom=-1):
         self.ops = ops if ops is not None else _ops.default_ops()
         self.plan = plan
         self.be = self.ops.be
@@ -100,6 +101,9 @@ class MeshPipeline:
         self.correlation_step = correlation_step
         self.integration_method = integration_method
         self.correlation_weight = correlation_weight
+        # projection.py:26-28, 38-39: only the atoms of this primitive type contribute, normalisation unchanged
+        # (what the reference's q loop gets through get_vc(project_on_atom=parameters.project_on_atom))
+        self.project_on_atom = int(project_on_atom)
         self.Q = plan.q_cart.shape[0]
         self.M = 3 * plan.n_prim
         self.group = group
@@ -116,7 +120,8 @@ class MeshPipeline:
         self.d_eig = self.be.asarray(eigenvectors, np.complex128).reshape(self.Q, self.M, self.M)
         # fused path: the projection writes the bare lattice DFT of every unit atom and the twiddle
         # (N/n_p)^-1/2 sqrt(m_u) exp(-i q.tau_u) rides on the eigenvectors: e'[q,s,u,k] = e[q,s,u,k] conj(tw[q,u])
-        self.fold_twiddle = plan.n_unit == plan.n_prim and bool(np.all(plan.unit_type == np.arange(plan.n_unit)))
+        self.fold_twiddle = plan.n_unit == plan.n_prim and bool(np.all(plan.unit_type == np.arange(plan.n_unit))) \
+            and self.project_on_atom < 0
         if self.fold_twiddle:
             e = np.asarray(self.be.asarray(eigenvectors, np.complex128).cpu() if hasattr(self.d_eig, "cpu")
                            else eigenvectors, dtype=np.complex128).reshape(self.Q, self.M, plan.n_prim, 3)
@@ -127,7 +132,7 @@ class MeshPipeline:
     def project(self, velocity):
         """Local frames (Tl, N, 3) real -> vc (Tl, Q, n_p, 3)."""
         return self.ops.project_commensurate(velocity, self.plan.dims, self.plan.unit_type, self.plan.n_prim,
-                                             self.d_qbin, self.d_tw)
+                                             self.d_qbin, self.d_tw, self.project_on_atom)
 
     def contract(self, vc):
         """vc -> vq; single rank: in place, (Tl, Q*M) time-major.  Multi rank: send layout

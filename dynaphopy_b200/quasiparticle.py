@@ -202,26 +202,69 @@ class Quasiparticle:
             self._power_spectrum_wave_vector = self._spectrum(vc.swapaxes(1, 2).reshape(-1, size))
         return np.nansum(self._power_spectrum_wave_vector, axis=1)
 
+    def _velocity_mass_average(self):
+        """(T, N, 3) mass-weighted velocities: the device tensor when the Dynamics mirror has one (no host round
+        trip), else the reference-typed numpy array."""
+        if hasattr(self.dynamic, "velocity_mass_average_device"):
+            return self.dynamic.velocity_mass_average_device()
+        return self.dynamic.get_velocity_mass_average()
+
     def get_power_spectrum_full(self, projection_on_coordinate=-1):          # :781-831
+        """All-atom power spectrum, branch for branch like the reference: ``parameters.project_on_atom >= 0`` keeps
+        the atoms of that primitive type ('Atom type ... does not exist' -> exit), and only then is
+        ``projection_on_coordinate`` honoured (>= number of dimensions -> exit); ``parameters.silent`` accumulates
+        the columns one by one in (atom, coordinate) order, otherwise the (F, columns) array of the
+        coordinate-major layout ``vm.swapaxes(1, 2).reshape(-1, size)`` is summed over its columns.  Either way the
+        spectra of ALL columns come from one launch.  Cached until ``power_spectra_clear`` whatever the arguments,
+        as in the reference."""
+        number_of_dimensions = self.dynamic.structure.get_number_of_dimensions()
+        projected_atom_type = self.parameters.project_on_atom
         if self._power_spectrum_direct is None:
-            print("Calculating full power spectrum")
-            vm = self.dynamic.velocity_mass_average_device() if hasattr(self.dynamic, "velocity_mass_average_device") \
-                else self.dynamic.get_velocity_mass_average()
-            n = vm.shape[1]
-            if projection_on_coordinate == -1:
-                cols = vm.swapaxes(1, 2).reshape(-1, n * vm.shape[2]) if isinstance(vm, np.ndarray) \
-                    else vm.transpose(1, 2).reshape(-1, n * vm.shape[2])
-            else:
-                cols = vm[:, :, projection_on_coordinate]
-            self._power_spectrum_direct = np.sum(self._spectrum(cols), axis=1)
+            print("Calculation full power spectrum")
+            vm = self._velocity_mass_average()
+            if projected_atom_type >= 0:
+                print('Power spectrum projected onto atom type {0}'.format(projected_atom_type))
+                supercell = self.dynamic.get_supercell_matrix()
+                atom_types = np.array(self.dynamic.structure.get_atom_type_index(supercell=supercell))
+                atom_indices = np.argwhere(atom_types == projected_atom_type).flatten()
+                if len(atom_indices) == 0:
+                    print('Atom type {0} does not exist'.format(projected_atom_type))
+                    raise SystemExit
+                # Only works if project on atom is requested! (reference comment, :803)
+                if projection_on_coordinate >= number_of_dimensions:
+                    print('Projected coordinate should be smaller than {}'.format(number_of_dimensions))
+                    raise SystemExit
+                idx = atom_indices if isinstance(vm, np.ndarray) else \
+                    self.dynamic.ops.be.asarray(atom_indices, np.int32).long()
+                if projection_on_coordinate > -1:
+                    print('Power spectrum projected onto coordinate {}'.format(projection_on_coordinate))
+                    vm = vm[:, idx, projection_on_coordinate][:, :, None]
+                else:
+                    vm = vm[:, idx]
+            n_atoms, n_coord = vm.shape[1], vm.shape[2]
+            size = n_atoms * n_coord
+            cols = vm.swapaxes(1, 2).reshape(-1, size) if isinstance(vm, np.ndarray) \
+                else vm.transpose(1, 2).reshape(-1, size)
+            ps = self._spectrum(cols)                                        # (F, size), column j * n_atoms + i
+            if self.parameters.silent:
+                # "Memory efficient algorithm" of the reference (:812-821): same columns, accumulated one at a time
+                acc = np.zeros_like(np.asarray(self.parameters.frequency_range, dtype=float)[None].T)
+                for i in range(n_atoms):
+                    for j in range(n_coord):
+                        acc += ps[:, j * n_atoms + i][None].T
+                ps = acc
+            self._power_spectrum_direct = np.sum(ps, axis=1)
         return self._power_spectrum_direct
 
-    def get_power_spectrum_partials(self):                                   # :833-854
+    def get_power_spectrum_partials(self, save_to_file=None):                # :833-854
         if self._power_spectrum_partials is None:
-            vm = self.dynamic.velocity_mass_average_device() if hasattr(self.dynamic, "velocity_mass_average_device") \
-                else self.dynamic.get_velocity_mass_average()
-            parts = [self._spectrum(vm[:, :, k]) for k in range(vm.shape[2])]
-            self._power_spectrum_partials = np.sum(parts, axis=0)
+            print("Calculation power spectrum partials")
+            vm = self._velocity_mass_average()
+            self._power_spectrum_partials = self._spectrum(vm[:, :, 0])
+            for i in [1, 2]:
+                self._power_spectrum_partials += self._spectrum(vm[:, :, i])
+        if save_to_file is not None:
+            np.savetxt(save_to_file, np.hstack([self.get_frequency_range()[None].T, self._power_spectrum_partials]))
         return self._power_spectrum_partials
 
     # -- whole commensurate mesh in one pass (the q loop of get_commensurate_points_data, :1130-1174) --------
@@ -267,7 +310,8 @@ class Quasiparticle:
                                      correlation_step=self.parameters.correlation_function_step,
                                      integration_method=self.parameters.integration_method,
                                      correlation_weight=1 if getattr(self.parameters, "correlation_weight",
-                                                                     "reference") == "intended" else 0)
+                                                                     "reference") == "intended" else 0,
+                                     project_on_atom=self.parameters.project_on_atom)
         ps = pipe.run(dyn.velocity_device)                                  # (F, Q*M) on the device
         sets_q, sets_flat = [], None
         if use_degeneracy:

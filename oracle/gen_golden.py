@@ -98,8 +98,49 @@ def hotpath_case(name, unit_cell, unit_pos, masses, numbers, prim_matrix, dims, 
                             step=10, integration_method=0) for i in range(vq0.shape[1])]).T
     # wave-vector spectrum input layout (dynaphopy/__init__.py:764): vc.swapaxes(1,2).reshape(-1, 3 n_p)
     out["ps_fft_wave_vector_cols"] = fns[2][0](vcs[1].swapaxes(1, 2).reshape(-1, 3 * n_prim), dyn, p)
+    out.update(_full_and_partial_spectra(dyn, freq, mem_order))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print("wrote", name, {k: np.shape(v) for k, v in out.items() if np.ndim(v) > 1})
+
+
+def _full_and_partial_spectra(dyn, freq, mem_order):
+    """Quasiparticle.get_power_spectrum_full / get_power_spectrum_partials of the reference itself
+    (dynaphopy/__init__.py:781-854) for every branch: all atoms / one atom type / one atom type and one
+    coordinate, the `silent` column-by-column path and the single-call path, FFT and MEM methods."""
+    import dynaphopy
+    pr = dynaphopy.parameters.Parameters()
+    saved = (pr.silent, pr.project_on_atom, pr.power_spectra_algorithm, pr.frequency_range,
+             pr.number_of_coefficients_mem)
+    res = {}
+    try:
+        pr.frequency_range = freq
+        pr.number_of_coefficients_mem = mem_order
+
+        def full(alg, atom, coord, silent):
+            pr.power_spectra_algorithm = alg
+            pr.project_on_atom = atom
+            pr.silent = silent
+            calc = dynaphopy.Quasiparticle(dyn)
+            return np.array(calc.get_power_spectrum_full(projection_on_coordinate=coord))
+
+        res["ps_full_fft"] = full(2, -1, -1, False)
+        res["ps_full_fft_silent"] = full(2, -1, -1, True)
+        res["ps_full_fft_coord1_ignored"] = full(2, -1, 1, False)       # coordinate is honoured only with an atom type
+        res["ps_full_fft_atom0"] = full(2, 0, -1, False)
+        res["ps_full_fft_atom1_silent"] = full(2, 1, -1, True)
+        res["ps_full_fft_atom0_coord1"] = full(2, 0, 1, False)
+        res["ps_full_fft_atom1_coord2_silent"] = full(2, 1, 2, True)
+        res["ps_full_mem"] = full(1, -1, -1, False)
+        res["ps_full_mem_atom0_coord0"] = full(1, 0, 0, False)
+        pr.project_on_atom = -1
+        pr.silent = False
+        for alg, key in ((2, "ps_partials_fft"), (1, "ps_partials_mem")):
+            pr.power_spectra_algorithm = alg
+            res[key] = np.array(dynaphopy.Quasiparticle(dyn).get_power_spectrum_partials())
+    finally:
+        pr.silent, pr.project_on_atom, pr.power_spectra_algorithm, pr.frequency_range, \
+            pr.number_of_coefficients_mem = saved
+    return res
 
 
 def displacement_case(name, seed):

@@ -71,6 +71,62 @@ def test_quasiparticle_path_vs_reference(kops, monkeypatch, name):
     Parameters().reset()
 
 
+@pytest.mark.parametrize("name", ["cubic2_232", "si_conv_222", "cubic2_222_complex"])
+def test_full_and_partial_spectra_vs_reference(kops, monkeypatch, name):
+    """Quasiparticle.get_power_spectrum_full / _partials (dynaphopy/__init__.py:781-854) against what the reference
+    itself returned (oracle/gen_golden.py::_full_and_partial_spectra): all atoms, one atom type, one atom type and
+    one coordinate, `silent` both ways, FFT and MEM methods; plus the reference's exits and its caching."""
+    from dynaphopy_b200.quasiparticle import Quasiparticle
+    from dynaphopy_b200.parameters import Parameters
+    _patch_default_ops(monkeypatch, kops)
+    g = golden(name)
+    pr = Parameters()
+    pr.reset()
+    dyn = _dynamics(g, kops)
+    calc = Quasiparticle(dyn)
+    pr.frequency_range = g["freq"]
+    pr.number_of_coefficients_mem = int(g["mem_order"])
+
+    def full(alg, atom, coord, silent):
+        pr.power_spectra_algorithm = alg
+        pr.project_on_atom = atom
+        pr.silent = silent
+        calc.power_spectra_clear()
+        return calc.get_power_spectrum_full(projection_on_coordinate=coord)
+
+    cases = [("ps_full_fft", 2, -1, -1, False), ("ps_full_fft_silent", 2, -1, -1, True),
+             ("ps_full_fft_coord1_ignored", 2, -1, 1, False), ("ps_full_fft_atom0", 2, 0, -1, False),
+             ("ps_full_fft_atom1_silent", 2, 1, -1, True), ("ps_full_fft_atom0_coord1", 2, 0, 1, False),
+             ("ps_full_fft_atom1_coord2_silent", 2, 1, 2, True), ("ps_full_mem", 1, -1, -1, False),
+             ("ps_full_mem_atom0_coord0", 1, 0, 0, False)]
+    for key, alg, atom, coord, silent in cases:
+        ps = full(alg, atom, coord, silent)
+        assert ps.shape == g[key].shape == (len(g["freq"]),), key
+        assert relerr(ps, g[key]) < TOL, key
+        assert int(np.argmax(ps)) == int(np.argmax(g[key])), key
+    # cached whatever the arguments until power_spectra_clear (the reference's `is None` test, :789)
+    again = calc.get_power_spectrum_full(projection_on_coordinate=2)
+    assert again is calc.get_power_spectrum_full()
+    # the reference's exits: unknown atom type, coordinate >= number of dimensions (only with an atom type)
+    pr.project_on_atom = 5
+    calc.power_spectra_clear()
+    with pytest.raises(SystemExit):
+        calc.get_power_spectrum_full()
+    pr.project_on_atom = 0
+    with pytest.raises(SystemExit):
+        calc.get_power_spectrum_full(projection_on_coordinate=3)
+    pr.project_on_atom = -1
+    pr.silent = False
+    for alg, key in ((2, "ps_partials_fft"), (1, "ps_partials_mem")):
+        pr.power_spectra_algorithm = alg
+        calc.power_spectra_clear()
+        pp = calc.get_power_spectrum_partials()
+        assert pp.shape == g[key].shape
+        assert relerr(pp, g[key]) < TOL, key
+        assert np.array_equal(pp.argmax(0), g[key].argmax(0)), key
+    pr.reset()
+
+
 def test_selector_contract_and_errors(kops, monkeypatch):
     from dynaphopy_b200 import power_spectrum
     from dynaphopy_b200.quasiparticle import Quasiparticle
@@ -157,6 +213,16 @@ def test_commensurate_points_batch_matches_q_loop(kops, monkeypatch):
             assert np.array_equal(data["averaged"][i][:, j], ref)
             assert data["guess_position"][i, j] == g["freq"][np.argmax(ref)]
             assert data["guess_height"][i, j] == np.max(ref)
+    # parameters.project_on_atom reaches the batched projection like it reaches get_vc in the reference's q loop
+    calc.set_projection_onto_atom_type(1)
+    data1 = calc.get_commensurate_points_spectra(eig, frequencies=fr, com_points=com)
+    for i in (0, 5, 11):
+        calc.set_reduced_q_vector(com[i])
+        calc.full_clear()
+        calc.set_eigenvectors(eig[i], frequencies=fr[i])
+        assert relerr(data1["power_spectra"][i], calc.get_power_spectrum_phonon()) < TOL
+    assert relerr(data1["power_spectra"], data["power_spectra"]) > 1e-3
+    Parameters().reset()
 
 
 def test_star_of_q_average_matches_loop(kops, monkeypatch):
