@@ -157,7 +157,7 @@ def cpu_sample(wl, v_sub, eig_sub, q_idx, n_series, frames_total):
     scale_proj = (frames_total / t_sub) * (wl["Q"] / len(q_idx))
     t_full = (t_proj + t_ph) * scale_proj + t_fft * (wl["Q"] * wl["M"] / n_series)
     return {"t_proj_sample_s": t_proj, "t_phonon_sample_s": t_ph, "t_fft_sample_s": t_fft,
-            "t_full_extrapolated_s": t_full, "value": wl["n_atoms"] * frames_total / t_full, "_vq0": vqs[0]}
+            "t_full_extrapolated_s": t_full, "value": wl["n_atoms"] * frames_total / t_full, "_vq": vqs}
 
 
 def run_reference(args):
@@ -169,7 +169,7 @@ def run_reference(args):
     rng = np.random.default_rng(SEED)
     t_sub = args.cpu_frames
     sigma = np.sqrt(KB * TEMP / wl["mass"])[None, :, None]
-    v_sub = rng.normal(size=(t_sub, wl["n_atoms"], 3)) * sigma
+    v_sub = rng.normal(size=(t_sub, wl["n_atoms"], 3)) * sigma             # white noise of the workload's amplitude
     q_idx = [0, 1237, 2560, 5119][: args.cpu_q]
     eig = np.stack([np.linalg.qr(rng.normal(size=(6, 6)) + 1j * rng.normal(size=(6, 6)))[0].T for _ in q_idx])
     times = []
@@ -208,6 +208,32 @@ def config_dict(wl, frames, gpus):
             "sharding": f"time-block x{gpus}" + (" (4096-frame blocks dealt cyclically to the ranks) + one exchange over NVLink "
                                                    "peer memory (copy engines; NCCL all-to-all fallback)" if gpus > 1 else ""),
             "l2_policy": "inputs (32 GB velocities, 64 GB projected series) far exceed the 126 MB L2"}
+
+
+def ncu_traffic_from_profiles(units_now):
+    """stage -> DRAM bytes of this launch, from profiles/ncu_index.json: a list of
+    {"stage", "file", "kernel", "units"} entries (newest last) pointing at tools/ncu_summary.py outputs."""
+    out, src = {}, {}
+    idx_path = os.path.join(ROOT, "profiles", "ncu_index.json")
+    if not os.path.exists(idx_path):
+        return out, src
+    for ent in json.load(open(idx_path)):
+        path = os.path.join(ROOT, "profiles", ent["file"])
+        if ent["stage"] not in units_now or not os.path.exists(path):
+            continue
+        for line in open(path):
+            try:
+                d = json.loads(line)
+            except ValueError:
+                continue
+            if ent["kernel"] in d.get("kernel", "") and "dram_read" in d:
+                def gb(x):
+                    val, unit = x.split()[:2]
+                    return float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[unit]
+                out[ent["stage"]] = (gb(d["dram_read"]) + gb(d["dram_write"])) / ent["units"] * units_now[ent["stage"]]
+                src[ent["stage"]] = "profiles/" + ent["file"]
+                break
+    return out, src
 
 
 def run_ours(args):
@@ -371,6 +397,58 @@ def run_ours(args):
     value = wl["n_atoms"] * frames / (ms_per_step * 1e-3)
     peak_bin = int(torch.argmax(ps[:, 0]).item())
     checksum = float(ps.sum().item())
+    # per-series sums of the spectra, in global series order (rank g owns the series of q block g): the cross-N parity
+    # reference -- every rank count must reproduce the single-GPU values (tests/golden/bench_cfg5a_series_sums.npy)
+    series_sums = ps.sum(dim=0)
+    series_peaks = torch.argmax(ps, dim=0).to(torch.float64)
+    if world > 1:
+        gathered = [torch.empty_like(series_sums) for _ in range(world)]
+        dist.all_gather(gathered, series_sums)
+        series_sums = torch.cat(gathered)
+        gathered = [torch.empty_like(series_peaks) for _ in range(world)]
+        dist.all_gather(gathered, series_peaks)
+        series_peaks = torch.cat(gathered)
+    series_sums = series_sums.cpu().numpy()
+    series_peaks = series_peaks.cpu().numpy().astype(np.int64)
+    parity = {"tolerance": 1e-10}
+    gpath = os.path.join(ROOT, "tests", "golden", "bench_cfg5a_series_sums.npz")
+    if args.write_golden and world == 1 and rank == 0 and frames == 131072:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savez_compressed(os.path.join(ROOT, "gpurun_out", "bench_cfg5a_series_sums.npz"), sums=series_sums, peaks=series_peaks)
+    if os.path.exists(gpath) and frames == 131072:
+        gold = np.load(gpath)
+        parity["cross_n"] = {"reference": "single-GPU run of this bench (tests/golden/bench_cfg5a_series_sums.npz)",
+                             "series": int(series_sums.size),
+                             "max_rel_err_series_sums": float(np.abs(series_sums - gold["sums"]).max() / np.abs(gold["sums"]).max()),
+                             "peak_bin_matches": int((series_peaks == gold["peaks"]).sum())}
+    # oracle parity on a sample of THIS run's data (world == 1: the contracted series are all on this device)
+    if world == 1 and not args.skip_cpu:
+        from oracle import port as _port
+        q_idx_p = [0, 1237, 2560, 5119]
+        tp = 1024
+        vsub_p = gen_chunk_torch(torch, dev, wl, 0, CHUNK)[:tp].cpu().numpy()
+        vm_p = _port.velocity_mass_average(vsub_p.astype(complex), wl["mass"])
+        eig_p = eig[q_idx_p].cpu().numpy()
+        err_vq = 0.0
+        for i, q in enumerate(q_idx_p):
+            vc_ref = _port.project_onto_wave_vector(vm_p, wl["pos"], wl["typ"], wl["n_prim"], wl["q_cart"][q])
+            vq_ref = _port.project_onto_phonon(vc_ref, eig_p[i].reshape(6, 2, 3))
+            vq_dev = send[0, q * wl["M"]:(q + 1) * wl["M"], :tp].t().cpu().numpy()
+            err_vq = max(err_vq, float(np.abs(vq_dev - vq_ref).max() / np.abs(vq_ref).max()))
+        s_idx = [0, 1, 7427, 15360, 15365, 22222, 30718, 30719]
+        ser = send[0, s_idx, :].t().cpu().numpy()                                 # (T, 8) device-contracted series
+        ps_ref = _port.fft_spectra(ser, DT, FREQ, use_fft_correlate=True) if frames >= 20000 else _port.fft_spectra(ser, DT, FREQ)
+        ps_dev = ps[:, s_idx].cpu().numpy()
+        parity["oracle"] = {
+            "vq_max_rel_err": err_vq, "vq_sample": "%d q x %d frames x %d modes vs oracle/port.py projection + contraction" % (len(q_idx_p), tp, wl["M"]),
+            "fft_spectra_max_rel_err": float(np.abs(ps_dev - ps_ref).max() / np.abs(ps_ref).max()),
+            "fft_spectra_sample": "%d series of %d samples vs oracle/port.py (np.correlate restated through FFTs + np.fft + np.interp)" % (len(s_idx), frames),
+            "peak_bin_matches": int((ps_dev.argmax(0) == ps_ref.argmax(0)).sum()), "peak_bin_total": len(s_idx)}
+        parity["ok"] = bool(err_vq < 1e-10 and parity["oracle"]["fft_spectra_max_rel_err"] < 1e-10
+                            and parity["oracle"]["peak_bin_matches"] == len(s_idx))
+    if "cross_n" in parity:
+        ok_n = parity["cross_n"]["max_rel_err_series_sums"] < 1e-10 and parity["cross_n"]["peak_bin_matches"] == parity["cross_n"]["series"]
+        parity["ok"] = bool(parity.get("ok", True) and ok_n)
 
     # ---- the other two spectrum methods of the selector on a bounded sample of the SAME series (not in the timed
     # region; the metric names "mode spectra/s" per algorithm): maximum entropy (m = 1000) and direct correlation
@@ -411,7 +489,7 @@ def run_ours(args):
         e2e_chunk = 2048 if world == 1 else CH                           # N > 1: the receive-buffer geometry of the timed steps
         pipe.run_from_host(vh, chunk_frames=e2e_chunk)                   # warm-up
         barrier()
-        es = max(1, min(args.steps, 2))
+        es = max(1, args.steps)
         t0 = time.perf_counter()
         for _ in range(es):
             ps_host = pipe.run_from_host(vh, chunk_frames=e2e_chunk)
@@ -424,7 +502,14 @@ def run_ours(args):
         e2e = {"value": wl["n_atoms"] * frames / dt_e2e, "unit": "atom*frames/s", "ms_per_step": dt_e2e * 1e3,
                "h2d_bytes_per_step": int(vh.numel() * 8 * world), "d2h_bytes_per_step": int(ps_host.size * 8 * world),
                "api": "dynaphopy_b200.pipeline.MeshPipeline.run_from_host (pinned host trajectory in, numpy spectra out)",
-               "peak_bin_matches_device_run": bool(int(np.argmax(ps_host[:, 0])) == peak_bin)}
+               "steps": es, "peak_bin_matches_device_run": bool(int(np.argmax(ps_host[:, 0])) == peak_bin)}
+        # the host-streamed result against the device-resident run of the timed region: per-series sums, all ranks
+        sums_e2e = torch.as_tensor(ps_host.sum(axis=0), device=dev)
+        if world > 1:
+            gathered = [torch.empty_like(sums_e2e) for _ in range(world)]
+            dist.all_gather(gathered, sums_e2e)
+            sums_e2e = torch.cat(gathered)
+        e2e["max_rel_err_series_sums_vs_device_run"] = float(np.abs(sums_e2e.cpu().numpy() - series_sums).max() / np.abs(series_sums).max())
         del vh
 
     if rank != 0:
@@ -460,11 +545,10 @@ def run_ours(args):
                                         if use_peers else "all_to_all per round (no symmetric memory)")
         stages["overlap"] = {"span_ms": statistics.mean(span_ms) if span_ms else None,
                              "note": "stage times are CUDA-event sums per stream; spectra overlap projection/contraction/exchange"}
-    # DRAM traffic of the dominant kernels from `ncu --set full` captures of smaller launches of the same
-    # kernels (profiles/r01_ncu_*.jsonl), scaled linearly to this launch: bytes per series / per frame
-    ncu_traffic = {"spectra": (1.901760e9 + 1.569485e9) / 296.0 * s_loc,              # 296 series captured
-                   "project": (1.077133e9 + 2.219636e9) / 4096.0 * tl,               # 4096 frames captured
-                   "contract": (2.016264e9 + 1.960431e9) / 4096.0 * tl}
+    # DRAM traffic of the dominant kernels: dram__bytes_read.sum + dram__bytes_write.sum of the newest `ncu --set full`
+    # capture of each kernel listed in profiles/ncu_index.json (smaller launches of the same kernels: bytes per series /
+    # per frame, scaled linearly to this launch)
+    ncu_traffic, ncu_src = ncu_traffic_from_profiles({"spectra": s_loc, "project": tl, "contract": tl})
     # fp64 view of the spectrum stage: 770.5 k warp-level fp64 instructions per series (7 windows, processed as
     # 3 pairs + 1 single; ncu instruction mix, profiles/r01_ncu_spectrum2.jsonl) against the measured
     # 64 lanes/clk/SM (tools/micro/fp64_rate.cu: 18.3 T lane-ops/s)
@@ -474,9 +558,9 @@ def run_ours(args):
     fp64["frac"] = fp64["achieved_Tops"] / fp64["peak_Tops"]
     dom = max(("project", "contract", "spectra"), key=lambda k: mean[k])
     roofline = {"kernel": kernels[dom], "bound": "hbm", "achieved": stages[dom]["achieved_GBps"], "peak": hbm,
-                "unit": "GB/s", "frac": stages[dom]["frac_of_hbm"], "traffic": ncu_traffic[dom],
+                "unit": "GB/s", "frac": stages[dom]["frac_of_hbm"], "traffic": ncu_traffic.get(dom),
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture of a smaller launch "
-                                "(profiles/r01_ncu_*.jsonl), scaled linearly to this launch", "algorithmic_bytes": bytes_stage[dom],
+                                "(%s), scaled linearly to this launch" % ncu_src.get(dom), "algorithmic_bytes": bytes_stage[dom],
                 "fp64": fp64 if dom == "spectra" else None, "peak_source": peak_src,
                 "share_of_step": mean[dom] / max(sum(mean.values()), 1e-9),
                 "note": "algorithmic bytes per launch / CUDA-event duration of the stage on rank 0; "
@@ -486,7 +570,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(wl, frames, world),
             "mode_spectra_per_s": wl["Q"] * wl["M"] / (ms_per_step * 1e-3),
-            "stages": stages, "spectra_methods": methods, "roofline": roofline, "gpu_launches": int(launches),
+            "stages": stages, "spectra_methods": methods, "roofline": roofline, "gpu_launches": int(launches), "parity": parity,
             "result_check": {"peak_bin_series0": peak_bin, "peak_freq_THz": float(FREQ[peak_bin]), "checksum": checksum}}
     if e2e:
         line["e2e"] = e2e
@@ -495,7 +579,8 @@ def run_ours(args):
         sampler.stop()
     if world == 1 and not args.skip_cpu:
         from oracle import port  # noqa: F401  (cpu_baseline leg: the oracle as the CPU baseline)
-        vsub = gen_chunk_torch(torch, dev, wl, 0, CHUNK)[: args.cpu_frames].cpu().numpy()
+        vsub = np.concatenate([gen_chunk_torch(torch, dev, wl, t0, t0 + CHUNK).cpu().numpy()
+                               for t0 in range(0, args.cpu_frames, CHUNK)])[: args.cpu_frames]
         q_idx = [0, 1237, 2560, 5119][: args.cpu_q]
         eig_sub = eig[q_idx].cpu().numpy()
         res = cpu_sample(wl, vsub, eig_sub, q_idx, args.cpu_series, frames)
@@ -525,7 +610,10 @@ def main():
     ap.add_argument("--sharding", default="auto", choices=["auto", "cyclic", "blocks"],
                     help="N > 1: chunk-cyclic time sharding with overlapped spectra (default) or one time block per rank")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=1024)  # <= 1024 (one generator chunk)
+    ap.add_argument("--cpu-frames", type=int, default=4096, help="frames of the CPU projection sample (BASELINE.md section 3: 4096)")
+    ap.add_argument("--write-golden", action="store_true",
+                    help="N = 1: write the per-series spectrum sums of this run to gpurun_out/ (committed under tests/golden/ "
+                         "as the cross-N parity reference of the multi-GPU runs)")
     ap.add_argument("--cpu-q", type=int, default=4)
     ap.add_argument("--cpu-series", type=int, default=8)
     args = ap.parse_args()

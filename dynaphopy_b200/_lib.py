@@ -54,6 +54,7 @@ SIGNATURES = {
     "dp_fft_c2c": (_I, [_P, _P, _I, _I, _I, _P, _Z, _P]),
 }
 
+DP_ERR_INVALID = -1
 DP_VC_ROWS = 0
 DP_VC_PAIRS = 1
 DP_CORR_WEIGHT_REFERENCE = 0

@@ -8,6 +8,7 @@
 #endif
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -95,5 +96,18 @@ __device__ __forceinline__ double warp_sum(double v) {
 int sm_count();
 // small host array -> device through kernel parameters (never blocks the host; see dp_core.cu)
 int upload_small(void* dst, const void* src, size_t bytes, cudaStream_t st);
+// host table of any size -> device without blocking the host when it is small (<= 64 KB: kernel parameters); larger
+// tables fall back to one pageable cudaMemcpyAsync (staged before it returns, may wait for earlier work of the stream)
+int upload_table(void* dst, const void* src, size_t bytes, cudaStream_t st);
+// Development knobs (skip masks, forced engines, grid overrides) read the environment only in -DDP_DEVELOP builds:
+// a stray variable can never change what the shipped library computes.
+inline const char* dev_env(const char* name) {
+#ifdef DP_DEVELOP
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 }  // namespace dp

@@ -64,6 +64,13 @@ int upload_small(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     return DP_OK;
 }
 
+int upload_table(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return DP_OK;
+    if (bytes <= 64 * 1024 && bytes % 4 == 0 && ((size_t)dst & 3) == 0) return upload_small(dst, src, bytes, st);
+    DP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    return DP_OK;
+}
+
 }  // namespace dp
 
 extern "C" {

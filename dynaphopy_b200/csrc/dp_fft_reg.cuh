@@ -42,7 +42,78 @@ template <int R1_, int R2_, int TG_> struct SubCfg {
 
 constexpr int SUBFFT_EWARP_MAX = 640;     // >= EWARP of every configuration instantiated below
 
+// ---- lean in-place power-of-two codelets ---------------------------------------------------------------
+// The generic PencilDft codelets are out of place (input + sub-transforms + output live at once: 3N complex
+// values); for the 16-point butterflies of the spectrum engine that costs spills at 255 registers.  These work in
+// place on the N values plus two temporaries; the digit-reversed result order is undone by a compile-time
+// renaming of the registers (no instructions).
+__device__ __forceinline__ void r4_inplace(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {      // forward: w_4 = -i
+    const cplx t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    const cplx t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2);
+    a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+__device__ __forceinline__ cplx mul_w8_1(cplx a) {      // a * exp(-i pi/4) = ((x + y) + i (y - x)) / sqrt(2)
+    constexpr double h = 0.70710678118654752440;
+    return make_double2((a.x + a.y) * h, (a.y - a.x) * h);
+}
+__device__ __forceinline__ cplx mul_w8_3(cplx a) {      // a * exp(-3 i pi/4) = ((y - x) - i (x + y)) / sqrt(2)
+    constexpr double h = 0.70710678118654752440;
+    return make_double2((a.y - a.x) * h, -(a.x + a.y) * h);
+}
+__device__ __forceinline__ void dft8_lean(cplx* v) {
+    // 8 = 2 x 4 (DIT): DFT4 of the even and of the odd samples, twiddle w_8^k, radix-2
+    r4_inplace(v[0], v[2], v[4], v[6]);
+    r4_inplace(v[1], v[3], v[5], v[7]);
+    // position 2k holds E[k], position 2k+1 holds O[k]
+    v[3] = mul_w8_1(v[3]);
+    v[5] = cmul_mi(v[5]);
+    v[7] = mul_w8_3(v[7]);
+    cplx t;
+    t = v[0]; v[0] = cadd(t, v[1]); v[1] = csub(t, v[1]);      // X0, X4
+    t = v[2]; v[2] = cadd(t, v[3]); v[3] = csub(t, v[3]);      // X1, X5
+    t = v[4]; v[4] = cadd(t, v[5]); v[5] = csub(t, v[5]);      // X2, X6
+    t = v[6]; v[6] = cadd(t, v[7]); v[7] = csub(t, v[7]);      // X3, X7
+    // rename: position 2k -> X[k], position 2k+1 -> X[k+4]
+    const cplx x1 = v[2], x2 = v[4], x3 = v[6], x4 = v[1], x5 = v[3], x6 = v[5];
+    v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6;
+}
+__device__ __forceinline__ void dft16_lean(cplx* v) {
+    // 16 = 4 x 4 (DIT): S_r = DFT4(v[r], v[r+4], v[r+8], v[r+12]) in place (position r + 4k holds S_r[k])
+    constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;     // cos, sin (pi/8)
+#pragma unroll
+    for (int r = 0; r < 4; r++) r4_inplace(v[r], v[r + 4], v[r + 8], v[r + 12]);
+    // twiddles w_16^(r k)
+    v[5] = cmul(v[5], make_double2(c1, -s1));       // r=1 k=1
+    v[9] = mul_w8_1(v[9]);                          // r=1 k=2: w16^2
+    v[13] = cmul(v[13], make_double2(s1, -c1));     // r=1 k=3: w16^3
+    v[6] = mul_w8_1(v[6]);                          // r=2 k=1: w16^2
+    v[10] = cmul_mi(v[10]);                         // r=2 k=2: w16^4
+    v[14] = mul_w8_3(v[14]);                        // r=2 k=3: w16^6
+    v[7] = cmul(v[7], make_double2(s1, -c1));       // r=3 k=1: w16^3
+    v[11] = mul_w8_3(v[11]);                        // r=3 k=2: w16^6
+    v[15] = cmul(v[15], make_double2(-c1, s1));     // r=3 k=3: w16^9
+    // X[k + 4u] = sum_r w_4^(r u) (twiddled S_r[k]): radix-4 across r on positions 4k + r, result u at 4k + u
+#pragma unroll
+    for (int k = 0; k < 4; k++) r4_inplace(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    // rename (transpose of the 4 x 4 index grid): position 4k + u -> X[k + 4u]
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int u = k + 1; u < 4; u++) {
+            const cplx t = v[4 * k + u];
+            v[4 * k + u] = v[4 * u + k];
+            v[4 * u + k] = t;
+        }
+}
+
 template <int R> __device__ __forceinline__ void dft_inplace(cplx* v) {
+#ifndef DP_NO_LEAN_CODELETS
+    if constexpr (R == 16) { dft16_lean(v); return; }
+    else if constexpr (R == 8) { dft8_lean(v); return; }
+    else if constexpr (R == 4) { r4_inplace(v[0], v[1], v[2], v[3]); return; }
+    else
+#endif
     if constexpr (R > 1) {
         cplx o[R];
         PencilDft<R>::run(v, o);

@@ -289,12 +289,12 @@ int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt
     int* d_list = (int*)ws;               ws += dp::align_up((size_t)N * sizeof(int), 256);
     int* d_off = (int*)ws;                ws += dp::align_up(1024 * sizeof(int), 256);
     dp::cplx* d_ph = (dp::cplx*)ws;
-    DP_CUDA_OK(cudaMemcpyAsync(d_q, q_cart, (size_t)Q * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(d_list, list.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(d_off, off.data(), (size_t)(n_prim + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-#ifndef DP_EMUL
-    DP_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope below
-#endif
+    // small tables travel as kernel parameters (no host synchronisation); tables above 64 KB use one pageable
+    // cudaMemcpyAsync, which is staged before it returns
+    int rc;
+    if ((rc = dp::upload_table(d_q, q_cart, (size_t)Q * 3 * sizeof(double), st))) return rc;
+    if ((rc = dp::upload_table(d_list, list.data(), (size_t)N * sizeof(int), st))) return rc;
+    if ((rc = dp::upload_table(d_off, off.data(), (size_t)(n_prim + 1) * sizeof(int), st))) return rc;
     double norm = 1.0 / sqrt((double)N / (double)n_prim);
     {
         int64_t total = (int64_t)Q * N;

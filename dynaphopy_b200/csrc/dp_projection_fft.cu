@@ -102,12 +102,14 @@ struct PfParams {
 
 __global__ void __launch_bounds__(256)
 qoffset_kernel(const int* __restrict__ qbin, int Q, int Nx, int Ny, int Nz, int Px, int2* __restrict__ qoff,
-               int* __restrict__ bad) {
+               int* __restrict__ /*unused*/) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x) {
         int mx = qbin[q * 3], my = qbin[q * 3 + 1], mz = qbin[q * 3 + 2];
-        if (mx < 0 || mx >= Nx || my < 0 || my >= Ny || mz < 0 || mz >= Nz) { atomicAdd(bad, 1); mx = my = mz = 0; }
+        const bool ok = !(mx < 0 || mx >= Nx || my < 0 || my >= Ny || mz < 0 || mz >= Nz);
+        if (!ok) mx = my = mz = 0;
         int nx = (Nx - mx) % Nx, ny = (Ny - my) % Ny, nz = (Nz - mz) % Nz;
-        qoff[q] = make_int2((mz * Ny + my) * Px + mx, (nz * Ny + ny) * Px + nx);
+        // a bin outside the grid: both offsets point at the poison element W[npad] (NaN), see project_fft_kernel
+        qoff[q] = ok ? make_int2((mz * Ny + my) * Px + mx, (nz * Ny + ny) * Px + nx) : make_int2(-1, -1);
     }
 }
 
@@ -147,7 +149,7 @@ __device__ __noinline__ void pf_load(const PfUnit& u, int Nc, int Nx, int Px, in
 template <bool ACC, bool TW>
 __device__ __noinline__ void pf_epilogue(const PfUnit& u, int npad, int Q, int n_unit, int tid, int nthreads) {
     DP_DYNSMEM(cplx, W);
-    const unsigned* __restrict__ qo = reinterpret_cast<const unsigned*>(W + npad);   // packed bin offsets (m, -m)
+    const unsigned* __restrict__ qo = reinterpret_cast<const unsigned*>(W + npad + 1);   // packed bin offsets (m, -m)
     const bool hasA = u.hasA, hasB = u.hasB;
     const cplx* __restrict__ twA = u.twA;
     const cplx* __restrict__ twB = u.twB;
@@ -230,13 +232,15 @@ project_fft_kernel(const __grid_constant__ PfParams p) {
     DP_DYNSMEM(cplx, W);
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz, Px = p.Px, Nc = p.Nc, Q = p.Q, n_unit = p.n_unit;
-    // shared memory: transform [npad] | packed bin offsets [Q] | jobs | terms  (staged once per CTA)
-    unsigned* qo = reinterpret_cast<unsigned*>(W + p.npad);
+    // shared memory: transform [npad] | poison element (NaN: the "bin" of a q outside the grid) | packed bin
+    // offsets [Q] | jobs | terms  (staged once per CTA)
+    unsigned* qo = reinterpret_cast<unsigned*>(W + p.npad + 1);
+    if (tid == 0) W[p.npad] = make_double2(nan(""), nan(""));
     PfJob* sjobs = reinterpret_cast<PfJob*>(qo + ((Q + 3) & ~3));
     PfTerm* sterms = reinterpret_cast<PfTerm*>(sjobs + p.njobs);
     for (int q = tid; q < Q; q += nthreads) {
         const int2 o = p.qoff[q];
-        qo[q] = (unsigned)o.x | ((unsigned)o.y << 16);
+        qo[q] = o.x < 0 ? ((unsigned)p.npad | ((unsigned)p.npad << 16)) : ((unsigned)o.x | ((unsigned)o.y << 16));
     }
     for (int i = tid; i < p.njobs; i += nthreads) sjobs[i] = p.jobs[i];
     for (int i = tid; i < p.nterms; i += nthreads) sterms[i] = p.terms[i];
@@ -306,7 +310,7 @@ static PfLayout pf_layout(int n_unit, int n_prim, int Q) {
 
 static int pick_threads(int Nx, int Ny, int Nz, int Q, int max_threads) {
     // every pass should keep at least 8 warps busy and waste few thread slots in its last round
-    const char* env = getenv("DP_PF_THREADS");
+    const char* env = dev_env("DP_PF_THREADS");
     if (env && atoi(env) >= 32 && atoi(env) <= max_threads) return atoi(env) / 32 * 32;
     int best = 256;
     double best_cost = -1;
@@ -357,7 +361,7 @@ int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, con
     const int Px = (Nx % 2 == 0) ? Nx + 1 : Nx;
     const int64_t Nc64 = (int64_t)Nx * Ny * Nz;
     const size_t smem_w = (size_t)Nz * Ny * Px * sizeof(dp::cplx);
-    const size_t smem = smem_w + dp::align_up((size_t)Q * sizeof(unsigned), 16) +
+    const size_t smem = smem_w + sizeof(dp::cplx) + dp::align_up((size_t)Q * sizeof(unsigned), 16) +
                         (size_t)(2 * n_prim + 2) * sizeof(dp::PfJob) + (size_t)(3 * n_unit + 4) * sizeof(dp::PfTerm);
     DP_REQUIRE((int64_t)Nz * Ny * Px <= 65535, DP_ERR_UNSUPPORTED,
                "dp_project_commensurate: %lld cells exceed the 16-bit bin offsets (use dp_project_wave_vector)", (long long)Nc64);
@@ -420,24 +424,23 @@ int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, con
     dp::PfTerm* d_terms = (dp::PfTerm*)(ws + lay.off_terms);
     int2* d_qoff = (int2*)(ws + lay.off_qoff);
     int* d_bad = (int*)(ws + lay.off_bad);
-    DP_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(dp::PfJob), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(d_terms, terms.data(), terms.size() * sizeof(dp::PfTerm), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    // job tables travel as kernel parameters and the q-bin check stays on the device: this entry point never blocks
+    // the host.  A bin outside the supercell grid poisons the output of that q with NaN (see the header).
+    int rc = dp::upload_table(d_jobs, jobs.data(), jobs.size() * sizeof(dp::PfJob), st);
+    if (rc) return rc;
+    rc = dp::upload_table(d_terms, terms.data(), terms.size() * sizeof(dp::PfTerm), st);
+    if (rc) return rc;
     {
         auto k = dp::qoffset_kernel;
         DP_LAUNCH(k, dim3((unsigned)dp::imin((Q + 255) / 256, 1024)), dim3(256), 0, st, qbin, Q, Nx, Ny, Nz, Px, d_qoff, d_bad);
         DP_CUDA_OK(cudaGetLastError());
     }
-    int bad = 0;
-    DP_CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DP_CUDA_OK(cudaStreamSynchronize(st));      // also keeps the host job vectors alive long enough
-    DP_REQUIRE(bad == 0, DP_ERR_INVALID, "dp_project_commensurate: %d q bins outside the supercell grid", bad);
 
     dp::PfParams p;
     p.v = v; p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Px = Px; p.Nc = Nc; p.N = n_unit * Nc;
     p.n_unit = n_unit; p.n_prim = n_prim; p.Q = Q; p.njobs = (int)jobs.size(); p.nterms = (int)terms.size();
     p.npad = Nz * Ny * Px; p.T = T; p.pair_major = (vc_layout == DP_VC_PAIRS);
-    p.skip = getenv("DP_PF_SKIP") ? atoi(getenv("DP_PF_SKIP")) : 0;
+    p.skip = dp::dev_env("DP_PF_SKIP") ? atoi(dp::dev_env("DP_PF_SKIP")) : 0;
     p.jobs = d_jobs; p.terms = d_terms; p.qoff = d_qoff; p.tw = (const dp::cplx*)twiddle; p.out = (dp::cplx*)out_vc;
     int per_sm = (int)dp::imin<size_t>(2, dp::imax<size_t>(1, (size_t)(226 * 1024) / (smem + 1024)));
     int threads = dp::pick_threads(Nx, Ny, Nz, Q, per_sm >= 2 ? 320 : 512);
@@ -446,7 +449,7 @@ int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, con
     // DP_RESERVE_SMS: leave some SMs to a concurrently running collective (the chunked all-to-all of the
     // multi-GPU pipeline); a persistent grid that fills every SM would make the NCCL kernel wait or be waited for
     int sms = dp::imax(dp::sm_count(), 1);
-    if (getenv("DP_RESERVE_SMS")) sms = dp::imax(sms - atoi(getenv("DP_RESERVE_SMS")), 1);
+    if (dp::dev_env("DP_RESERVE_SMS")) sms = dp::imax(sms - atoi(dp::dev_env("DP_RESERVE_SMS")), 1);
     int grid = (int)dp::imin<int64_t>(nunits, (int64_t)sms * per_sm);
     if (per_sm >= 2 && threads <= 256) {
         auto k = dp::project_fft_kernel<256, 2>;

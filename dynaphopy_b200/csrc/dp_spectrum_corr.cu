@@ -251,6 +251,10 @@ static CorrLayout corr_layout(int64_t T, int S, int F, int step, int method) {
     return l;
 }
 
+__global__ void __launch_bounds__(256) corr_fill_kernel(double* __restrict__ out, int64_t n, double value) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) out[e] = value;
+}
+
 }  // namespace dp
 
 extern "C" {
@@ -284,12 +288,17 @@ int dp_power_correlation(const double* series, int64_t T, int S, int64_t ld, dou
     const double ndiv = (double)(N / step);               // integer division, c/correlation.c:177
     if (lay.nl_valid == 0) {
         // no lag has any origin: the reference returns 0 * dt / (N div step) (NaN when N < step)
-        std::vector<double> host((size_t)F * S, (0.0 * dt / ndiv) * scale);
-        DP_CUDA_OK(cudaMemcpyAsync(out, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        DP_CUDA_OK(cudaStreamSynchronize(st));
+        auto kf = dp::corr_fill_kernel;
+        const int64_t total = (int64_t)F * S;
+        DP_LAUNCH(kf, dim3((unsigned)dp::imin<int64_t>((total + 255) / 256, 1024)), dim3(256), 0, st, out, total,
+                  (0.0 * dt / ndiv) * scale);
+        DP_CUDA_OK(cudaGetLastError());
         return DP_OK;
     }
-    DP_CUDA_OK(cudaMemcpyAsync(d_freq, freq, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        int rc = dp::upload_table(d_freq, freq, (size_t)F * sizeof(double), st);    // kernel parameters: no host sync
+        if (rc) return rc;
+    }
     {
         auto k = dp::corr_weights_kernel;
         int64_t total = (int64_t)lay.nl_valid * F;

@@ -116,7 +116,7 @@ static int make_spec_plan(int64_t T, double dt, const double* freq, int F, SpecH
     }
     pl->lo = (int)lo;
     pl->nkeep = (int)(hi - lo + 1);
-    const char* force = getenv("DP_SPECTRUM_ENGINE");      // "v1" forces the general engine (validation)
+    const char* force = dev_env("DP_SPECTRUM_ENGINE");      // "v1" forces the general engine (validation)
     pl->use_v2 = !(force && force[0] == 'v' && force[1] == '1') && make_s2_plan(L, pl->nkeep, &pl->s2);
     if (pl->use_v2) { pl->P = pl->s2.P; return DP_OK; }
     if (!make_fft_split(L, &pl->sl)) {
@@ -282,8 +282,8 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
     l.off_spec = o;   o += align_up((size_t)S * pl.starts.size() * pl.nkeep * sizeof(double), 256);
     int64_t items = (int64_t)S * (int64_t)(pl.use_v2 ? (pl.starts.size() + 1) / 2 : pl.starts.size());
     l.nslots = (int)imin<int64_t>(items, (int64_t)imax(sm_count(), 1));
-    if (getenv("DP_S2_GRID") && atoi(getenv("DP_S2_GRID")) > 0)      // development aid: fewer persistent CTAs
-        l.nslots = (int)imin<int64_t>(l.nslots, atoi(getenv("DP_S2_GRID")));
+    if (dev_env("DP_S2_GRID") && atoi(dev_env("DP_S2_GRID")) > 0)      // development aid: fewer persistent CTAs
+        l.nslots = (int)imin<int64_t>(l.nslots, atoi(dev_env("DP_S2_GRID")));
     l.slab_elems = pl.use_v2 ? (size_t)pl.P + (size_t)pl.P / 2 : (size_t)pl.P + pl.L;   // v2: A[P] complex + Sr[P] real
     l.off_scratch = o; o += align_up((size_t)l.nslots * l.slab_elems * sizeof(cplx), 256);
     l.total = o;
@@ -379,8 +379,8 @@ int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_
         p.scratch = (dp::cplx*)(ws + lay.off_scratch); p.slab_elems = lay.slab_elems;
         p.spec = spec; p.lo = pl.lo; p.nkeep = pl.nkeep;
         p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
-        p.skip_mask = getenv("DP_S2_SKIP") ? atoi(getenv("DP_S2_SKIP")) : 0;
-        p.pair = (n_windows >= 2 && !(getenv("DP_S2_PAIR") && atoi(getenv("DP_S2_PAIR")) == 0)) ? 1 : 0;
+        p.skip_mask = dp::dev_env("DP_S2_SKIP") ? atoi(dp::dev_env("DP_S2_SKIP")) : 0;
+        p.pair = (n_windows >= 2 && !(dp::dev_env("DP_S2_PAIR") && atoi(dp::dev_env("DP_S2_PAIR")) == 0)) ? 1 : 0;
         auto k = dp::spectrum2_kernel;
         DP_CUDA_OK(DP_SET_SMEM(k, dp::S2_SMEM_BYTES));
         DP_LAUNCH(k, dim3(grid), dim3(dp::S2_THREADS), dp::S2_SMEM_BYTES, st, p);
@@ -417,13 +417,11 @@ int dp_power_fft_finish(int64_t T, int S, double dt, const double* freq, int F, 
     DP_REQUIRE(workspace_bytes >= lay.total, DP_ERR_WORKSPACE, "dp_power_fft: workspace %zu < %zu", workspace_bytes, lay.total);
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_idx0, pl.idx0.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_mode, pl.mode.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_dx, pl.dx.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_den, pl.den.data(), (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
-#ifndef DP_EMUL
-    DP_CUDA_OK(cudaStreamSynchronize(st));   // plan vectors are host temporaries
-#endif
+    // interpolation plan: small tables as kernel parameters -- no host synchronisation
+    if ((rc = dp::upload_table(ws + lay.off_idx0, pl.idx0.data(), (size_t)F * sizeof(int), st))) return rc;
+    if ((rc = dp::upload_table(ws + lay.off_mode, pl.mode.data(), (size_t)F * sizeof(int), st))) return rc;
+    if ((rc = dp::upload_table(ws + lay.off_dx, pl.dx.data(), (size_t)F * sizeof(double), st))) return rc;
+    if ((rc = dp::upload_table(ws + lay.off_den, pl.den.data(), (size_t)F * sizeof(double), st))) return rc;
     const int npieces = (int)pl.starts.size();
     auto kf = dp::spectrum_finalize_kernel;
     int64_t total = (int64_t)F * S;

@@ -84,6 +84,15 @@ struct S2Smem {
 #ifndef DP_S2_PREFETCH
 #define DP_S2_PREFETCH 0
 #endif
+// Register software pipeline of passes 1-3 (see s2_pass1): next tile's loads issued between the two butterfly stages.
+#ifndef DP_S2_SWP
+#define DP_S2_SWP 0
+#endif
+#ifdef DP_EMUL
+#define DP_LAMBDA_INLINE
+#else
+#define DP_LAMBDA_INLINE __attribute__((always_inline))
+#endif
 constexpr size_t S2_PF_ELEMS = DP_S2_PREFETCH ? (size_t)S2_WARPS * 512 : 0;
 constexpr size_t S2_E_ELEMS = S2_WARPS * SUBFFT_EWARP_MAX > 2 * S2_NP_MAX * S2_CPITCH ? S2_WARPS * SUBFFT_EWARP_MAX
                                                                                   : 2 * S2_NP_MAX * S2_CPITCH;
@@ -199,7 +208,7 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
     const int seq = lane % C::NS, g = lane / C::NS;
     cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
-    auto load_tile = [&](int tile, cplx (&w)[16]) {
+    auto load_tile = [&](int tile, cplx (&w)[16]) DP_LAMBDA_INLINE {
         const int col = tile * C::NS + seq;
 #pragma unroll
         for (int i = 0; i < C::NB1; i++)
@@ -239,8 +248,20 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
     };
     if (warp < ntiles) prefetch_tile(warp);
 #endif
+#if DP_S2_SWP
+    cplx v[16], nx[16];
+    if (warp < ntiles) load_tile(warp, v);
+#endif
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int col = tile * C::NS + seq;
+#if DP_S2_SWP
+        // software pipeline: the next tile's samples are requested as soon as this tile's first butterflies are
+        // parked in the exchange slab, and travel while the second butterflies, twiddles and stores run
+        sub_dit_a<C>(v, E, sm.T1, g);
+        const bool more = tile + S2_WARPS < ntiles;
+        if (more) load_tile(tile + S2_WARPS, nx);
+        sub_dit_b<C>(v, E, g);
+#else
         cplx v[16];
 #if DP_S2_PREFETCH
         s2_cp_wait();
@@ -251,6 +272,7 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
         load_tile(tile, v);
 #endif
         sub_dit<C>(v, E, sm.T1, g);
+#endif
         // four-step twiddle w_P^(col*kk), kk = k1 + R1*k2: geometric in k2
         const cplx ratio = tw2level(sm.fine, sm.coarse, col * C::R1);
 #pragma unroll
@@ -264,6 +286,12 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
             }
         }
         __syncwarp();
+#if DP_S2_SWP
+        if (more) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = nx[r];
+        }
+#endif
     }
 }
 
@@ -280,7 +308,7 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
     const int seq = lane % C::NS, g = lane / C::NS;
     cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int ntiles = n1 / C::NS;
-    auto load_tile = [&](int tile, cplx (&w)[16]) {
+    auto load_tile = [&](int tile, cplx (&w)[16]) DP_LAMBDA_INLINE {
         const cplx* Ar = A + (size_t)(tile * C::NS + seq) * n2;
 #pragma unroll
         for (int i = 0; i < C::NB1; i++)
@@ -299,9 +327,14 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
     };
     if (warp < ntiles) prefetch_tile(warp);
 #endif
+#if DP_S2_SWP
+    cplx v[16], nx[16];
+    if (warp < ntiles) load_tile(warp, v);
+#endif
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int row = tile * C::NS + seq;
         cplx* __restrict__ Ar = A + (size_t)row * n2;
+#if !DP_S2_SWP
         cplx v[16];
 #if DP_S2_PREFETCH
         s2_cp_wait();
@@ -311,6 +344,7 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 #else
         load_tile(tile, v);
 #endif
+#endif
         double sa[16];
         double* __restrict__ Srow = Sr + (size_t)row * n2;
         if (MODE == 2) {                       // |X_a|^2 of the partner window, requested before the butterflies
@@ -319,7 +353,14 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 #pragma unroll
                 for (int k2 = 0; k2 < C::R2; k2++) sa[i * C::R2 + k2] = __ldcg(Srow + g + C::TG * i + C::R1 * k2);
         }
+#if DP_S2_SWP
+        sub_dit_a<C>(v, E, sm.T2, g);
+        const bool more = tile + S2_WARPS < ntiles;
+        if (more) load_tile(tile + S2_WARPS, nx);      // next rows travel underneath the rest of this tile
+        sub_dit_b<C>(v, E, g);
+#else
         sub_dit<C>(v, E, sm.T2, g);
+#endif
         if constexpr (MODE == 1) {
 #pragma unroll
             for (int i = 0; i < C::NB2; i++)
@@ -350,6 +391,12 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
             }
         }
         __syncwarp();
+#if DP_S2_SWP
+        if (more) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = nx[r];
+        }
+#endif
     }
 }
 
@@ -366,7 +413,7 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
     const int seq = lane % C::NS, g = lane / C::NS;
     cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
-    auto load_tile = [&](int tile, cplx (&w)[16]) {
+    auto load_tile = [&](int tile, cplx (&w)[16]) DP_LAMBDA_INLINE {
         const int col = tile * C::NS + seq;
 #pragma unroll
         for (int i = 0; i < C::NB1; i++)
@@ -386,8 +433,18 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
     };
     if (warp < ntiles) prefetch_tile(warp);
 #endif
+#if DP_S2_SWP
+    cplx v[16], nx[16];
+    if (warp < ntiles) load_tile(warp, v);
+#endif
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int col = tile * C::NS + seq;
+#if DP_S2_SWP
+        sub_dit_a<C>(v, E, sm.T1, g);
+        const bool more = tile + S2_WARPS < ntiles;
+        if (more) load_tile(tile + S2_WARPS, nx);      // other columns: independent of this tile's in-place stores
+        sub_dit_b<C>(v, E, g);
+#else
         cplx v[16];
 #if DP_S2_PREFETCH
         s2_cp_wait();
@@ -398,6 +455,7 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
         load_tile(tile, v);
 #endif
         sub_dit<C>(v, E, sm.T1, g);
+#endif
         __syncwarp();          // every lane of the warp has its column in registers before rows are overwritten
 #pragma unroll
         for (int i = 0; i < C::NB2; i++)
@@ -411,6 +469,12 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
                     s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, -v[i * C::R2 + k2].y * sc), pol);
                 }
             }
+#if DP_S2_SWP
+        if (more) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = nx[r];
+        }
+#endif
     }
 }
 

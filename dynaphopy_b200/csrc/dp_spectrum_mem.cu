@@ -394,7 +394,10 @@ int dp_power_mem(const double* series, int64_t T, int S, int64_t ld, double dt, 
     DP_REQUIRE(workspace_bytes >= lay.total, DP_ERR_WORKSPACE, "dp_power_mem: workspace %zu < %zu", workspace_bytes, lay.total);
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    DP_CUDA_OK(cudaMemcpyAsync(ws + lay.off_freq, freq, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        int rc_up = dp::upload_table(ws + lay.off_freq, freq, (size_t)F * sizeof(double), st);   // kernel parameters: no host sync
+        if (rc_up) return rc_up;
+    }
     dp::BurgParams p;
     p.series = series; p.ld = ld; p.N = (int)T; p.m = coefficients;
     p.unit0 = 0; p.nunits = 2 * S;
@@ -402,7 +405,7 @@ int dp_power_mem(const double* series, int64_t T, int S, int64_t ld, double dt, 
     p.coef = (double*)(ws + lay.off_coef);
     p.xms = (double*)(ws + lay.off_xms);
 #ifndef DP_EMUL
-    const int cluster_E = (lay.smem_mode || getenv("DP_MEM_NO_CLUSTER")) ? 0 : dp::burg_cluster_E(T, coefficients);
+    const int cluster_E = (lay.smem_mode || dp::dev_env("DP_MEM_NO_CLUSTER")) ? 0 : dp::burg_cluster_E(T, coefficients);
 #else
     const int cluster_E = 0;
 #endif

@@ -156,7 +156,7 @@ class Ops:
         return out
 
     def project_commensurate(self, velocity, dims, unit_type, n_prim, qbin, twiddle, project_on_atom=-1, out=None,
-                             pair_major=False):
+                             pair_major=False, validate_bins=True):
         """3-D DFT projection: real (T,N,3) -> (T,Q,n_prim,3) complex128 for commensurate q.
         ``out``: optional preallocated contiguous (T,Q,n_prim,3) destination (e.g. a time slice).
         ``pair_major``: write the intermediate layout (T, 3*n_prim/2, Q, 2) instead (DP_VC_PAIRS), to be
@@ -168,6 +168,12 @@ class Ops:
         ut = _host(unit_type, np.int32)
         n_unit = ut.shape[0]
         assert N == n_unit * int(np.prod(dims_h)), "atom count does not match dims * n_unit"
+        if validate_bins and not is_device_array(qbin):
+            # host-side bins are checked here; device-resident bins are checked by the kernel itself (a bin outside the
+            # grid gives NaN for that q), so the call never waits for the device
+            qh = np.asarray(qbin).reshape(-1, 3)
+            if qh.size and (qh.min() < 0 or (qh >= dims_h[None, :]).any()):
+                raise _lib.DpError(_lib.DP_ERR_INVALID, "project_commensurate: q bins outside the supercell grid")
         qb = be.asarray(qbin, np.int32)
         Q = be.shape(qb)[0]
         tw = be.asarray(twiddle, np.complex128) if twiddle is not None else None      # None: bare lattice DFT

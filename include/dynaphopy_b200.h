@@ -11,8 +11,12 @@
  *   - Pointers marked [dev] are CUDA device pointers, [host] are host pointers.
  *   - Complex numbers are interleaved (re, im) doubles (numpy complex128 layout).
  *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
- *     asynchronous with respect to the host unless stated, re-entrant, and keep no
- *     global state except the per-thread last-error string.
+ *     asynchronous with respect to the host, re-entrant, and keep no global state except the
+ *     per-thread last-error string.  No entry point calls cudaStreamSynchronize: small [host]
+ *     tables travel as kernel parameters; a [host] table above 64 KB (dp_project_wave_vector with
+ *     Q > 2730 or N > 16384) is staged by one pageable cudaMemcpyAsync, which may wait for earlier
+ *     work of the stream before it returns.  Development knobs (DP_* environment variables) are
+ *     compiled in only with -DDP_DEVELOP.
  *   - No hidden device allocation: scratch memory is a caller-owned workspace whose
  *     size is returned by the matching *_workspace_bytes function.
  *   - Return value: 0 on success, negative DP_ERR_* on failure; dp_last_error() gives
@@ -135,7 +139,9 @@ int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt
  *   v         [dev]  T x N x 3 real velocities, N = n_unit * dims[0]*dims[1]*dims[2]
  *   dims      [host] 3 supercell multiplicities (Dynamics.get_supercell_matrix)
  *   unit_type [host] n_unit primitive-atom index of every unit-cell atom
- *   qbin      [dev]  Q x 3 int32 DFT bin of every q: round(q_unitcell * dims) mod dims
+ *   qbin      [dev]  Q x 3 int32 DFT bin of every q: round(q_unitcell * dims) mod dims.  The bins live on the
+ *                    device and are checked there (the call never waits for the device): a bin outside
+ *                    [0, dims) makes every out_vc entry of that q NaN
  *   twiddle   [dev]  Q x n_unit complex128: (N/n_prim)^-1/2 sqrt(mass_u) exp(-i q.tau_u); or NULL (only when
  *                    n_unit == n_prim): out_vc[t,q,u,k] is the bare lattice DFT of unit atom u, and the caller
  *                    folds the twiddle into the eigenvectors of the contraction that follows

@@ -210,9 +210,17 @@ def test_projection_ragged_and_empty(kops):
     from dynaphopy_b200._lib import DpError
     with pytest.raises(DpError):
         kops.project_wave_vector(g["velocity"], sm, g["positions"], g["atom_type"], n_prim, q, project_on_atom=5)
-    with pytest.raises(DpError):      # DFT bin outside the grid
-        dims, unit_type, n_prim, qb, tw, _ = _commensurate_inputs(g)
+    dims, unit_type, n_prim, qb, tw, _ = _commensurate_inputs(g)
+    with pytest.raises(DpError):      # DFT bin outside the grid, bins on the host: checked before the launch
         kops.project_commensurate(g["velocity"], dims, unit_type, n_prim, qb + 7, tw)
+    # bins already on the device: checked by the kernel (no host round trip), the offending q comes back as NaN
+    bad = qb.copy()
+    bad[1] = [0, 7, 0]
+    out = to_np(kops.project_commensurate(g["velocity"], dims, unit_type, n_prim, bad, tw, validate_bins=False))
+    good = to_np(kops.project_commensurate(g["velocity"], dims, unit_type, n_prim, qb, tw))
+    assert np.isnan(out[:, 1]).all()
+    keep = [i for i in range(len(qb)) if i != 1]
+    assert np.array_equal(out[:, keep], good[:, keep])
 
 
 def test_pair_major_intermediate_layout(kops):
@@ -354,6 +362,72 @@ def test_power_fft_long_windows(kops):
     ref = port.fft_spectra(x, 0.001, f, use_fft_correlate=True)      # FFT-based np.correlate restatement
     assert relerr(ps, ref) < TOL
     assert np.array_equal(ps.argmax(0), ref.argmax(0))
+
+
+@pytest.mark.gpu
+def test_power_fft_cfg5b_single_window(cuda_ops):
+    """cfg 5-B: resolution 2^-17/dt so that ONE window covers the whole 2^17-sample run
+    (the reference's piece list is the same window twice, power_spectrum/__init__.py:33-51), 5244 frequencies.
+    Against the oracle with the FFT-based restatement of np.correlate (the O(L^2) form takes minutes per series)."""
+    nt, dt = 131072, 0.001
+    rng = np.random.default_rng(517)
+    x = _series(rng, nt, 3, dt)
+    f = np.arange(5244) * (1.0 / (nt * dt))
+    L, pieces = cuda_ops.fft_pieces(nt, dt, f)
+    assert L == nt and pieces == [[0, nt], [0, nt]] == port.division_of_data(f[1] - f[0], nt, dt)
+    ref = port.fft_spectra(x, dt, f, use_fft_correlate=True)
+    for lay, arr in (("time-major", x), ("series-major", np.ascontiguousarray(x.T))):
+        ps = to_np(cuda_ops.power_fft(arr, dt, f, series_major=(lay == "series-major")))
+        assert ps.shape == ref.shape == (5244, 3)
+        assert relerr(ps, ref) < TOL, lay
+        assert np.array_equal(ps.argmax(0), ref.argmax(0)), lay
+
+
+@pytest.mark.gpu
+def test_c_abi_calls_do_not_block_the_host(cuda_ops):
+    """include/dynaphopy_b200.h: every entry point only ENQUEUES work.  A long-running job is put on the stream first;
+    the calls that used to synchronise (commensurate projection, dense projection, FFT finish, direct correlation,
+    MEM) are then queued behind it 20 times each -- if any of them waited for the stream, the host loop would take at
+    least as long as the job in front of it."""
+    import time
+    import torch
+    ops = cuda_ops
+    rng = np.random.default_rng(5)
+    g = golden("cubic2_232")
+    dims, unit_type, n_prim, qb, tw, _ = _commensurate_inputs(g)
+    dev = ops.be.device
+    v = torch.as_tensor(g["velocity"], device=dev)
+    d_qb = torch.as_tensor(qb, device=dev)
+    d_tw = torch.as_tensor(tw, device=dev)
+    sm = torch.as_tensor(np.sqrt(g["masses"]), device=dev)
+    pos = torch.as_tensor(g["positions"], device=dev)
+    x = torch.as_tensor(_series(rng, 4000, 4, 0.002), device=dev)
+    f = np.arange(0, 30.0, 0.5)
+    big = torch.randn((296, 131072), dtype=torch.complex128, device=dev)
+    fbig = np.arange(0, 40.05, 0.05)
+
+    def small_calls():
+        ops.project_commensurate(v, dims, unit_type, n_prim, d_qb, d_tw)
+        ops.project_wave_vector(v, sm, pos, g["atom_type"], n_prim, g["q_cart"])
+        ops.power_fft(x, 0.002, f)
+        ops.power_correlation(x, 0.002, f, 10, 1, 1)
+        ops.power_mem(x, 0.002, f, 50)
+
+    small_calls()
+    ops.power_fft(big, 0.001, fbig, series_major=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(24):
+        ops.power_fft(big, 0.001, fbig, series_major=True)          # ~30 ms of device work in front
+    h0 = time.perf_counter()
+    for _ in range(20):
+        small_calls()
+    host_ms = (time.perf_counter() - h0) * 1e3
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1)
+    assert host_ms < 0.5 * dev_ms, "host enqueue loop %.1f ms vs %.1f ms of device work: a call waited" % (host_ms, dev_ms)
 
 
 def test_power_mem_vs_oracle(kops):
