@@ -52,7 +52,7 @@ void count_launch();
 #define DP_LAUNCH(kfn, grid, block, smem, stream, ...) \
     (dp::count_launch(), kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define DP_DYNSMEM(type, name)                                   \
-    extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+    extern __shared__ __align__(128) unsigned char name##_raw_[]; \
     type* name = reinterpret_cast<type*>(name##_raw_)
 #define DP_SET_SMEM(kfn, bytes) \
     cudaFuncSetAttribute((const void*)(kfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))

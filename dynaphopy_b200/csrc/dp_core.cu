@@ -3,6 +3,7 @@
 #include <cstdarg>
 
 #include "dp_common.cuh"
+#include "dp_tma.cuh"
 
 namespace dp {
 
@@ -69,6 +70,47 @@ int upload_table(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     if (bytes <= 64 * 1024 && bytes % 4 == 0 && ((size_t)dst & 3) == 0) return upload_small(dst, src, bytes, st);
     DP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
     return DP_OK;
+}
+
+int make_tensor_map_2d(TensorMap2D* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                       uint32_t box_inner, uint32_t box_rows) {
+    DP_REQUIRE(tm && base && inner > 0 && rows > 0 && pitch_bytes % 16 == 0 && ((size_t)base & 15) == 0 &&
+                   box_inner >= 2 && box_inner <= 256 && box_inner % 2 == 0 && box_rows >= 1 && box_rows <= 256,
+               DP_ERR_INVALID, "make_tensor_map_2d: bad tensor description");
+#ifdef DP_EMUL
+    tm->base = (double*)base; tm->inner = inner; tm->rows = rows; tm->pitch_bytes = pitch_bytes;
+    tm->box_inner = box_inner; tm->box_rows = box_rows;
+    return DP_OK;
+#else
+    // cuTensorMapEncodeTiled comes from the driver; fetched through the runtime so that the library does not link libcuda
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !fn) {
+            (void)cudaGetLastError();
+            set_error("make_tensor_map_2d: the driver does not provide cuTensorMapEncodeTiled");
+            return DP_ERR_UNSUPPORTED;
+        }
+        encode = (EncodeFn)fn;
+    }
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstr[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("make_tensor_map_2d: cuTensorMapEncodeTiled failed with %d", (int)r);
+        return DP_ERR_UNSUPPORTED;
+    }
+    return DP_OK;
+#endif
 }
 
 }  // namespace dp

@@ -379,6 +379,24 @@ int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_
         p.scratch = (dp::cplx*)(ws + lay.off_scratch); p.slab_elems = lay.slab_elems;
         p.spec = spec; p.lo = pl.lo; p.nkeep = pl.nkeep;
         p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
+        // bulk stores of passes 1-3 (dp_spectrum_fft2.cuh): the slabs as one 2-D tensor, one box per warp tile
+        {
+            const int n1 = pl.s2.n1, n2 = pl.s2.n2;
+            const int tg = n1 == 16 ? 1 : (n1 == 32 || n1 == 64) ? 4 : n1 == 128 ? 8 : 16;   // SubCfg::TG of C16 .. C256
+            const int ns = 32 / tg;                            // columns per warp tile
+            p.slab_rows = (int)(lay.slab_elems / (size_t)n2);
+            p.r_lo = dp::imin(n1, pl.s2.half / n2 + 1);
+            p.r_hi = dp::imax(p.r_lo, (pl.s2.P - pl.s2.half) / n2);
+            const uint64_t rows = (uint64_t)grid * (uint64_t)p.slab_rows;
+            const uint64_t pitch = (uint64_t)n2 * sizeof(dp::cplx);
+            rc = dp::make_tensor_map_2d(&p.tm_col, p.scratch, 2ull * n2, rows, pitch, 2u * ns, (uint32_t)n1);
+            if (rc) return rc;
+            rc = dp::make_tensor_map_2d(&p.tm_lo, p.scratch, 2ull * n2, rows, pitch, 2u * ns, (uint32_t)p.r_lo);
+            if (rc) return rc;
+            rc = dp::make_tensor_map_2d(&p.tm_hi, p.scratch, 2ull * n2, rows, pitch, 2u * ns,
+                                        (uint32_t)dp::imax(1, n1 - p.r_hi));
+            if (rc) return rc;
+        }
         p.skip_mask = dp::dev_env("DP_S2_SKIP") ? atoi(dp::dev_env("DP_S2_SKIP")) : 0;
         p.pair = (n_windows >= 2 && !(dp::dev_env("DP_S2_PAIR") && atoi(dp::dev_env("DP_S2_PAIR")) == 0)) ? 1 : 0;
         auto k = dp::spectrum2_kernel;

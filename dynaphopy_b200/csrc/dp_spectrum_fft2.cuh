@@ -17,13 +17,14 @@
 #pragma once
 
 #include "dp_fft_reg.cuh"
+#include "dp_tma.cuh"
 
 namespace dp {
 
 #ifndef DP_S2_THREADS
-#define DP_S2_THREADS 256
+#define DP_S2_THREADS 384
 #endif
-constexpr int S2_THREADS = DP_S2_THREADS;          // 8 warps x <= 255 registers
+constexpr int S2_THREADS = DP_S2_THREADS;          // 12 warps x <= 168 registers (measured best of 8 / 12 / 16 warps)
 constexpr int S2_WARPS = S2_THREADS / 32;
 constexpr int S2_BINSLOTS = 8;                    // bins per residue thread in pass 4
 constexpr int S2_TILE_COLS = S2_THREADS / 16;     // pass-4 column tile: 16 threads per column
@@ -66,6 +67,10 @@ struct S2Params {
     double dt, acf_scale;
     int skip_mask;                 // development aid (DP_S2_SKIP): bit i set = skip pass i+1
     int pair;                      // 1: process the windows of a series two at a time (see spectrum2_kernel)
+    // bulk stores of passes 1-3: all slabs form ONE 2-D tensor of doubles (gridDim.x * slab_rows rows of 2*n2);
+    // boxes of one warp tile (2*NS doubles wide): n1 rows (pass 1), the r_lo first / n1 - r_hi last rows (pass 3)
+    int slab_rows, r_lo, r_hi;
+    TensorMap2D tm_col, tm_lo, tm_hi;
 };
 
 struct S2Smem {
@@ -75,28 +80,21 @@ struct S2Smem {
     cplx* Ts;       // [k1*R2 + j2] = w_n1'^(j2 k1)     pass 4
     cplx* fine;     // [256] w_P^j
     cplx* coarse;   // [256] w_P^(256 j)
-    cplx* E;        // S2_WARPS * SUBFFT_EWARP_MAX      exchange slabs (pass 4: the column tile)
-    cplx* PF;       // S2_WARPS * 512                   per-warp landing zone of the NEXT tile (cp.async, passes 1-3)
+    cplx* E;        // S2_WARPS * SUBFFT_EWARP_MAX      per-warp exchange slab, reused as the warp's staging tile of
+                    //                                  the bulk stores (pass 4: the column tile)
 };
-// Measured (B200, cfg 5-A): 138.4 ms with the cp.async pipeline vs 129.7 ms without -- the passes are limited by
-// LSU / L2-port throughput (LSU wavefronts 50 %), not by exposed load latency, and the extra shared-memory round trip
-// costs more than the overlap buys.  Kept as a build option (-DDP_S2_PREFETCH=1) for other window lengths.
-#ifndef DP_S2_PREFETCH
-#define DP_S2_PREFETCH 0
+// Slab traffic of passes 1-3 (history): per-lane ld/st.global with L2 eviction hints, plain .cg accesses and a
+// cp.async landing zone all measured the same or slower (B200, cfg 5-A: 129-138 ms) -- the passes were limited by
+// the in-order load/store unit: every warp's 16 stores per tile (8 wavefronts of 64 bytes each in the column
+// passes) drain at the SM's L2 write rate (~26 B/clk) and the next tile's loads queue up behind them.  Stores now
+// leave through the bulk-copy engine (dp_tma.cuh): a tile is written to the warp's staging area in shared memory
+// (conflict-free STS) and ONE elected lane issues a tensor-box / bulk store; the load/store unit sees loads only.
+#ifndef DP_S2_TMA
+#define DP_S2_TMA 1
 #endif
-// Register software pipeline of passes 1-3 (see s2_pass1): next tile's loads issued between the two butterfly stages.
-#ifndef DP_S2_SWP
-#define DP_S2_SWP 0
-#endif
-#ifdef DP_EMUL
-#define DP_LAMBDA_INLINE
-#else
-#define DP_LAMBDA_INLINE __attribute__((always_inline))
-#endif
-constexpr size_t S2_PF_ELEMS = DP_S2_PREFETCH ? (size_t)S2_WARPS * 512 : 0;
 constexpr size_t S2_E_ELEMS = S2_WARPS * SUBFFT_EWARP_MAX > 2 * S2_NP_MAX * S2_CPITCH ? S2_WARPS * SUBFFT_EWARP_MAX
                                                                                   : 2 * S2_NP_MAX * S2_CPITCH;
-constexpr size_t S2_SMEM_BYTES = (size_t)(6 * 256 + S2_E_ELEMS + S2_PF_ELEMS) * sizeof(cplx);
+constexpr size_t S2_SMEM_BYTES = (size_t)(6 * 256 + S2_E_ELEMS) * sizeof(cplx);
 
 // carve the CTA's dynamic shared memory; done inside every pass (from the __shared__ symbol itself) so
 // that the compiler sees shared-space pointers and emits LDS/STS instead of generic loads
@@ -104,7 +102,6 @@ __device__ __forceinline__ S2Smem s2_carve(cplx* smem) {
     S2Smem sm;
     sm.T1 = smem; sm.T2 = smem + 256; sm.T2f = smem + 512; sm.Ts = smem + 768;
     sm.fine = smem + 1024; sm.coarse = smem + 1280; sm.E = smem + 1536;
-    sm.PF = smem + 1536 + S2_E_ELEMS;
     return sm;
 }
 #define S2_SMEM_HERE() DP_DYNSMEM(cplx, s2_smem_base_); const S2Smem sm = s2_carve(s2_smem_base_)
@@ -121,78 +118,53 @@ __device__ __forceinline__ void s2_prefetch_l2(const void* ptr) {
 #endif
 }
 
-// Slab accesses carry an L2 evict_last policy (the slab must survive in L2 between the passes), the window
-// samples are read with the streaming (evict_first) hint: they are used once.
-__device__ __forceinline__ unsigned long long s2_slab_policy() {
+// slab accesses of the load/store unit: L2 only (the slab is shared with the bulk-copy engine, never cached in L1)
+__device__ __forceinline__ cplx s2_ld_slab(const cplx* ptr) {
 #ifdef DP_EMUL
-    return 0;
-#else
-    unsigned long long pol;
-#ifndef DP_S2_EVICT_FRAC
-#define DP_S2_EVICT_FRAC 1.0
-#endif
-#define DP_S2_STR2(x) #x
-#define DP_S2_STR(x) DP_S2_STR2(x)
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, " DP_S2_STR(DP_S2_EVICT_FRAC) ";\n" : "=l"(pol));
-    return pol;
-#endif
-}
-#ifndef DP_S2_LDMODE
-#define DP_S2_LDMODE 2
-#endif
-__device__ __forceinline__ cplx s2_ld_slab(const cplx* ptr, unsigned long long pol) {
-#if defined(DP_EMUL) || DP_S2_LDMODE == 0
     return *ptr;
-#elif DP_S2_LDMODE == 1
+#else
     return __ldcg(ptr);
-#else
-    cplx v;
-    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;\n" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol) : "memory");
-    return v;
 #endif
 }
-__device__ __forceinline__ void s2_st_slab(cplx* ptr, cplx v, unsigned long long pol) {
-#if defined(DP_EMUL) || DP_S2_LDMODE == 0
+__device__ __forceinline__ void s2_st_slab(cplx* ptr, cplx v) {
+#ifdef DP_EMUL
     *ptr = v;
-#elif DP_S2_LDMODE == 1
+#else
     __stcg(ptr, v);
-#else
-    asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;\n" ::"l"(ptr), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 #endif
 }
 
-
-// ---- software pipeline of passes 1-3: the NEXT tile of a warp travels global -> shared memory with cp.async while
-// the current one is transformed; a lane copies exactly the 16 values it will load into registers (slot r*32 + lane:
-// conflict-free), so no cross-lane synchronisation is involved.  Zero fill for samples beyond the window.
-__device__ __forceinline__ unsigned long long s2_stream_policy() {
-#ifdef DP_EMUL
-    return 0;
-#else
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
-    return pol;
+// ---- staging-tile protocol of one warp (DP_S2_TMA) -------------------------------------------------------------
+// The staging tile shares the warp's exchange slab E: (1) before the first write to E of a tile, the bulk stores of the
+// previous tile must have finished reading it: s2_stage_acquire; (2) after the last exchange read, a warp barrier, then
+// the results are written to E in the tile layout; (3) s2_stage_publish orders those writes before the asynchronous
+// proxy; the elected lanes then issue their stores and commit.  s2_stage_drain at the end of a pass: the global writes
+// are complete (and ordered before the ordinary loads of the next pass, after the CTA barrier that follows).
+__device__ __forceinline__ void s2_stage_acquire() {
+#if DP_S2_TMA
+    bulk_wait_read<0>();          // lanes that issued nothing return at once
+    __syncwarp();
 #endif
 }
-__device__ __forceinline__ void s2_cp16(cplx* dst_smem, const cplx* src, bool valid, unsigned long long pol) {
-#ifdef DP_EMUL
-    *dst_smem = valid ? *src : make_double2(0.0, 0.0);
-#else
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(d), "l"(src), "r"(sz), "l"(pol) : "memory");
+__device__ __forceinline__ void s2_stage_publish() {
+#if DP_S2_TMA
+    fence_proxy_async_smem();
+    __syncwarp();
 #endif
 }
-__device__ __forceinline__ void s2_cp_commit() {
-#ifndef DP_EMUL
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+__device__ __forceinline__ void s2_stage_drain() {
+#if DP_S2_TMA
+    bulk_wait<0>();
+    fence_proxy_async();
 #endif
 }
-__device__ __forceinline__ void s2_cp_wait() {
-#ifndef DP_EMUL
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-#endif
-}
+// row pitch (in elements of 16 / 8 bytes) of a staged ROW tile of NS rows: spreads the rows of a quarter-/half-warp
+// over the shared-memory bank groups (same rule as SubCfg::ESEQ)
+template <class C> struct S2RowPitch {
+    static constexpr int NSQ = C::NS < 8 ? C::NS : 8;
+    __device__ static __forceinline__ int cplx_pitch(int n2) { return n2 + 8 / NSQ; }
+    __device__ static __forceinline__ int real_pitch(int n2) { return n2 + (16 / C::NS > 2 ? 16 / C::NS : 2); }
+};
 
 // ---- pass 1: window -> column FFTs -> A -----------------------------------------------------------
 // LAYOUT 0: time axis contiguous (stride_t == 1, no blocks) -- plain pointer arithmetic in the unrolled loads;
@@ -201,15 +173,16 @@ template <class C, int LAYOUT>
 __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict__ x, int t0, cplx* __restrict__ A,
                                       int warp, int lane) {
     S2_SMEM_HERE();
-    const unsigned long long pol = s2_slab_policy();
     const int n2 = p.pl.n2, L = p.pl.L;
     const int tb_shift = p.tb_shift;
     const int64_t tb_stride = p.tb_stride;
     const int seq = lane % C::NS, g = lane / C::NS;
-    cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
+    cplx* Ew = sm.E + (size_t)warp * SUBFFT_EWARP_MAX;       // the warp's exchange slab / staging tile
+    cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
-    auto load_tile = [&](int tile, cplx (&w)[16]) DP_LAMBDA_INLINE {
+    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int col = tile * C::NS + seq;
+        cplx v[16];
 #pragma unroll
         for (int i = 0; i < C::NB1; i++)
 #pragma unroll
@@ -223,55 +196,12 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
                         val = __ldcs(x + (int64_t)b * tb_stride + (t - (b << tb_shift)));
                     } else val = __ldcs(x + s2_time_offset(p, t0 + idx));
                 }
-                w[i * C::R1 + a] = val;
+                v[i * C::R1 + a] = val;
             }
-    };
-#if DP_S2_PREFETCH
-    cplx* PB = sm.PF + (size_t)warp * 512 + lane;
-    const unsigned long long spol = s2_stream_policy();
-    auto prefetch_tile = [&](int tile) {
-        const int col = tile * C::NS + seq;
-#pragma unroll
-        for (int i = 0; i < C::NB1; i++)
-#pragma unroll
-            for (int a = 0; a < C::R1; a++) {
-                const int idx = (a * C::R2 + g + C::TG * i) * n2 + col;
-                const bool ok = idx < L;
-                const int t = t0 + (ok ? idx : 0);
-                const cplx* src;
-                if (LAYOUT == 0) src = x + t;
-                else if (LAYOUT == 1) { const int b = t >> tb_shift; src = x + (int64_t)b * tb_stride + (t - (b << tb_shift)); }
-                else src = x + s2_time_offset(p, t);
-                s2_cp16(PB + (i * C::R1 + a) * 32, src, ok, spol);
-            }
-        s2_cp_commit();
-    };
-    if (warp < ntiles) prefetch_tile(warp);
-#endif
-#if DP_S2_SWP
-    cplx v[16], nx[16];
-    if (warp < ntiles) load_tile(warp, v);
-#endif
-    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
-        const int col = tile * C::NS + seq;
-#if DP_S2_SWP
-        // software pipeline: the next tile's samples are requested as soon as this tile's first butterflies are
-        // parked in the exchange slab, and travel while the second butterflies, twiddles and stores run
-        sub_dit_a<C>(v, E, sm.T1, g);
-        const bool more = tile + S2_WARPS < ntiles;
-        if (more) load_tile(tile + S2_WARPS, nx);
-        sub_dit_b<C>(v, E, g);
-#else
-        cplx v[16];
-#if DP_S2_PREFETCH
-        s2_cp_wait();
-#pragma unroll
-        for (int r = 0; r < 16; r++) v[r] = PB[r * 32];
-        if (tile + S2_WARPS < ntiles) prefetch_tile(tile + S2_WARPS);
-#else
-        load_tile(tile, v);
-#endif
+        s2_stage_acquire();
         sub_dit<C>(v, E, sm.T1, g);
+#if DP_S2_TMA
+        __syncwarp();                 // every lane has read its exchange values: E becomes the staging tile [n1][NS]
 #endif
         // four-step twiddle w_P^(col*kk), kk = k1 + R1*k2: geometric in k2
         const cplx ratio = tw2level(sm.fine, sm.coarse, col * C::R1);
@@ -281,18 +211,26 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
             cplx tw = tw2level(sm.fine, sm.coarse, col * k1);
 #pragma unroll
             for (int k2 = 0; k2 < C::R2; k2++) {
-                s2_st_slab(A + (size_t)(k1 + C::R1 * k2) * n2 + col, cmul(v[i * C::R2 + k2], tw), pol);
+                const cplx val = cmul(v[i * C::R2 + k2], tw);
+#if DP_S2_TMA
+                Ew[(k1 + C::R1 * k2) * C::NS + seq] = val;
+#else
+                s2_st_slab(A + (size_t)(k1 + C::R1 * k2) * n2 + col, val);
+#endif
                 if (k2 + 1 < C::R2) tw = cmul(tw, ratio);
             }
         }
-        __syncwarp();
-#if DP_S2_SWP
-        if (more) {
-#pragma unroll
-            for (int r = 0; r < 16; r++) v[r] = nx[r];
+#if DP_S2_TMA
+        s2_stage_publish();
+        if (lane == 0) {
+            tma_store_2d(&p.tm_col, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows), Ew);
+            bulk_commit();
         }
+#else
+        __syncwarp();
 #endif
     }
+    s2_stage_drain();
 }
 
 // ---- pass 2: rows: FFT -> |.|^2 -> FFT (DIF) -> twiddle, in place ------------------------------------
@@ -303,48 +241,20 @@ template <class C, int MODE>
 __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, double* __restrict__ Sr, int warp,
                                       int lane) {
     S2_SMEM_HERE();
-    const unsigned long long pol = s2_slab_policy();
     const int n1 = p.pl.n1, n2 = p.pl.n2;
     const int seq = lane % C::NS, g = lane / C::NS;
-    cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
+    cplx* Ew = sm.E + (size_t)warp * SUBFFT_EWARP_MAX;
+    cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n1 / C::NS;
-    auto load_tile = [&](int tile, cplx (&w)[16]) DP_LAMBDA_INLINE {
-        const cplx* Ar = A + (size_t)(tile * C::NS + seq) * n2;
-#pragma unroll
-        for (int i = 0; i < C::NB1; i++)
-#pragma unroll
-            for (int a = 0; a < C::R1; a++) w[i * C::R1 + a] = s2_ld_slab(Ar + a * C::R2 + g + C::TG * i, pol);
-    };
-#if DP_S2_PREFETCH
-    cplx* PB = sm.PF + (size_t)warp * 512 + lane;
-    auto prefetch_tile = [&](int tile) {
-        const cplx* Ar = A + (size_t)(tile * C::NS + seq) * n2;
-#pragma unroll
-        for (int i = 0; i < C::NB1; i++)
-#pragma unroll
-            for (int a = 0; a < C::R1; a++) s2_cp16(PB + (i * C::R1 + a) * 32, Ar + a * C::R2 + g + C::TG * i, true, pol);
-        s2_cp_commit();
-    };
-    if (warp < ntiles) prefetch_tile(warp);
-#endif
-#if DP_S2_SWP
-    cplx v[16], nx[16];
-    if (warp < ntiles) load_tile(warp, v);
-#endif
+    const int rp = S2RowPitch<C>::cplx_pitch(n2), rpd = S2RowPitch<C>::real_pitch(n2);
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int row = tile * C::NS + seq;
         cplx* __restrict__ Ar = A + (size_t)row * n2;
-#if !DP_S2_SWP
         cplx v[16];
-#if DP_S2_PREFETCH
-        s2_cp_wait();
 #pragma unroll
-        for (int r = 0; r < 16; r++) v[r] = PB[r * 32];
-        if (tile + S2_WARPS < ntiles) prefetch_tile(tile + S2_WARPS);
-#else
-        load_tile(tile, v);
-#endif
-#endif
+        for (int i = 0; i < C::NB1; i++)
+#pragma unroll
+            for (int a = 0; a < C::R1; a++) v[i * C::R1 + a] = s2_ld_slab(Ar + a * C::R2 + g + C::TG * i);
         double sa[16];
         double* __restrict__ Srow = Sr + (size_t)row * n2;
         if (MODE == 2) {                       // |X_a|^2 of the partner window, requested before the butterflies
@@ -353,22 +263,32 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 #pragma unroll
                 for (int k2 = 0; k2 < C::R2; k2++) sa[i * C::R2 + k2] = __ldcg(Srow + g + C::TG * i + C::R1 * k2);
         }
-#if DP_S2_SWP
-        sub_dit_a<C>(v, E, sm.T2, g);
-        const bool more = tile + S2_WARPS < ntiles;
-        if (more) load_tile(tile + S2_WARPS, nx);      // next rows travel underneath the rest of this tile
-        sub_dit_b<C>(v, E, g);
-#else
+        s2_stage_acquire();
         sub_dit<C>(v, E, sm.T2, g);
-#endif
         if constexpr (MODE == 1) {
+#if DP_S2_TMA
+            __syncwarp();             // exchange reads done: E becomes the staging tile, NS rows of n2 doubles
+            double* Sw = reinterpret_cast<double*>(Ew) + (size_t)seq * rpd;
+#endif
 #pragma unroll
             for (int i = 0; i < C::NB2; i++)
 #pragma unroll
                 for (int k2 = 0; k2 < C::R2; k2++) {
                     const cplx x = v[i * C::R2 + k2];
+#if DP_S2_TMA
+                    Sw[g + C::TG * i + C::R1 * k2] = x.x * x.x + x.y * x.y;
+#else
                     __stcg(Srow + g + C::TG * i + C::R1 * k2, x.x * x.x + x.y * x.y);
+#endif
                 }
+#if DP_S2_TMA
+            s2_stage_publish();
+            if (lane < C::NS) {       // lane s ships row s of the tile: n2 contiguous doubles
+                bulk_s2g(Sr + (size_t)(tile * C::NS + lane) * n2, reinterpret_cast<double*>(Ew) + (size_t)lane * rpd,
+                         (unsigned)(n2 * sizeof(double)));
+                bulk_commit();
+            }
+#endif
         } else {
 #pragma unroll
             for (int r = 0; r < C::NB2 * C::R2; r++) {
@@ -377,6 +297,10 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
             }
             __syncwarp();
             sub_dif<C>(v, E, sm.T2f, g);
+#if DP_S2_TMA
+            __syncwarp();             // exchange reads done: E becomes the staging tile, NS rows of n2 complex values
+            cplx* Ow = Ew + (size_t)seq * rp;
+#endif
             // four-step twiddle w_P^(row*k), k = d*R2 + c: geometric in d
             const cplx ratio = tw2level(sm.fine, sm.coarse, row * C::R2);
 #pragma unroll
@@ -385,97 +309,85 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
                 cplx tw = tw2level(sm.fine, sm.coarse, row * c);
 #pragma unroll
                 for (int d = 0; d < C::R1; d++) {
-                    s2_st_slab(Ar + d * C::R2 + c, cmul(v[i * C::R1 + d], tw), pol);
+                    const cplx val = cmul(v[i * C::R1 + d], tw);
+#if DP_S2_TMA
+                    Ow[d * C::R2 + c] = val;
+#else
+                    s2_st_slab(Ar + d * C::R2 + c, val);
+#endif
                     if (d + 1 < C::R1) tw = cmul(tw, ratio);
                 }
             }
+#if DP_S2_TMA
+            s2_stage_publish();
+            if (lane < C::NS) {
+                bulk_s2g(A + (size_t)(tile * C::NS + lane) * n2, Ew + (size_t)lane * rp, (unsigned)(n2 * sizeof(cplx)));
+                bulk_commit();
+            }
+#endif
         }
+#if !DP_S2_TMA
         __syncwarp();
-#if DP_S2_SWP
-        if (more) {
-#pragma unroll
-            for (int r = 0; r < 16; r++) v[r] = nx[r];
-        }
 #endif
     }
+    s2_stage_drain();
 }
 
 // ---- pass 3: column FFTs -> conj -> lags 0..half of the autocorrelation, in place ------------------------
 // r[kappa] lands at A[kappa]: a warp overwrites only rows of the columns it has just read.
 // PAIRED: A holds Y = FFT_P(|X_a|^2 + i |X_b|^2); rho[kappa] = r_a[kappa] + i r_b[kappa] = Y[-kappa] / P, so the
 // lags -half..half are Y at indices 0..half and P-half..P-1 (no conjugation, no Hermitian shortcut).
+// Only the rows that hold needed lags are written: rows [0, r_lo) and, PAIRED, rows [r_hi, n1) (whole rows of the
+// warp's own columns: the few extra elements of the boundary rows are never read).
 template <class C, bool PAIRED>
 __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, int warp, int lane) {
     S2_SMEM_HERE();
-    const unsigned long long pol = s2_slab_policy();
     const int n2 = p.pl.n2, half = p.pl.half;
     const double sc = p.acf_scale;
     const int seq = lane % C::NS, g = lane / C::NS;
-    cplx* E = sm.E + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
+    cplx* Ew = sm.E + (size_t)warp * SUBFFT_EWARP_MAX;
+    cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
-    auto load_tile = [&](int tile, cplx (&w)[16]) DP_LAMBDA_INLINE {
-        const int col = tile * C::NS + seq;
-#pragma unroll
-        for (int i = 0; i < C::NB1; i++)
-#pragma unroll
-            for (int a = 0; a < C::R1; a++) w[i * C::R1 + a] = s2_ld_slab(A + (size_t)(a * C::R2 + g + C::TG * i) * n2 + col, pol);
-    };
-#if DP_S2_PREFETCH
-    cplx* PB = sm.PF + (size_t)warp * 512 + lane;
-    auto prefetch_tile = [&](int tile) {
-        const int col = tile * C::NS + seq;
-#pragma unroll
-        for (int i = 0; i < C::NB1; i++)
-#pragma unroll
-            for (int a = 0; a < C::R1; a++)
-                s2_cp16(PB + (i * C::R1 + a) * 32, A + (size_t)(a * C::R2 + g + C::TG * i) * n2 + col, true, pol);
-        s2_cp_commit();
-    };
-    if (warp < ntiles) prefetch_tile(warp);
-#endif
-#if DP_S2_SWP
-    cplx v[16], nx[16];
-    if (warp < ntiles) load_tile(warp, v);
-#endif
+    const int r_lo = p.r_lo, r_hi = p.r_hi;
     for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
         const int col = tile * C::NS + seq;
-#if DP_S2_SWP
-        sub_dit_a<C>(v, E, sm.T1, g);
-        const bool more = tile + S2_WARPS < ntiles;
-        if (more) load_tile(tile + S2_WARPS, nx);      // other columns: independent of this tile's in-place stores
-        sub_dit_b<C>(v, E, g);
-#else
         cplx v[16];
-#if DP_S2_PREFETCH
-        s2_cp_wait();
 #pragma unroll
-        for (int r = 0; r < 16; r++) v[r] = PB[r * 32];
-        if (tile + S2_WARPS < ntiles) prefetch_tile(tile + S2_WARPS);
-#else
-        load_tile(tile, v);
-#endif
+        for (int i = 0; i < C::NB1; i++)
+#pragma unroll
+            for (int a = 0; a < C::R1; a++) v[i * C::R1 + a] = s2_ld_slab(A + (size_t)(a * C::R2 + g + C::TG * i) * n2 + col);
+        s2_stage_acquire();
         sub_dit<C>(v, E, sm.T1, g);
-#endif
         __syncwarp();          // every lane of the warp has its column in registers before rows are overwritten
 #pragma unroll
         for (int i = 0; i < C::NB2; i++)
 #pragma unroll
             for (int k2 = 0; k2 < C::R2; k2++) {
-                const int kap = (g + C::TG * i + C::R1 * k2) * n2 + col;
+                const int row = g + C::TG * i + C::R1 * k2;
+#if DP_S2_TMA
+                if (row < r_lo || (PAIRED && row >= r_hi))
+                    Ew[row * C::NS + seq] = make_double2(v[i * C::R2 + k2].x * sc, PAIRED ? v[i * C::R2 + k2].y * sc : -v[i * C::R2 + k2].y * sc);
+#else
+                const int kap = row * n2 + col;
                 if (PAIRED) {
                     if (kap <= half || kap >= p.pl.P - half)
-                        s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, v[i * C::R2 + k2].y * sc), pol);
+                        s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, v[i * C::R2 + k2].y * sc));
                 } else if (kap <= half) {
-                    s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, -v[i * C::R2 + k2].y * sc), pol);
+                    s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, -v[i * C::R2 + k2].y * sc));
                 }
+#endif
             }
-#if DP_S2_SWP
-        if (more) {
-#pragma unroll
-            for (int r = 0; r < 16; r++) v[r] = nx[r];
+#if DP_S2_TMA
+        s2_stage_publish();
+        if (lane == 0) {
+            tma_store_2d(&p.tm_lo, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows), Ew);
+            if (PAIRED) tma_store_2d(&p.tm_hi, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows) + r_hi, Ew + (size_t)r_hi * C::NS);
+            bulk_commit();
         }
 #endif
     }
+    s2_stage_drain();
+    (void)half;
 }
 
 // ---- pass 4: the kept bins of FFT_L(a) ------------------------------------------------------------------
@@ -491,7 +403,6 @@ template <class C, bool PAIRED>
 __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict__ R, double* __restrict__ spec,
                                       int tid) {
     S2_SMEM_HERE();
-    const unsigned long long pol = s2_slab_policy();
     const int L = p.pl.L, half = p.pl.half, n2L = p.pl.n2L;
     constexpr int NP = C::N, R1 = C::R1, R2 = C::R2;
     cplx* Ca = sm.E;                                    // [NP][S2_CPITCH] after the first butterfly
@@ -504,9 +415,9 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
             for (int a = 0; a < R1; a++) {
                 const int kap = (a * R2 + g) * n2L + col - half;
                 if (PAIRED) {
-                    v[a] = s2_ld_slab(R + (kap > 0 ? p.pl.P - kap : -kap), pol);      // Y[-kappa]
+                    v[a] = s2_ld_slab(R + (kap > 0 ? p.pl.P - kap : -kap));      // Y[-kappa]
                 } else {
-                    v[a] = s2_ld_slab(R + (kap >= 0 ? kap : -kap), pol);
+                    v[a] = s2_ld_slab(R + (kap >= 0 ? kap : -kap));
                     if (kap < 0) v[a].y = -v[a].y;                 // negative lag: conj(r[-kappa])
                 }
             }
@@ -515,19 +426,24 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
             for (int a = 0; a < R1; a++) v[a] = make_double2(0.0, 0.0);
         }
     };
-    // bins owned by this thread (residue thread r = tid < NP)
+    // bins owned by this thread: residue r = tid % NP, and of that residue's kept bins e = r + NP*j every NSPLIT-th one
+    // (j = h + NSPLIT*b, h = tid / NP) -- all threads of the CTA take part in the Horner phase, not only the first NP
+    constexpr int NSPLIT = S2_THREADS / NP < 1 ? 1 : (S2_THREADS / NP > S2_BINSLOTS ? S2_BINSLOTS : S2_THREADS / NP);
+    constexpr int SLOTS = (S2_BINSLOTS + NSPLIT - 1) / NSPLIT;
+    const int r = tid % NP, h = tid / NP;
     int k_lo = p.lo - half;
     if (k_lo < 0) k_lo += L;
-    const int nbins = tid < NP ? (p.nkeep - tid + NP - 1) / NP : 0;   // kept indices tid, tid+NP, ... < nkeep
-    cplx acc[S2_BINSLOTS], z[S2_BINSLOTS];
+    const int nres = h < NSPLIT ? (p.nkeep - r + NP - 1) / NP : 0;       // kept bins of residue r: e = r + NP*j, j < nres
+    const int nbins = nres > h ? (nres - h + NSPLIT - 1) / NSPLIT : 0;    // ... of which this thread owns j = h + NSPLIT*b
+    cplx acc[SLOTS], z[SLOTS];
 #pragma unroll
-    for (int b = 0; b < S2_BINSLOTS; b++) {
-        int k = k_lo + tid + NP * b;
+    for (int b = 0; b < SLOTS; b++) {
+        int k = k_lo + r + NP * (h + NSPLIT * b);
         k %= L;
         z[b] = b < nbins ? __ldg(p.g_twL + k) : make_double2(0.0, 0.0);
         acc[b] = make_double2(0.0, 0.0);
     }
-    const cplx* crow = Cb + ((k_lo + tid) % NP) * S2_CPITCH;
+    const cplx* crow = Cb + ((k_lo + r) % NP) * S2_CPITCH;
     const int ntile = (n2L + S2_TILE_COLS - 1) / S2_TILE_COLS;
     cplx v[16];
     load_tile((ntile - 1) * S2_TILE_COLS, v);
@@ -556,7 +472,7 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
             for (int cc = ncols - 1; cc >= 0; cc--) {
                 const cplx cv = crow[cc];
 #pragma unroll
-                for (int b = 0; b < S2_BINSLOTS; b++) {
+                for (int b = 0; b < SLOTS; b++) {
                     if (b < nbins) {
                         const cplx a = acc[b];
                         acc[b].x = fma(a.x, z[b].x, fma(-a.y, z[b].y, cv.x));
@@ -568,26 +484,27 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
     }
     if (!PAIRED) {
 #pragma unroll
-        for (int b = 0; b < S2_BINSLOTS; b++)
-            if (b < nbins) spec[tid + NP * b] = __dmul_rn(hypot(acc[b].x, acc[b].y), p.dt);
+        for (int b = 0; b < SLOTS; b++)
+            if (b < nbins) spec[r + NP * (h + NSPLIT * b)] = __dmul_rn(hypot(acc[b].x, acc[b].y), p.dt);
     } else {
         // Im r_a[-L/2], Im r_b[-L/2] from rho[-half] = Y[half], rho[+half] = Y[P - half] (even L only)
         double Ia = 0.0, Ib = 0.0;
         if ((L & 1) == 0) {
-            const cplx rm = s2_ld_slab(R + half, pol), rp = s2_ld_slab(R + p.pl.P - half, pol);
+            const cplx rm = s2_ld_slab(R + half), rp = s2_ld_slab(R + p.pl.P - half);
             Ia = 0.5 * (rm.y - rp.y);
             Ib = 0.5 * (rp.x - rm.x);
         }
         double* __restrict__ spec_b = spec + p.nkeep;             // the pair's second window
 #pragma unroll
-        for (int b = 0; b < S2_BINSLOTS; b++) {
+        for (int b = 0; b < SLOTS; b++) {
             if (b < nbins) {
-                const int k = (k_lo + tid + NP * b) % L;
+                const int e = r + NP * (h + NSPLIT * b);
+                const int k = (k_lo + e) % L;
                 const cplx ph = __ldg(p.g_twL + (int)(((int64_t)half * k) % L));      // w_L^(half k)
                 const cplx wt = cmulc(acc[b], ph);                                     // remove the phase
                 const double sgn = (k & 1) ? -1.0 : 1.0;
-                spec[tid + NP * b] = __dmul_rn(hypot(wt.x + sgn * Ib, Ia), p.dt);
-                spec_b[tid + NP * b] = __dmul_rn(hypot(wt.y - sgn * Ia, Ib), p.dt);
+                spec[e] = __dmul_rn(hypot(wt.x + sgn * Ib, Ia), p.dt);
+                spec_b[e] = __dmul_rn(hypot(wt.y - sgn * Ia, Ib), p.dt);
             }
         }
     }
