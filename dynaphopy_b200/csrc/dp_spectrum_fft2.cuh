@@ -12,8 +12,7 @@
 //           Horner's rule in z = w_L^k over the columns                                    -> spec
 // The slab (P complex per CTA, <= 1 MB; pass 3 writes r over the rows it has consumed) is written and
 // re-read by the same SM within microseconds and stays in the 126 MB L2; HBM sees the window once
-// (16 B per sample; the next item's window is prefetched into L2 while passes 3-4 run) and the kept
-// bins (8 B each).
+// (16 B per sample) and the kept bins (8 B each).
 #pragma once
 
 #include "dp_fft_reg.cuh"
@@ -134,6 +133,19 @@ __device__ __forceinline__ void s2_st_slab(cplx* ptr, cplx v) {
 #endif
 }
 
+// ---- tile scheduling of passes 1-3: a CTA-wide counter (monotonic over the whole kernel) hands out the tiles of a pass,
+// so that any number of warps stays balanced (64 tiles over 12 warps).  The claim for the NEXT tile is issued at the top
+// of a tile and read at its end: the shared-memory atomic's latency is never exposed.
+struct S2Tiles {
+    int* counter;
+    int base;           // counter value at which the current pass starts (uniform over the CTA)
+};
+__device__ __forceinline__ int s2_claim_issue(const S2Tiles& ts, int lane) {
+    return lane == 0 ? atomicAdd(ts.counter, 1) - ts.base : 0;
+}
+__device__ __forceinline__ int s2_claim_get(int raw) { return __shfl_sync(0xffffffffu, raw, 0); }
+__device__ __forceinline__ void s2_tiles_done(S2Tiles& ts, int ntiles) { ts.base += ntiles + S2_WARPS; }   // one claim beyond the end per warp
+
 // ---- staging-tile protocol of one warp (DP_S2_TMA) -------------------------------------------------------------
 // The staging tile shares the warp's exchange slab E: (1) before the first write to E of a tile, the bulk stores of the
 // previous tile must have finished reading it: s2_stage_acquire; (2) after the last exchange read, a warp barrier, then
@@ -171,7 +183,7 @@ template <class C> struct S2RowPitch {
 // 1: contiguous power-of-two time blocks (the all-to-all's receive layout); 2: anything else.
 template <class C, int LAYOUT>
 __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict__ x, int t0, cplx* __restrict__ A,
-                                      int warp, int lane) {
+                                      S2Tiles& ts, int warp, int lane) {
     S2_SMEM_HERE();
     const int n2 = p.pl.n2, L = p.pl.L;
     const int tb_shift = p.tb_shift;
@@ -180,7 +192,8 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
     cplx* Ew = sm.E + (size_t)warp * SUBFFT_EWARP_MAX;       // the warp's exchange slab / staging tile
     cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
-    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
+    for (int tile = s2_claim_get(s2_claim_issue(ts, lane)); tile < ntiles;) {
+        const int next_raw = s2_claim_issue(ts, lane);
         const int col = tile * C::NS + seq;
         cplx v[16];
 #pragma unroll
@@ -229,8 +242,10 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
 #else
         __syncwarp();
 #endif
+        tile = s2_claim_get(next_raw);
     }
     s2_stage_drain();
+    s2_tiles_done(ts, ntiles);
 }
 
 // ---- pass 2: rows: FFT -> |.|^2 -> FFT (DIF) -> twiddle, in place ------------------------------------
@@ -238,8 +253,8 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
 // see spectrum2_kernel): MODE 1 = first window, rows FFT -> |X|^2 parked as REAL values in Sr (digit order);
 // MODE 2 = second window, rows FFT -> |X|^2, z = Sr + i |X|^2, FFT (DIF) -> twiddle -> A.
 template <class C, int MODE>
-__device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, double* __restrict__ Sr, int warp,
-                                      int lane) {
+__device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, double* __restrict__ Sr, S2Tiles& ts,
+                                      int warp, int lane) {
     S2_SMEM_HERE();
     const int n1 = p.pl.n1, n2 = p.pl.n2;
     const int seq = lane % C::NS, g = lane / C::NS;
@@ -247,7 +262,8 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
     cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n1 / C::NS;
     const int rp = S2RowPitch<C>::cplx_pitch(n2), rpd = S2RowPitch<C>::real_pitch(n2);
-    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
+    for (int tile = s2_claim_get(s2_claim_issue(ts, lane)); tile < ntiles;) {
+        const int next_raw = s2_claim_issue(ts, lane);
         const int row = tile * C::NS + seq;
         cplx* __restrict__ Ar = A + (size_t)row * n2;
         cplx v[16];
@@ -329,8 +345,10 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 #if !DP_S2_TMA
         __syncwarp();
 #endif
+        tile = s2_claim_get(next_raw);
     }
     s2_stage_drain();
+    s2_tiles_done(ts, ntiles);
 }
 
 // ---- pass 3: column FFTs -> conj -> lags 0..half of the autocorrelation, in place ------------------------
@@ -340,7 +358,7 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 // Only the rows that hold needed lags are written: rows [0, r_lo) and, PAIRED, rows [r_hi, n1) (whole rows of the
 // warp's own columns: the few extra elements of the boundary rows are never read).
 template <class C, bool PAIRED>
-__device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, int warp, int lane) {
+__device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, S2Tiles& ts, int warp, int lane) {
     S2_SMEM_HERE();
     const int n2 = p.pl.n2, half = p.pl.half;
     const double sc = p.acf_scale;
@@ -349,7 +367,8 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
     cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n2 / C::NS;
     const int r_lo = p.r_lo, r_hi = p.r_hi;
-    for (int tile = warp; tile < ntiles; tile += S2_WARPS) {
+    for (int tile = s2_claim_get(s2_claim_issue(ts, lane)); tile < ntiles;) {
+        const int next_raw = s2_claim_issue(ts, lane);
         const int col = tile * C::NS + seq;
         cplx v[16];
 #pragma unroll
@@ -385,8 +404,10 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, i
             bulk_commit();
         }
 #endif
+        tile = s2_claim_get(next_raw);
     }
     s2_stage_drain();
+    s2_tiles_done(ts, ntiles);
     (void)half;
 }
 
@@ -512,26 +533,26 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
 
 #define DP_S2_PASS1_L(xptr, t0v, LAY)                                               \
     switch (p.pl.n1) {                                                              \
-        case 16: s2_pass1<C16, LAY>(p, xptr, t0v, A, warp, lane); break;            \
-        case 32: s2_pass1<C32, LAY>(p, xptr, t0v, A, warp, lane); break;            \
-        case 64: s2_pass1<C64, LAY>(p, xptr, t0v, A, warp, lane); break;            \
-        case 128: s2_pass1<C128, LAY>(p, xptr, t0v, A, warp, lane); break;          \
-        default: s2_pass1<C256, LAY>(p, xptr, t0v, A, warp, lane); break;           \
+        case 16: s2_pass1<C16, LAY>(p, xptr, t0v, A, ts, warp, lane); break;            \
+        case 32: s2_pass1<C32, LAY>(p, xptr, t0v, A, ts, warp, lane); break;            \
+        case 64: s2_pass1<C64, LAY>(p, xptr, t0v, A, ts, warp, lane); break;            \
+        case 128: s2_pass1<C128, LAY>(p, xptr, t0v, A, ts, warp, lane); break;          \
+        default: s2_pass1<C256, LAY>(p, xptr, t0v, A, ts, warp, lane); break;           \
     }
 #define DP_S2_PASS1(xptr, t0v)                                                      \
     if (layout == 0) { DP_S2_PASS1_L(xptr, t0v, 0) }                                \
     else if (layout == 1) { DP_S2_PASS1_L(xptr, t0v, 1) }                           \
     else { DP_S2_PASS1_L(xptr, t0v, 2) }
 #define DP_S2_PASS2(MODE)                                                           \
-    if (p.pl.n2 == 64) s2_pass2<C64, MODE>(p, A, Sr, warp, lane);                   \
-    else s2_pass2<C256, MODE>(p, A, Sr, warp, lane);
+    if (p.pl.n2 == 64) s2_pass2<C64, MODE>(p, A, Sr, ts, warp, lane);                   \
+    else s2_pass2<C256, MODE>(p, A, Sr, ts, warp, lane);
 #define DP_S2_PASS3(PAIRED)                                                         \
     switch (p.pl.n1) {                                                              \
-        case 16: s2_pass3<C16, PAIRED>(p, A, warp, lane); break;                    \
-        case 32: s2_pass3<C32, PAIRED>(p, A, warp, lane); break;                    \
-        case 64: s2_pass3<C64, PAIRED>(p, A, warp, lane); break;                    \
-        case 128: s2_pass3<C128, PAIRED>(p, A, warp, lane); break;                  \
-        default: s2_pass3<C256, PAIRED>(p, A, warp, lane); break;                   \
+        case 16: s2_pass3<C16, PAIRED>(p, A, ts, warp, lane); break;                    \
+        case 32: s2_pass3<C32, PAIRED>(p, A, ts, warp, lane); break;                    \
+        case 64: s2_pass3<C64, PAIRED>(p, A, ts, warp, lane); break;                    \
+        case 128: s2_pass3<C128, PAIRED>(p, A, ts, warp, lane); break;                  \
+        default: s2_pass3<C256, PAIRED>(p, A, ts, warp, lane); break;                   \
     }
 
 // Items: (series, pair of consecutive windows).  Two windows of one series share everything after the
@@ -541,9 +562,14 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
 __global__ void __launch_bounds__(S2_THREADS, 1)
 spectrum2_kernel(const __grid_constant__ S2Params p) {
     S2_SMEM_HERE();
+    __shared__ int s2_tile_counter;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = tid; k < 6 * 256; k += S2_THREADS) sm.T1[k] = p.g_tables[k];
+    if (tid == 0) s2_tile_counter = 0;
     __syncthreads();
+    S2Tiles ts;
+    ts.counter = &s2_tile_counter;
+    ts.base = 0;
     cplx* A = p.scratch + (size_t)blockIdx.x * p.slab_elems;
     double* Sr = reinterpret_cast<double*>(A + p.pl.P);            // [P] real: |X_a|^2 of a pair's first window
     const int layout = p.stride_t != 1 ? 2 : (p.tb_len == 0 ? 0 : (p.tb_shift >= 0 ? 1 : 2));
@@ -555,15 +581,9 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
         const bool paired = p.pair && (w0 + 1 < p.w_first + p.w_count);
         const cplx* x = p.series + (int64_t)s * p.stride_s;
         double* spec = p.spec + ((size_t)s * p.npieces + w0) * p.nkeep;
-        // the next item's first window starts its way from HBM to L2 (time-contiguous layouts only)
-        auto prefetch_next = [&]() {
-            if (item + gridDim.x < nitems && p.stride_t == 1) {
-                const int64_t nxt = item + gridDim.x;
-                const cplx* xn = p.series + (int64_t)(nxt % p.S) * p.stride_s;
-                const int tn = p.starts[p.w_first + (p.pair ? 2 * (int)(nxt / p.S) : (int)(nxt / p.S))];
-                for (int i = tid * 8; i < p.pl.L; i += S2_THREADS * 8) s2_prefetch_l2(xn + s2_time_offset(p, tn + i));
-            }
-        };
+        // (No explicit L2 prefetch of the coming windows: both per-line prefetch.global.L2 and evict-first bulk prefetches
+        // were measured to HURT -- 5.66 -> 5.39 ms per 1480 series without them -- because the 148 slabs already fill the
+        // L2 and every prefetched window evicts slab lines of some CTA.)
         if (!paired) {
             if (!(p.skip_mask & 1)) { DP_S2_PASS1(x, p.starts[w0]) }
             __syncthreads();
@@ -571,7 +591,6 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
             __syncthreads();
             if (!(p.skip_mask & 4)) { DP_S2_PASS3(false) }
             __syncthreads();
-            prefetch_next();
             if (!(p.skip_mask & 8)) switch (p.pl.m1 * 32 + p.pl.m2) {
 #define DP_S2_CASE(a, b) case (a) * 32 + (b): s2_pass4<SubCfg<a, b, 16>, false>(p, A, spec, tid); break;
                 DP_S2_MIXED_MENU(DP_S2_CASE)
@@ -581,9 +600,6 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
         } else {
             if (!(p.skip_mask & 1)) { DP_S2_PASS1(x, p.starts[w0]) }
             __syncthreads();
-            // the pair's second window is needed right after this pass: bring it to L2 now
-            if (p.stride_t == 1)
-                for (int i = tid * 8; i < p.pl.L; i += S2_THREADS * 8) s2_prefetch_l2(x + s2_time_offset(p, p.starts[w0 + 1] + i));
             if (!(p.skip_mask & 2)) { DP_S2_PASS2(1) }
             __syncthreads();
             if (!(p.skip_mask & 1)) { DP_S2_PASS1(x, p.starts[w0 + 1]) }
@@ -592,7 +608,6 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
             __syncthreads();
             if (!(p.skip_mask & 4)) { DP_S2_PASS3(true) }
             __syncthreads();
-            prefetch_next();
             if (!(p.skip_mask & 8)) switch (p.pl.m1 * 32 + p.pl.m2) {
 #define DP_S2_CASE(a, b) case (a) * 32 + (b): s2_pass4<SubCfg<a, b, 16>, true>(p, A, spec, tid); break;
                 DP_S2_MIXED_MENU(DP_S2_CASE)

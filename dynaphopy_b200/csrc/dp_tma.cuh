@@ -124,6 +124,18 @@ template <int N> __device__ __forceinline__ void bulk_wait() {
 #endif
 }
 
+// bring [src, src + bytes) into L2 ahead of its use (bytes a multiple of 16) with evict-first priority: the lines are
+// used once, soon, and must not displace longer-lived data
+__device__ __forceinline__ void bulk_prefetch_l2_evict_first(const void* src, unsigned bytes) {
+#ifndef DP_EMUL
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;\n" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+#else
+    (void)src; (void)bytes;
+#endif
+}
+
 // ---- 2-D tensor boxes: shared-memory tile is dense, [box_rows][box_inner] doubles ----------------------------------
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const TensorMap2D* tm, int c_inner, int c_row, mbar_t* b) {
 #ifdef DP_EMUL

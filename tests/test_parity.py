@@ -535,6 +535,25 @@ def test_power_fft_series_major_and_time_blocks(kops):
     assert np.array_equal(a, b) and np.array_equal(a, c)
 
 
+@pytest.mark.parametrize("nt,dt,res", [(4096, 0.002, 0.5), (8192, 0.001, 1.0 / 3.0), (2048, 0.002, 2.0)])
+def test_power_fft_series_rows_as_tensor_boxes(kops, nt, dt, res):
+    """Series-major input whose rows start on multiples of the row length of the padded transform: pass 1 fetches its
+    window tiles as boxes of the series tensor (bulk copies); every window start (any offset inside a row), the last
+    window touching the end of the array, and the result identical to the per-lane load path of the (T, S) layout."""
+    rng = np.random.default_rng(nt)
+    ns = 3
+    x = _series(rng, nt, ns, dt)
+    f = np.arange(0, 30.0, res)
+    L, pieces = kops.fft_pieces(nt, dt, f)
+    assert len(pieces) >= 2 and any(p[0] % 64 for p in pieces)
+    ref = port.fft_spectra(x, dt, f)
+    a = to_np(kops.power_fft(x, dt, f))
+    b = to_np(kops.power_fft(np.ascontiguousarray(x.T), dt, f, series_major=True))
+    assert relerr(a, ref) < TOL and relerr(b, ref) < TOL
+    assert np.array_equal(a, b)
+    assert np.array_equal(b.argmax(0), ref.argmax(0))
+
+
 def test_power_fft_incremental_windows(kops):
     """dp_power_fft_windows / dp_power_fft_finish: windows transformed in several calls (any split, even while
     later samples are still garbage) give exactly the one-shot spectrum."""
