@@ -284,7 +284,8 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
     l.nslots = (int)imin<int64_t>(items, (int64_t)imax(sm_count(), 1));
     if (dev_env("DP_S2_GRID") && atoi(dev_env("DP_S2_GRID")) > 0)      // development aid: fewer persistent CTAs
         l.nslots = (int)imin<int64_t>(l.nslots, atoi(dev_env("DP_S2_GRID")));
-    l.slab_elems = pl.use_v2 ? (size_t)pl.P + (size_t)pl.P / 2 : (size_t)pl.P + pl.L;   // v2: A[P] complex + Sr[P] real
+    // v2: A[P] complex (+ Sr[P] real when |X_a|^2 of a window pair cannot be parked in the SM's 256 KB of tensor memory)
+    l.slab_elems = pl.use_v2 ? (size_t)pl.P + (s2_parks_in_tmem(pl.s2) ? 0 : (size_t)pl.P / 2) : (size_t)pl.P + pl.L;
     l.off_scratch = o; o += align_up((size_t)l.nslots * l.slab_elems * sizeof(cplx), 256);
     l.total = o;
     return l;
@@ -397,6 +398,9 @@ int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_
                                         (uint32_t)dp::imax(1, n1 - p.r_hi));
             if (rc) return rc;
         }
+        p.park = dp::s2_parks_in_tmem(pl.s2) ? 1 : 0;
+        p.park_cols = 32;
+        while (p.park_cols < pl.s2.P / 64) p.park_cols *= 2;       // P doubles over 128 lanes: P / 128 * 2 columns
         p.skip_mask = dp::dev_env("DP_S2_SKIP") ? atoi(dp::dev_env("DP_S2_SKIP")) : 0;
         p.pair = (n_windows >= 2 && !(dp::dev_env("DP_S2_PAIR") && atoi(dp::dev_env("DP_S2_PAIR")) == 0)) ? 1 : 0;
         auto k = dp::spectrum2_kernel;

@@ -17,6 +17,7 @@
 
 #include "dp_fft_reg.cuh"
 #include "dp_tma.cuh"
+#include "dp_tmem.cuh"
 
 namespace dp {
 
@@ -70,6 +71,7 @@ struct S2Params {
     // boxes of one warp tile (2*NS doubles wide): n1 rows (pass 1), the r_lo first / n1 - r_hi last rows (pass 3)
     int slab_rows, r_lo, r_hi;
     TensorMap2D tm_col, tm_lo, tm_hi;
+    int park, park_cols;           // |X_a|^2 parked in tensor memory (park_cols columns allocated) instead of the slab
 };
 
 struct S2Smem {
@@ -88,9 +90,6 @@ struct S2Smem {
 // passes) drain at the SM's L2 write rate (~26 B/clk) and the next tile's loads queue up behind them.  Stores now
 // leave through the bulk-copy engine (dp_tma.cuh): a tile is written to the warp's staging area in shared memory
 // (conflict-free STS) and ONE elected lane issues a tensor-box / bulk store; the load/store unit sees loads only.
-#ifndef DP_S2_TMA
-#define DP_S2_TMA 1
-#endif
 constexpr size_t S2_E_ELEMS = S2_WARPS * SUBFFT_EWARP_MAX > 2 * S2_NP_MAX * S2_CPITCH ? S2_WARPS * SUBFFT_EWARP_MAX
                                                                                   : 2 * S2_NP_MAX * S2_CPITCH;
 constexpr size_t S2_SMEM_BYTES = (size_t)(6 * 256 + S2_E_ELEMS) * sizeof(cplx);
@@ -146,29 +145,23 @@ __device__ __forceinline__ int s2_claim_issue(const S2Tiles& ts, int lane) {
 __device__ __forceinline__ int s2_claim_get(int raw) { return __shfl_sync(0xffffffffu, raw, 0); }
 __device__ __forceinline__ void s2_tiles_done(S2Tiles& ts, int ntiles) { ts.base += ntiles + S2_WARPS; }   // one claim beyond the end per warp
 
-// ---- staging-tile protocol of one warp (DP_S2_TMA) -------------------------------------------------------------
+// ---- staging-tile protocol of one warp -------------------------------------------------------------
 // The staging tile shares the warp's exchange slab E: (1) before the first write to E of a tile, the bulk stores of the
 // previous tile must have finished reading it: s2_stage_acquire; (2) after the last exchange read, a warp barrier, then
 // the results are written to E in the tile layout; (3) s2_stage_publish orders those writes before the asynchronous
 // proxy; the elected lanes then issue their stores and commit.  s2_stage_drain at the end of a pass: the global writes
 // are complete (and ordered before the ordinary loads of the next pass, after the CTA barrier that follows).
 __device__ __forceinline__ void s2_stage_acquire() {
-#if DP_S2_TMA
     bulk_wait_read<0>();          // lanes that issued nothing return at once
     __syncwarp();
-#endif
 }
 __device__ __forceinline__ void s2_stage_publish() {
-#if DP_S2_TMA
     fence_proxy_async_smem();
     __syncwarp();
-#endif
 }
 __device__ __forceinline__ void s2_stage_drain() {
-#if DP_S2_TMA
     bulk_wait<0>();
     fence_proxy_async();
-#endif
 }
 // row pitch (in elements of 16 / 8 bytes) of a staged ROW tile of NS rows: spreads the rows of a quarter-/half-warp
 // over the shared-memory bank groups (same rule as SubCfg::ESEQ)
@@ -213,9 +206,7 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
             }
         s2_stage_acquire();
         sub_dit<C>(v, E, sm.T1, g);
-#if DP_S2_TMA
         __syncwarp();                 // every lane has read its exchange values: E becomes the staging tile [n1][NS]
-#endif
         // four-step twiddle w_P^(col*kk), kk = k1 + R1*k2: geometric in k2
         const cplx ratio = tw2level(sm.fine, sm.coarse, col * C::R1);
 #pragma unroll
@@ -225,23 +216,15 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
 #pragma unroll
             for (int k2 = 0; k2 < C::R2; k2++) {
                 const cplx val = cmul(v[i * C::R2 + k2], tw);
-#if DP_S2_TMA
                 Ew[(k1 + C::R1 * k2) * C::NS + seq] = val;
-#else
-                s2_st_slab(A + (size_t)(k1 + C::R1 * k2) * n2 + col, val);
-#endif
                 if (k2 + 1 < C::R2) tw = cmul(tw, ratio);
             }
         }
-#if DP_S2_TMA
         s2_stage_publish();
         if (lane == 0) {
             tma_store_2d(&p.tm_col, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows), Ew);
             bulk_commit();
         }
-#else
-        __syncwarp();
-#endif
         tile = s2_claim_get(next_raw);
     }
     s2_stage_drain();
@@ -252,9 +235,14 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
 // MODE 0: single window.  Paired windows (two windows of one series share the second half of the pipeline,
 // see spectrum2_kernel): MODE 1 = first window, rows FFT -> |X|^2 parked as REAL values in Sr (digit order);
 // MODE 2 = second window, rows FFT -> |X|^2, z = Sr + i |X|^2, FFT (DIF) -> twiddle -> A.
-template <class C, int MODE>
+// PARK: |X_a|^2 waits in tensor memory (dp_tmem.cuh) instead of Sr: the thread that produced the 16 values of a tile in
+// MODE 1 is the one that consumes them in MODE 2 (static tile -> warp assignment in those two modes; warp % 4 is the
+// TMEM lane quarter, so S2_WARPS must be a multiple of 4; tile t uses columns 32 * (t / 4) of quarter t % 4).  The slab
+// shrinks from 1.5 P to P elements -- 148 x 512 KB at cfg 5-A, which the 126 MB L2 holds.
+template <class C, int MODE, bool PARK>
 __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, double* __restrict__ Sr, S2Tiles& ts,
-                                      int warp, int lane) {
+                                      uint32_t tmem, int warp, int lane) {
+    static_assert(!PARK || S2_WARPS % 4 == 0, "TMEM parking maps tile % 4 to the warp's lane quarter");
     S2_SMEM_HERE();
     const int n1 = p.pl.n1, n2 = p.pl.n2;
     const int seq = lane % C::NS, g = lane / C::NS;
@@ -262,8 +250,9 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
     cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n1 / C::NS;
     const int rp = S2RowPitch<C>::cplx_pitch(n2), rpd = S2RowPitch<C>::real_pitch(n2);
-    for (int tile = s2_claim_get(s2_claim_issue(ts, lane)); tile < ntiles;) {
-        const int next_raw = s2_claim_issue(ts, lane);
+    constexpr bool STATIC = PARK && MODE != 0;
+    for (int tile = STATIC ? warp : s2_claim_get(s2_claim_issue(ts, lane)); tile < ntiles;) {
+        const int next_raw = STATIC ? 0 : s2_claim_issue(ts, lane);
         const int row = tile * C::NS + seq;
         cplx* __restrict__ Ar = A + (size_t)row * n2;
         cplx v[16];
@@ -272,40 +261,46 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 #pragma unroll
             for (int a = 0; a < C::R1; a++) v[i * C::R1 + a] = s2_ld_slab(Ar + a * C::R2 + g + C::TG * i);
         double sa[16];
+        uint32_t parked[32];
         double* __restrict__ Srow = Sr + (size_t)row * n2;
         if (MODE == 2) {                       // |X_a|^2 of the partner window, requested before the butterflies
+            if (PARK) tmem_fetch16(tmem, warp, lane, 32 * (tile >> 2), parked);
+            else {
 #pragma unroll
-            for (int i = 0; i < C::NB2; i++)
+                for (int i = 0; i < C::NB2; i++)
 #pragma unroll
-                for (int k2 = 0; k2 < C::R2; k2++) sa[i * C::R2 + k2] = __ldcg(Srow + g + C::TG * i + C::R1 * k2);
+                    for (int k2 = 0; k2 < C::R2; k2++) sa[i * C::R2 + k2] = __ldcg(Srow + g + C::TG * i + C::R1 * k2);
+            }
         }
         s2_stage_acquire();
         sub_dit<C>(v, E, sm.T2, g);
-        if constexpr (MODE == 1) {
-#if DP_S2_TMA
+        if constexpr (MODE == 1 && PARK) {
+            double pw[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) pw[r] = v[r].x * v[r].x + v[r].y * v[r].y;
+            tmem_park16(tmem, warp, lane, 32 * (tile >> 2), pw);
+        } else if constexpr (MODE == 1) {
             __syncwarp();             // exchange reads done: E becomes the staging tile, NS rows of n2 doubles
             double* Sw = reinterpret_cast<double*>(Ew) + (size_t)seq * rpd;
-#endif
 #pragma unroll
             for (int i = 0; i < C::NB2; i++)
 #pragma unroll
                 for (int k2 = 0; k2 < C::R2; k2++) {
                     const cplx x = v[i * C::R2 + k2];
-#if DP_S2_TMA
                     Sw[g + C::TG * i + C::R1 * k2] = x.x * x.x + x.y * x.y;
-#else
-                    __stcg(Srow + g + C::TG * i + C::R1 * k2, x.x * x.x + x.y * x.y);
-#endif
                 }
-#if DP_S2_TMA
             s2_stage_publish();
             if (lane < C::NS) {       // lane s ships row s of the tile: n2 contiguous doubles
                 bulk_s2g(Sr + (size_t)(tile * C::NS + lane) * n2, reinterpret_cast<double*>(Ew) + (size_t)lane * rpd,
                          (unsigned)(n2 * sizeof(double)));
                 bulk_commit();
             }
-#endif
         } else {
+            if (MODE == 2 && PARK) {
+                tmem_fetch_wait();
+#pragma unroll
+                for (int r = 0; r < 16; r++) sa[r] = tmem_value(parked, r);
+            }
 #pragma unroll
             for (int r = 0; r < C::NB2 * C::R2; r++) {
                 const double sb = v[r].x * v[r].x + v[r].y * v[r].y;
@@ -313,10 +308,8 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
             }
             __syncwarp();
             sub_dif<C>(v, E, sm.T2f, g);
-#if DP_S2_TMA
             __syncwarp();             // exchange reads done: E becomes the staging tile, NS rows of n2 complex values
             cplx* Ow = Ew + (size_t)seq * rp;
-#endif
             // four-step twiddle w_P^(row*k), k = d*R2 + c: geometric in d
             const cplx ratio = tw2level(sm.fine, sm.coarse, row * C::R2);
 #pragma unroll
@@ -326,29 +319,21 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
 #pragma unroll
                 for (int d = 0; d < C::R1; d++) {
                     const cplx val = cmul(v[i * C::R1 + d], tw);
-#if DP_S2_TMA
                     Ow[d * C::R2 + c] = val;
-#else
-                    s2_st_slab(Ar + d * C::R2 + c, val);
-#endif
                     if (d + 1 < C::R1) tw = cmul(tw, ratio);
                 }
             }
-#if DP_S2_TMA
             s2_stage_publish();
             if (lane < C::NS) {
                 bulk_s2g(A + (size_t)(tile * C::NS + lane) * n2, Ew + (size_t)lane * rp, (unsigned)(n2 * sizeof(cplx)));
                 bulk_commit();
             }
-#endif
         }
-#if !DP_S2_TMA
-        __syncwarp();
-#endif
-        tile = s2_claim_get(next_raw);
+        tile = STATIC ? tile + S2_WARPS : s2_claim_get(next_raw);
     }
+    if (MODE == 1 && PARK) tmem_park_wait();
     s2_stage_drain();
-    s2_tiles_done(ts, ntiles);
+    if (!STATIC) s2_tiles_done(ts, ntiles);
 }
 
 // ---- pass 3: column FFTs -> conj -> lags 0..half of the autocorrelation, in place ------------------------
@@ -383,27 +368,15 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, S
 #pragma unroll
             for (int k2 = 0; k2 < C::R2; k2++) {
                 const int row = g + C::TG * i + C::R1 * k2;
-#if DP_S2_TMA
                 if (row < r_lo || (PAIRED && row >= r_hi))
                     Ew[row * C::NS + seq] = make_double2(v[i * C::R2 + k2].x * sc, PAIRED ? v[i * C::R2 + k2].y * sc : -v[i * C::R2 + k2].y * sc);
-#else
-                const int kap = row * n2 + col;
-                if (PAIRED) {
-                    if (kap <= half || kap >= p.pl.P - half)
-                        s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, v[i * C::R2 + k2].y * sc));
-                } else if (kap <= half) {
-                    s2_st_slab(A + kap, make_double2(v[i * C::R2 + k2].x * sc, -v[i * C::R2 + k2].y * sc));
-                }
-#endif
             }
-#if DP_S2_TMA
         s2_stage_publish();
         if (lane == 0) {
             tma_store_2d(&p.tm_lo, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows), Ew);
             if (PAIRED) tma_store_2d(&p.tm_hi, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows) + r_hi, Ew + (size_t)r_hi * C::NS);
             bulk_commit();
         }
-#endif
         tile = s2_claim_get(next_raw);
     }
     s2_stage_drain();
@@ -543,9 +516,14 @@ __device__ __noinline__ void s2_pass4(const S2Params& p, const cplx* __restrict_
     if (layout == 0) { DP_S2_PASS1_L(xptr, t0v, 0) }                                \
     else if (layout == 1) { DP_S2_PASS1_L(xptr, t0v, 1) }                           \
     else { DP_S2_PASS1_L(xptr, t0v, 2) }
-#define DP_S2_PASS2(MODE)                                                           \
-    if (p.pl.n2 == 64) s2_pass2<C64, MODE>(p, A, Sr, ts, warp, lane);                   \
-    else s2_pass2<C256, MODE>(p, A, Sr, ts, warp, lane);
+#define DP_S2_PASS2(MODE)                                                                   \
+    if (p.park) {                                                                           \
+        if (p.pl.n2 == 64) s2_pass2<C64, MODE, true>(p, A, Sr, ts, tmem_base, warp, lane);  \
+        else s2_pass2<C256, MODE, true>(p, A, Sr, ts, tmem_base, warp, lane);               \
+    } else {                                                                                \
+        if (p.pl.n2 == 64) s2_pass2<C64, MODE, false>(p, A, Sr, ts, 0u, warp, lane);        \
+        else s2_pass2<C256, MODE, false>(p, A, Sr, ts, 0u, warp, lane);                     \
+    }
 #define DP_S2_PASS3(PAIRED)                                                         \
     switch (p.pl.n1) {                                                              \
         case 16: s2_pass3<C16, PAIRED>(p, A, ts, warp, lane); break;                    \
@@ -563,10 +541,13 @@ __global__ void __launch_bounds__(S2_THREADS, 1)
 spectrum2_kernel(const __grid_constant__ S2Params p) {
     S2_SMEM_HERE();
     __shared__ int s2_tile_counter;
+    __shared__ uint32_t s2_tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int k = tid; k < 6 * 256; k += S2_THREADS) sm.T1[k] = p.g_tables[k];
     if (tid == 0) s2_tile_counter = 0;
-    __syncthreads();
+    if (p.park && warp == 0) tmem_alloc(&s2_tmem_slot, (uint32_t)p.park_cols);
+    tmem_alloc_done();             // includes the CTA barrier
+    const uint32_t tmem_base = p.park ? s2_tmem_slot : 0u;
     S2Tiles ts;
     ts.counter = &s2_tile_counter;
     ts.base = 0;
@@ -617,6 +598,7 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
         }
         __syncthreads();
     }
+    if (p.park && warp == 0) tmem_free(tmem_base, (uint32_t)p.park_cols);      // every TMEM access precedes the barrier above
 }
 #undef DP_S2_PASS1
 #undef DP_S2_PASS1_L
@@ -662,6 +644,16 @@ static bool make_s2_plan(int L, int nkeep, S2Plan* pl) {
     // cost of the transforms themselves
     if ((double)nkeep * pl->n2L > 12.0 * (double)L) return false;
     return true;
+}
+
+// |X_a|^2 of a window pair (P doubles) fits the SM's tensor memory (128 lanes x 512 columns x 4 bytes)
+static inline bool s2_parks_in_tmem(const S2Plan& pl) {
+#ifdef DP_S2_NO_PARK
+    (void)pl;
+    return false;
+#else
+    return S2_WARPS % 4 == 0 && (size_t)pl.P * sizeof(double) <= 256 * 1024;
+#endif
 }
 
 // tables (256 entries each): T1, T2, T2f, Ts, fine, coarse -- see S2Smem
