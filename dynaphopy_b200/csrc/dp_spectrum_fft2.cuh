@@ -562,9 +562,10 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
         const bool paired = p.pair && (w0 + 1 < p.w_first + p.w_count);
         const cplx* x = p.series + (int64_t)s * p.stride_s;
         double* spec = p.spec + ((size_t)s * p.npieces + w0) * p.nkeep;
-        // (No explicit L2 prefetch of the coming windows: both per-line prefetch.global.L2 and evict-first bulk prefetches
-        // were measured to HURT -- 5.66 -> 5.39 ms per 1480 series without them -- because the 148 slabs already fill the
-        // L2 and every prefetched window evicts slab lines of some CTA.)
+        // (No explicit L2 prefetch of the coming windows.  Per-line prefetch.global.L2 and bulk prefetches, with normal
+        // and with evict-first priority, one or two passes ahead, were all measured to HURT -- 5.66 -> 5.39 ms per 1480
+        // series without them at 114 MB of slabs, 4.83 -> 5.11 ms with them at 76 MB: the slabs, dirty all the time and
+        // partly mirrored in the far L2 partition, fill the L2 and every prefetched window evicts lines of some CTA.)
         if (!paired) {
             if (!(p.skip_mask & 1)) { DP_S2_PASS1(x, p.starts[w0]) }
             __syncthreads();

@@ -136,6 +136,15 @@ __device__ __forceinline__ void bulk_prefetch_l2_evict_first(const void* src, un
 #endif
 }
 
+// bring [src, src + bytes) into L2 ahead of its use (bytes a multiple of 16), normal priority
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+#ifndef DP_EMUL
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
+#else
+    (void)src; (void)bytes;
+#endif
+}
+
 // ---- 2-D tensor boxes: shared-memory tile is dense, [box_rows][box_inner] doubles ----------------------------------
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const TensorMap2D* tm, int c_inner, int c_row, mbar_t* b) {
 #ifdef DP_EMUL
