@@ -3,8 +3,8 @@
 //
 // Dense projection = real(3T x N) x complex(N x Q) contraction per primitive type; the
 // phases exp(-i q.r_i) * sqrt(m_i) / sqrt(N/n_p) are tabulated once per call (Q x N), the
-// main kernel stages frame and phase tiles in shared memory and keeps 3 complex
-// accumulators per (frame, q) in registers.  Bound: fp64 FMA (12 flop per atom-frame-q).
+// main kernel is a tensor-core GEMM (mma.sync m8n8k4 f64 = DMMA, see project_dense_kernel).
+// Bound: fp64 (12 flop per atom-frame-q).
 // The commensurate fast path (3-D DFT, HBM-bound) lives in dp_projection_fft.cu.
 #include <algorithm>
 #include <vector>
@@ -34,69 +34,142 @@ phase_table_kernel(const double* __restrict__ q_cart, const double* __restrict__
     }
 }
 
-constexpr int PJ_TQ = 32;   // q per CTA (threadIdx.x)
-constexpr int PJ_TT = 8;    // frames per CTA (threadIdx.y)
-constexpr int PJ_AC = 32;   // atoms per shared-memory chunk
+// ---- dense projection as a tensor-core GEMM (DMMA) ------------------------------------------------------------
+// Per primitive type p:  C[(k, t), (q, re|im)] = sum_a V[(k, t), a] * Ph[a, (q, re|im)]  -- a real (3T x N_p) times
+// real (N_p x 2Q) product in fp64, computed with mma.sync.aligned.m8n8k4.f64 (SASS: DMMA.8x8x4).  Complex velocities
+// double the contraction length: A' = [Re V | Im V], B' = [[Pr, Pi], [-Pi, Pr]].
+// CTA = 16 warps, tile PJ_F frames x 3 components (96 rows, row = k * PJ_F + frame) by PJ_Q wave vectors (128 columns,
+// column = 2 q + re|im); warp tile 24 x 32 = 3 x 4 fragments of 8 x 8 (24 fp64 accumulators per thread).  The atoms are
+// consumed in chunks of PJ_KA atoms staged in shared memory -- A as [row][step], B TRANSPOSED as [column][step], both
+// with a row pitch of 4 (mod 16) doubles, so that every fragment load and every staging store of a warp is conflict
+// free and both global reads are coalesced (consecutive threads: consecutive components / atoms of one frame,
+// consecutive atoms of one wave vector).  The next chunk travels global -> registers while the current one is multiplied.
+constexpr int PJ_F = 32;     // frames per CTA
+constexpr int PJ_Q = 64;     // wave vectors per CTA
+constexpr int PJ_KA = 32;    // atoms per chunk
+constexpr int PJ_THREADS = 512;
+constexpr int PJ_ROWS = 3 * PJ_F, PJ_COLS = 2 * PJ_Q;
+template <int NC> struct PjCfg {
+    static constexpr int KC = PJ_KA * NC;                 // contraction steps (doubles per row) per chunk
+    static constexpr int PITCH = KC + 4;                  // shared-memory pitch of As and Bt rows (doubles)
+    static constexpr int NA = PJ_F * PJ_KA * 3 * NC / PJ_THREADS;       // staged doubles of A per thread
+    static constexpr int NB = PJ_Q * PJ_KA / PJ_THREADS;                // staged phases (complex) per thread
+    static constexpr size_t SMEM = (size_t)(PJ_ROWS + PJ_COLS) * PITCH * sizeof(double) + PJ_KA * sizeof(int);
+};
+
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+#ifdef DP_EMUL
+    (void)c; (void)a; (void)b;      // the emulated kernel below does not use fragments
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+#endif
+}
 
 template <int NC>   // 1: real velocities, 2: complex128 velocities
-__global__ void __launch_bounds__(PJ_TQ* PJ_TT)
+__global__ void __launch_bounds__(PJ_THREADS, 1)
 project_dense_kernel(const double* __restrict__ v, const cplx* __restrict__ ph,
                      const int* __restrict__ atom_list, const int* __restrict__ type_off, int N,
                      int n_prim, int64_t T, int Q, int p_first, int p_last, cplx* __restrict__ out) {
-    __shared__ double vs[PJ_TT][PJ_AC][3 * NC];
-    __shared__ cplx phs[PJ_AC][PJ_TQ + 1];
-    const int tq = threadIdx.x, tt = threadIdx.y;
-    const int lin = tt * PJ_TQ + tq;
-    const int64_t t0 = (int64_t)blockIdx.x * PJ_TT;
-    const int q0 = blockIdx.y * PJ_TQ;
-    const int64_t t = t0 + tt;
-    const int q = q0 + tq;
+    typedef PjCfg<NC> Cfg;
+    constexpr int KC = Cfg::KC, PITCH = Cfg::PITCH;
+    DP_DYNSMEM(double, pj_smem);                       // As[PJ_ROWS][PITCH] | Bt[PJ_COLS][PITCH] | atoms[PJ_KA]
+    double* As = pj_smem;
+    double* Bt = pj_smem + PJ_ROWS * PITCH;
+    int* atoms = reinterpret_cast<int*>(pj_smem + (PJ_ROWS + PJ_COLS) * PITCH);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * PJ_F;
+    const int q0 = blockIdx.y * PJ_Q;
+    const int wr = (warp >> 2) * 24, wc = (warp & 3) * 32;       // warp tile origin
     for (int p = p_first; p <= p_last; p++) {
-        cplx acc[3];
-        acc[0] = acc[1] = acc[2] = make_double2(0.0, 0.0);
         const int a_begin = type_off[p], a_end = type_off[p + 1];
-        for (int a0 = a_begin; a0 < a_end; a0 += PJ_AC) {
-            const int na = imin(PJ_AC, a_end - a0);
-            __syncthreads();
-            for (int e = lin; e < PJ_TT * PJ_AC * 3 * NC; e += PJ_TQ * PJ_TT) {
-                int ft = e / (PJ_AC * 3 * NC), rem = e % (PJ_AC * 3 * NC);
-                int aa = rem / (3 * NC), kk = rem % (3 * NC);
+        const int natoms = a_end - a_begin;
+        double acc[3][4][2];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        double ra[Cfg::NA];
+        cplx rb[Cfg::NB];
+        // A: element e -> frame f = e / (KA*3*NC), then (atom, component k, re|im) fastest: the three (six) doubles of
+        // an atom are adjacent in global memory.  B: element e -> wave vector e / KA, atom e % KA.
+        auto fetch = [&](int a0) {
+#pragma unroll
+            for (int i = 0; i < Cfg::NA; i++) {
+                const int e = tid + i * PJ_THREADS, f = e / (PJ_KA * 3 * NC), r = e % (PJ_KA * 3 * NC);
+                const int a = r / (3 * NC), kc = r % (3 * NC);
                 double val = 0.0;
-                if (aa < na && t0 + ft < T) {
-                    int i = atom_list[a0 + aa];
-                    val = __ldg(v + ((t0 + ft) * N + i) * (3 * NC) + kk);
-                }
-                vs[ft][aa][kk] = val;
+                if (a0 + a < natoms && t0 + f < T)
+                    val = __ldg(v + ((t0 + f) * N + __ldg(atom_list + a_begin + a0 + a)) * (3 * NC) + kc);
+                ra[i] = val;
             }
-            for (int e = lin; e < PJ_AC * PJ_TQ; e += PJ_TQ * PJ_TT) {
-                int fq = e / PJ_AC, aa = e % PJ_AC;
-                cplx w = make_double2(0.0, 0.0);
-                if (aa < na && q0 + fq < Q) w = ph[(int64_t)(q0 + fq) * N + a0 + aa];
-                phs[aa][fq] = w;
+#pragma unroll
+            for (int i = 0; i < Cfg::NB; i++) {
+                const int e = tid + i * PJ_THREADS, q = q0 + e / PJ_KA, a = e % PJ_KA;
+                rb[i] = (a0 + a < natoms && q < Q) ? __ldg(ph + (int64_t)q * N + a_begin + a0 + a) : make_double2(0.0, 0.0);
             }
+        };
+        auto stash = [&]() {
+#pragma unroll
+            for (int i = 0; i < Cfg::NA; i++) {
+                const int e = tid + i * PJ_THREADS, f = e / (PJ_KA * 3 * NC), r = e % (PJ_KA * 3 * NC);
+                const int a = r / (3 * NC), kc = r % (3 * NC), k = kc / NC, c = kc % NC;
+                As[(k * PJ_F + f) * PITCH + a * NC + c] = ra[i];
+            }
+#pragma unroll
+            for (int i = 0; i < Cfg::NB; i++) {
+                const int e = tid + i * PJ_THREADS, ql = e / PJ_KA, a = e % PJ_KA;
+                double* b0 = Bt + (2 * ql) * PITCH + a * NC;       // column (q, re), then (q, im) one pitch further
+                if (NC == 1) { b0[0] = rb[i].x; b0[PITCH] = rb[i].y; }
+                else { b0[0] = rb[i].x; b0[1] = -rb[i].y; b0[PITCH] = rb[i].y; b0[PITCH + 1] = rb[i].x; }
+            }
+        };
+        fetch(0);
+        for (int a0 = 0; a0 < natoms; a0 += PJ_KA) {
+            __syncthreads();                       // the previous chunk has been consumed
+            stash();
             __syncthreads();
-#pragma unroll 4
-            for (int aa = 0; aa < PJ_AC; aa++) {
-                cplx w = phs[aa][tq];
+            if (a0 + PJ_KA < natoms) fetch(a0 + PJ_KA);       // next chunk in flight underneath the multiplications
+#ifdef DP_EMUL
+            // host emulation (tests only): the same tile product without tensor-core fragments; thread (lane, warp)
+            // owns the accumulator entries the DMMA layout gives it
 #pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    if (NC == 1) {
-                        double x = vs[tt][aa][k];
-                        acc[k].x = fma(x, w.x, acc[k].x);
-                        acc[k].y = fma(x, w.y, acc[k].y);
-                    } else {
-                        double xr = vs[tt][aa][2 * k], xi = vs[tt][aa][2 * k + 1];
-                        acc[k].x = fma(xr, w.x, fma(-xi, w.y, acc[k].x));
-                        acc[k].y = fma(xr, w.y, fma(xi, w.x, acc[k].y));
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    for (int kk = 0; kk < KC; kk++) {
+                        const double a = As[(wr + i * 8 + lane / 4) * PITCH + kk];
+                        acc[i][j][0] += a * Bt[(wc + j * 8 + 2 * (lane % 4)) * PITCH + kk];
+                        acc[i][j][1] += a * Bt[(wc + j * 8 + 2 * (lane % 4) + 1) * PITCH + kk];
                     }
-                }
-            }
-        }
-        if (t < T && q < Q) {
+#else
 #pragma unroll
-            for (int k = 0; k < 3; k++) out[((t * Q + q) * n_prim + p) * 3 + k] = acc[k];
+            for (int ks = 0; ks < KC / 4; ks++) {
+                double fa[3], fb[4];
+#pragma unroll
+                for (int i = 0; i < 3; i++) fa[i] = As[(wr + i * 8 + lane / 4) * PITCH + ks * 4 + lane % 4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) fb[j] = Bt[(wc + j * 8 + lane / 4) * PITCH + ks * 4 + lane % 4];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma_884(acc[i][j], fa[i], fb[j]);
+            }
+#endif
+        }
+        // accumulator (row, col) = (wr + 8 i + lane / 4, wc + 8 j + 2 (lane % 4) + {0, 1}): one complex value per register pair
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int row = wr + i * 8 + lane / 4, k = row / PJ_F;
+            const int64_t t = t0 + row % PJ_F;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q = q0 + ((wc + j * 8) >> 1) + lane % 4;
+                if (t < T && q < Q) out[((t * Q + q) * n_prim + p) * 3 + k] = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
         }
     }
+    (void)atoms;
 }
 
 // vq[t,q,s] = sum_p ( sum_k vc[t,q,p,k] conj(e[q,s,p,k]) ): CTA = one q, PH_TF frames.
@@ -308,15 +381,17 @@ int dp_project_wave_vector(const double* v, int v_is_complex, const double* sqrt
         DP_CUDA_OK(cudaMemsetAsync(out_vc, 0, (size_t)T * Q * n_prim * 3 * sizeof(dp::cplx), st));
         p_first = p_last = project_on_atom;
     }
-    dim3 grid((unsigned)((T + dp::PJ_TT - 1) / dp::PJ_TT), (unsigned)((Q + dp::PJ_TQ - 1) / dp::PJ_TQ));
-    dim3 block(dp::PJ_TQ, dp::PJ_TT);
+    dim3 grid((unsigned)((T + dp::PJ_F - 1) / dp::PJ_F), (unsigned)((Q + dp::PJ_Q - 1) / dp::PJ_Q));
+    dim3 block(dp::PJ_THREADS);
     DP_REQUIRE(grid.y <= 65535, DP_ERR_UNSUPPORTED, "dp_project_wave_vector: Q=%d too large for one launch", Q);
     if (v_is_complex) {
         auto k = dp::project_dense_kernel<2>;
-        DP_LAUNCH(k, grid, block, 0, st, v, d_ph, d_list, d_off, N, n_prim, T, Q, p_first, p_last, (dp::cplx*)out_vc);
+        DP_CUDA_OK(DP_SET_SMEM(k, dp::PjCfg<2>::SMEM));
+        DP_LAUNCH(k, grid, block, dp::PjCfg<2>::SMEM, st, v, d_ph, d_list, d_off, N, n_prim, T, Q, p_first, p_last, (dp::cplx*)out_vc);
     } else {
         auto k = dp::project_dense_kernel<1>;
-        DP_LAUNCH(k, grid, block, 0, st, v, d_ph, d_list, d_off, N, n_prim, T, Q, p_first, p_last, (dp::cplx*)out_vc);
+        DP_CUDA_OK(DP_SET_SMEM(k, dp::PjCfg<1>::SMEM));
+        DP_LAUNCH(k, grid, block, dp::PjCfg<1>::SMEM, st, v, d_ph, d_list, d_off, N, n_prim, T, Q, p_first, p_last, (dp::cplx*)out_vc);
     }
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;

@@ -77,6 +77,13 @@ if "dense" in which:
     typ = np.repeat([0, 1], nc).astype(np.int32)
     t = timeit(lambda: ops.project_wave_vector(v[:Td], sm, pos, typ, 2, q_cart[:256]), reps=3, warm=1)
     report("project_wave_vector(dense)", t, flops=12.0 * N * Td * 256, extra=f"T={Td} Q=256")
+    Tb, Qb = min(T, 2048), 512
+    t = timeit(lambda: ops.project_wave_vector(v[:Tb], sm, pos, typ, 2, q_cart[:Qb]), reps=3, warm=1)
+    report("project_wave_vector(dense)", t, flops=12.0 * N * Tb * Qb, extra=f"T={Tb} Q={Qb} (fp64 peak 36.6 TFLOP/s: frac {12.0 * N * Tb * Qb / t[0] / 36.6e12:.3f})")
+    vcx = torch.randn((512, N, 3), dtype=torch.complex128, device=dev, generator=None)
+    t = timeit(lambda: ops.project_wave_vector(vcx, sm, pos, typ, 2, q_cart[:Qb]), reps=3, warm=1)
+    report("project_wave_vector(dense, complex v)", t, flops=24.0 * N * 512 * Qb, extra=f"T=512 Q={Qb}")
+    del vcx
 if "phonon" in which:
     if vc is None:
         vc = torch.randn((T, Q, 2, 3), dtype=torch.complex128, device=dev)
