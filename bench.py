@@ -236,6 +236,44 @@ def ncu_traffic_from_profiles(units_now):
     return out, src
 
 
+def methods_cpu_baselines(methods, send, ps_m_head, frames, torch, ops):
+    """CPU side of `spectra_methods` (N = 1, rank 0): the reference's own compiled C kernels (oracle/_ref: c/mem.c and
+    c/correlation.c built with -O2 -fopenmp by oracle/Makefile) on the host cores, on a bounded sample of THIS run's
+    contracted series; MEM doubles as the parity check of the full-length device result."""
+    from oracle import ref
+    if not ref.available():
+        return
+    cores = os.cpu_count()
+    # maximum entropy: 8 full-length series, deterministic build (Data[N] := 0)
+    x8 = np.ascontiguousarray(send[0, :8, :].t().cpu().numpy())
+    t0 = time.perf_counter()
+    ref_m = np.stack([ref.mem_det().mem(FREQ, np.ascontiguousarray(x8[:, i]), DT, coefficients=1000) for i in range(8)], axis=1)
+    t_m = time.perf_counter() - t0
+    ref_m = np.nan_to_num(ref_m) * 0.00010585723
+    methods["mem"]["cpu_baseline"] = {"value": 8 / t_m, "unit": "series/s", "kind": "reference", "cores": cores,
+                                      "sample": "8 series of %d samples, mem.mem of c/mem.c (OpenMP over frequencies), %.2f s" % (frames, t_m)}
+    methods["mem"]["parity"] = {"max_rel_err": float(np.abs(ps_m_head - ref_m[:, :2]).max() / np.abs(ref_m[:, :2]).max()),
+                                "peak_bin_matches": int((ps_m_head.argmax(0) == ref_m[:, :2].argmax(0)).sum()), "series": 2,
+                                "vs": "compiled reference c/mem.c (deterministic build) on the same series"}
+    # direct correlation: as shipped, N = 4096 (the reference recomputes the lag products for every frequency: O(F N^2 / step))
+    n_c = 4096
+    xc = np.ascontiguousarray(x8[:n_c, :2])
+    t0 = time.perf_counter()
+    for i in range(2):
+        ref.correlation_shipped().correlation_par(FREQ, np.ascontiguousarray(xc[:, i]), DT, step=10, integration_method=1)
+    t_c = time.perf_counter() - t0
+    # parity of the device kernel against the reference's intended-weight build on the same truncated series
+    ref_c = ref.correlation_intended().correlation_par(FREQ, np.ascontiguousarray(xc[:, 0]), DT, step=10, integration_method=1) * 0.00010585723
+    dev_c = ops.power_correlation(send[0, :1, :n_c].contiguous(), DT, FREQ, 10, 1, 1, series_major=True)[:, 0].cpu().numpy()
+    methods["correlation"]["parity"] = {"max_rel_err": float(np.abs(dev_c - ref_c).max() / np.abs(ref_c).max()),
+                                        "peak_bin_matches": int(dev_c.argmax() == ref_c.argmax()), "series": 1,
+                                        "vs": "compiled reference c/correlation.c (intended-weight build), first %d samples" % n_c}
+    per_series_full = t_c / 2 * (frames / n_c) ** 2
+    methods["correlation"]["cpu_baseline"] = {"value": 1.0 / per_series_full, "unit": "series/s", "kind": "reference", "cores": cores,
+                                              "sample": "2 series of %d samples, correlation.correlation_par of c/correlation.c (OpenMP "
+                                                        "over frequencies), %.2f s; scaled by N^2 to %d samples (extrapolated)" % (n_c, t_c, frames)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -452,27 +490,51 @@ def run_ours(args):
 
     # ---- the other two spectrum methods of the selector on a bounded sample of the SAME series (not in the timed
     # region; the metric names "mode spectra/s" per algorithm): maximum entropy (m = 1000) and direct correlation
+    # ---- the other two spectrum methods of the selector on the WHOLE job (all 30 720 series, every rank its own share,
+    # read in place from the exchanged / contracted blocks -- dp_power_mem_strided, dp_power_correlation_strided): maximum
+    # entropy (m = 1000, c/mem.c) and direct correlation (step 10, method 1, intended weights exp(i w tau), c/correlation.c)
     methods = None
-    if world == 1 and not args.skip_methods:
-        def timed(fn):
-            fn()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); out = fn(); b.record(); torch.cuda.synchronize()
-            return a.elapsed_time(b) * 1e-3, out
-        ns_c, ns_m = 128, 148
-        x = send[0, :ns_m, :].t().contiguous()                      # (T, S) time-major, the reference's layout
-        t_c, _ = timed(lambda: ops.power_correlation(x[:, :ns_c], DT, FREQ, 10, 1, 1))
-        t_m, _ = timed(lambda: ops.power_mem(x, DT, FREQ, 1000))
-        fl_c = 4.0 * tl * tl / 10 * ns_c
-        methods = {
-            "fft": {"series_per_s": wl["Q"] * wl["M"] / (np.mean(stage_ms["spectra"]) * 1e-3), "sample": "all series (timed region)"},
-            "correlation": {"series_per_s": ns_c / t_c, "sample": "%d series, step 10, method 1" % ns_c,
-                            "fp64_TFLOPs": fl_c / t_c / 1e12, "frac_of_fp64_peak": fl_c / t_c / 1e12 / (2 * FP64_PEAK_TOPS),
-                            "full_job_extrapolated_s": wl["Q"] * wl["M"] / (ns_c / t_c)},
-            "mem": {"series_per_s": ns_m / t_m, "sample": "%d series, 1000 coefficients" % ns_m,
-                    "full_job_extrapolated_s": wl["Q"] * wl["M"] / (ns_m / t_m)},
-        }
-        del x
+    if not args.skip_methods:
+        if world == 1:
+            blocks = send
+        elif cyclic:
+            blocks = pipe._peer["cyc_recv"] if use_peers else None
+        else:
+            blocks = recv.reshape(world * (tl // CH), pipe.q_block * pipe.M, CH)
+        if blocks is not None:
+            s_all = wl["Q"] * wl["M"]
+
+            def timed(fn):
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+                tms = torch.tensor([a.elapsed_time(b) * 1e-3], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                return float(tms.item()), out
+            warm = blocks[:, :64, :]
+            ops.power_mem(warm, DT, FREQ, 1000, series_major=True)
+            ops.power_correlation(warm, DT, FREQ, 10, 1, 1, series_major=True)
+            t_m, ps_m = timed(lambda: ops.power_mem(blocks, DT, FREQ, 1000, series_major=True))
+            mem_peak0 = int(torch.argmax(ps_m[:, 0]).item())
+            ps_m_head = ps_m[:, :2].cpu().numpy()
+            del ps_m
+            t_c, ps_c = timed(lambda: ops.power_correlation(blocks, DT, FREQ, 10, 1, 1, series_major=True))
+            corr_peak0 = int(torch.argmax(ps_c[:, 0]).item())
+            del ps_c
+            fl_c = 4.0 * frames * frames / 10 * s_all
+            methods = {
+                "fft": {"series_per_s": s_all / (np.mean(stage_ms["spectra"]) * 1e-3), "sample": "all series (timed region)"},
+                "mem": {"series_per_s": s_all / t_m, "seconds_full_job": t_m, "sample": "all %d series, 1000 coefficients" % s_all,
+                        "peak_bin_series0": mem_peak0},
+                "correlation": {"series_per_s": s_all / t_c, "seconds_full_job": t_c,
+                                "sample": "all %d series, step 10, method 1, intended weights" % s_all,
+                                "fp64_TFLOPs": fl_c / t_c / 1e12, "frac_of_fp64_peak": fl_c / t_c / 1e12 / (2 * FP64_PEAK_TOPS * world),
+                                "peak_bin_series0": corr_peak0},
+            }
+            if world == 1 and rank == 0 and not args.skip_cpu:
+                methods_cpu_baselines(methods, send, ps_m_head, frames, torch, ops)
+            del blocks
 
     # ---- end to end through the host-facing call (pinned host trajectory) -----------------------------
     e2e = None

@@ -43,6 +43,8 @@ SIGNATURES = {
     "dp_power_fft_pieces": (_I, [_L, _D, _P, _I, _P, _P, _P, _I]),
     "dp_power_mem_workspace_bytes": (_Z, [_L, _I, _I, _I]),
     "dp_power_mem": (_I, [_P, _L, _I, _L, _D, _P, _I, _I, _D, _I, _P, _P, _Z, _P]),
+    "dp_power_mem_strided": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _I, _D, _I, _P, _P, _Z, _P]),
+    "dp_power_correlation_strided": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _I, _I, _I, _D, _P, _P, _Z, _P]),
     "dp_power_correlation_workspace_bytes": (_Z, [_L, _I, _I, _I]),
     "dp_power_correlation": (_I, [_P, _L, _I, _L, _D, _P, _I, _I, _I, _I, _D, _P, _P, _Z, _P]),
     "dp_spectra_peaks": (_I, [_P, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P]),

@@ -93,6 +93,22 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// A set of complex128 time series in device memory: sample t of series s is at
+//   base[s*stride_s + (t / tb_len)*tb_stride + (t % tb_len)*stride_t]   (tb_len > 0: the time axis arrives in blocks,
+//   e.g. one block per source rank and chunk after the time-sharded -> series-sharded exchange), or
+//   base[s*stride_s + t*stride_t]                                       (tb_len == 0).
+// (T, ld) time-major arrays of the reference are stride_s = 1, stride_t = ld; series-major is stride_t = 1.
+struct SeriesView {
+    const cplx* base;
+    int64_t stride_s, stride_t, tb_stride;
+    int tb_len;
+    __host__ __device__ __forceinline__ const cplx* at(int64_t s, int64_t t) const {
+        if (tb_len == 0) return base + s * stride_s + t * stride_t;
+        const int64_t b = t / tb_len;
+        return base + s * stride_s + b * tb_stride + (t - b * tb_len) * stride_t;
+    }
+};
+
 int sm_count();
 // small host array -> device through kernel parameters (never blocks the host; see dp_core.cu)
 int upload_small(void* dst, const void* src, size_t bytes, cudaStream_t st);

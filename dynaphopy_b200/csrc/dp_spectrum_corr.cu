@@ -22,22 +22,38 @@ namespace dp {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Decimated layout of one series: u_r[n] = v[r + n*step], r in [0, step), stored as ud[s][r][n] with row pitch NP.
-// series[t*ld + s] -> ud[((s - s0)*step + t % step)*NP + t / step]   (32 x 32 tile through shared memory)
+// Time-major input (stride_s == 1, the reference's (T, S) array): 32 x 32 tiles through shared memory so that both the
+// read (consecutive series) and the write (consecutive n) are coalesced.
 __global__ void __launch_bounds__(256)
-decimate_series_kernel(const cplx* __restrict__ series, int64_t ld, int N, int s0, int ns, int step, int NP,
-                       cplx* __restrict__ ud) {
+decimate_series_kernel(SeriesView x, int N, int s0, int ns, int step, int NP, cplx* __restrict__ ud) {
     __shared__ cplx tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
     const int ntb = (N + 31) / 32;
     const int tb = (int)(blockIdx.x % ntb) * 32, sb = (int)(blockIdx.x / ntb) * 32;
     for (int r = ty; r < 32; r += 8) {
         int t = tb + r, s = sb + tx;
-        if (t < N && s < ns) tile[r][tx] = series[(int64_t)t * ld + s0 + s];
+        if (t < N && s < ns) tile[r][tx] = *x.at(s0 + s, t);
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         int s = sb + r, t = tb + tx;
         if (t < N && s < ns) ud[((size_t)s * step + t % step) * NP + t / step] = tile[tx][r];
+    }
+}
+// Any other layout (series-major, blocked time axis): thread n of a series gathers u_r[n] for every residue r -- the
+// `step` reads of a warp cover one contiguous span of the series (each line is fetched from DRAM once), the writes are
+// contiguous in n.
+__global__ void __launch_bounds__(256)
+decimate_series_gather_kernel(SeriesView x, int N, int s0, int ns, int step, int NP, cplx* __restrict__ ud) {
+    const int nn = (N + step - 1) / step;
+    const int nchunks = (nn + 255) / 256;
+    for (int64_t blk = blockIdx.x; blk < (int64_t)ns * nchunks; blk += gridDim.x) {
+        const int s = (int)(blk / nchunks), n = (int)(blk % nchunks) * 256 + threadIdx.x;
+        if (n >= nn) continue;
+        for (int r = 0; r < step; r++) {
+            const int t = r + n * step;
+            if (t < N) ud[((size_t)s * step + r) * NP + n] = __ldg(x.at(s0 + s, t));
+        }
     }
 }
 
@@ -267,8 +283,22 @@ size_t dp_power_correlation_workspace_bytes(int64_t T, int S, int F, int step) {
 int dp_power_correlation(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq, int F,
                          int step, int integration_method, int weight_mode, double scale, double* out,
                          void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(S > 0 && ld >= S, DP_ERR_INVALID, "dp_power_correlation: bad sizes");
+    return dp_power_correlation_strided(series, T, S, 1, ld, 0, 0, dt, freq, F, step, integration_method, weight_mode, scale,
+                                        out, workspace, workspace_bytes, stream);
+}
+
+int dp_power_correlation_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                                 int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int step,
+                                 int integration_method, int weight_mode, double scale, double* out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
     DP_REQUIRE(series && freq && out && workspace, DP_ERR_INVALID, "dp_power_correlation: null pointer");
-    DP_REQUIRE(S > 0 && ld >= S && F > 0 && T >= 1 && step >= 1, DP_ERR_INVALID, "dp_power_correlation: bad sizes");
+    DP_REQUIRE(S > 0 && F > 0 && T >= 1 && step >= 1 && stride_t != 0 && tb_len >= 0 && tb_len < (1LL << 31), DP_ERR_INVALID,
+               "dp_power_correlation: bad sizes");
+    if (tb_len >= T) tb_len = 0;
+    dp::SeriesView view;
+    view.base = (const dp::cplx*)series; view.stride_s = stride_s; view.stride_t = stride_t; view.tb_len = (int)tb_len;
+    view.tb_stride = tb_stride;
     DP_REQUIRE(T < (1LL << 30), DP_ERR_UNSUPPORTED, "dp_power_correlation: T too large");
     // c/correlation.c:138-141: "Integration method selected does not exist" (returns NULL)
     DP_REQUIRE(integration_method == 0 || integration_method == 1, DP_ERR_INVALID,
@@ -313,11 +343,16 @@ int dp_power_correlation(const double* series, int64_t T, int S, int64_t ld, dou
     const size_t smem = ((size_t)dp::CR_CH + 9 * ((size_t)dp::CR_CH / 8 + nw * 32)) * sizeof(dp::cplx);
     for (int s0 = 0; s0 < S; s0 += lay.chunk) {
         const int ns = dp::imin(lay.chunk, S - s0);
-        {
+        if (stride_s == 1) {
             auto k = dp::decimate_series_kernel;
             const int64_t nblocks = (int64_t)((N + 31) / 32) * ((ns + 31) / 32);
             DP_REQUIRE(nblocks < (1LL << 31), DP_ERR_UNSUPPORTED, "dp_power_correlation: chunk too large");
-            DP_LAUNCH(k, dim3((unsigned)nblocks), dim3(256), 0, st, (const dp::cplx*)series, ld, N, s0, ns, step, lay.NP, ud);
+            DP_LAUNCH(k, dim3((unsigned)nblocks), dim3(256), 0, st, view, N, s0, ns, step, lay.NP, ud);
+            DP_CUDA_OK(cudaGetLastError());
+        } else {
+            auto k = dp::decimate_series_gather_kernel;
+            const int64_t nblocks = (int64_t)ns * (((N + step - 1) / step + 255) / 256);
+            DP_LAUNCH(k, dim3((unsigned)dp::imin<int64_t>(nblocks, 1 << 20)), dim3(256), 0, st, view, N, s0, ns, step, lay.NP, ud);
             DP_CUDA_OK(cudaGetLastError());
         }
         {

@@ -26,8 +26,7 @@ constexpr int BURG_THREADS = 512;
 constexpr int BURG_WARPS = BURG_THREADS / 32;
 
 struct BurgParams {
-    const double* series;   // complex128, time-major, leading dimension ld (in complex elements)
-    int64_t ld;
+    SeriesView x;           // the series (any layout, see SeriesView)
     int N, m;
     int unit0, nunits;      // units = 2*series + part
     double* slabs;          // global-mode storage: per CTA 2*len doubles (nullptr in smem mode)
@@ -63,14 +62,14 @@ __global__ void __launch_bounds__(BURG_THREADS) burg_kernel(BurgParams p) {
 
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const int gu = p.unit0 + unit;
-        const double* x = p.series + (size_t)(gu >> 1) * 2 + (gu & 1);
-        const int64_t xs = p.ld * 2;
+        const int xser = gu >> 1, xpart = gu & 1;           // sample j, part Re / Im: xval(j)
+        auto xval = [&](int j) { return __ldg(reinterpret_cast<const double*>(p.x.at(xser, j)) + xpart); };
         __syncthreads();
         // ---- init: f[j] = x[j+1], b[j] = x[j+2] (x[N] := 0); power and first inner products ----
         double pw = 0.0, num = 0.0, den = 0.0;
         for (int j = tid; j < len; j += BURG_THREADS) {
-            double fj = __ldg(x + (int64_t)(j + 1) * xs);
-            double bj = (j + 2 < N) ? __ldg(x + (int64_t)(j + 2) * xs) : 0.0;
+            double fj = xval(j + 1);
+            double bj = (j + 2 < N) ? xval(j + 2) : 0.0;
             f[j] = fj; b[j] = bj;
             pw += __dmul_rn(fj, fj);
             num += __dmul_rn(fj, bj);
@@ -191,8 +190,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) burg_cluster_kernel(BurgParams 
 
     for (int unit = cl; unit < p.nunits; unit += ncl) {
         const int gu = p.unit0 + unit;
-        const double* x = p.series + (size_t)(gu >> 1) * 2 + (gu & 1);
-        const int64_t xs = p.ld * 2;
+        const int xser = gu >> 1, xpart = gu & 1;
+        auto xval = [&](int j) { return __ldg(reinterpret_cast<const double*>(p.x.at(xser, j)) + xpart); };
         // ---- init: f[j] = x[j+1], b[j] = x[j+2] (x[N] := 0) ----
         double f[E];
         double pw = 0.0, num = 0.0, den = 0.0;
@@ -201,8 +200,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) burg_cluster_kernel(BurgParams 
             const int j = j0 + e;
             double fj = 0.0, bj = 0.0;
             if (j < len) {
-                fj = __ldg(x + (int64_t)(j + 1) * xs);
-                bj = (j + 2 < N) ? __ldg(x + (int64_t)(j + 2) * xs) : 0.0;
+                fj = xval(j + 1);
+                bj = (j + 2 < N) ? xval(j + 2) : 0.0;
                 pw = fma(fj, fj, pw);
                 num = fma(fj, bj, num);
                 den = fma(fj, fj, fma(bj, bj, den));
@@ -382,8 +381,18 @@ size_t dp_power_mem_workspace_bytes(int64_t T, int S, int F, int coefficients) {
 int dp_power_mem(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq, int F,
                  int coefficients, double scale, int nan_to_num, double* out, void* workspace,
                  size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(S > 0 && ld >= S, DP_ERR_INVALID, "dp_power_mem: bad sizes");
+    return dp_power_mem_strided(series, T, S, 1, ld, 0, 0, dt, freq, F, coefficients, scale, nan_to_num, out, workspace,
+                                workspace_bytes, stream);
+}
+
+int dp_power_mem_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t, int64_t tb_len,
+                         int64_t tb_stride, double dt, const double* freq, int F, int coefficients, double scale,
+                         int nan_to_num, double* out, void* workspace, size_t workspace_bytes, void* stream) {
     DP_REQUIRE(series && freq && out && workspace, DP_ERR_INVALID, "dp_power_mem: null pointer");
-    DP_REQUIRE(S > 0 && ld >= S && F > 0 && coefficients >= 1, DP_ERR_INVALID, "dp_power_mem: bad sizes");
+    DP_REQUIRE(S > 0 && F > 0 && coefficients >= 1 && stride_t != 0 && tb_len >= 0 && tb_len < (1LL << 31), DP_ERR_INVALID,
+               "dp_power_mem: bad sizes");
+    if (tb_len >= T) tb_len = 0;
     // reference guard, dynaphopy/power_spectrum/__init__.py:85-87 (prints and exit()s there)
     DP_REQUIRE(T > (int64_t)coefficients + 1, DP_ERR_INVALID,
                "Number of coefficients should be smaller than the number of time steps (T=%lld, m=%d)",
@@ -399,7 +408,9 @@ int dp_power_mem(const double* series, int64_t T, int S, int64_t ld, double dt, 
         if (rc_up) return rc_up;
     }
     dp::BurgParams p;
-    p.series = series; p.ld = ld; p.N = (int)T; p.m = coefficients;
+    p.x.base = (const dp::cplx*)series; p.x.stride_s = stride_s; p.x.stride_t = stride_t; p.x.tb_len = (int)tb_len;
+    p.x.tb_stride = tb_stride;
+    p.N = (int)T; p.m = coefficients;
     p.unit0 = 0; p.nunits = 2 * S;
     p.slabs = lay.smem_mode ? nullptr : (double*)(ws + lay.off_slabs);
     p.coef = (double*)(ws + lay.off_coef);

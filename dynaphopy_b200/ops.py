@@ -323,27 +323,31 @@ class Ops:
                       be.stream())
         return out
 
-    def power_mem(self, series, dt, frequency_range, coefficients, scale=UNIT_CONVERSION, nan_to_num=True):
+    def power_mem(self, series, dt, frequency_range, coefficients, scale=UNIT_CONVERSION, nan_to_num=True,
+                  series_major=False):
+        """Maximum-entropy spectrum of every series -> (F, S).  ``series`` layouts as in ``power_fft``."""
         be = self.be
-        s, T, S = self._series(series)
+        s, T, S, st = self._series_layout(series, series_major)
         f = _host(frequency_range, np.float64)
         nbytes = max(self.lib.size("dp_power_mem_workspace_bytes", T, S, f.size, int(coefficients)), 256)
         ws = be.empty((nbytes,), np.uint8)
         out = be.empty((f.size, S), np.float64)
-        self.lib.call("dp_power_mem", be.ptr(s), T, S, S, float(dt), _hptr(f), f.size, int(coefficients),
-                      float(scale), int(bool(nan_to_num)), be.ptr(out), be.ptr(ws), nbytes, be.stream())
+        self.lib.call("dp_power_mem_strided", be.ptr(s), T, S, st[0], st[1], st[2], st[3], float(dt), _hptr(f), f.size,
+                      int(coefficients), float(scale), int(bool(nan_to_num)), be.ptr(out), be.ptr(ws), nbytes, be.stream())
         return out
 
     def power_correlation(self, series, dt, frequency_range, step=10, integration_method=1,
-                          weight=_lib.DP_CORR_WEIGHT_REFERENCE, scale=UNIT_CONVERSION):
+                          weight=_lib.DP_CORR_WEIGHT_REFERENCE, scale=UNIT_CONVERSION, series_major=False):
+        """Direct-correlation spectrum of every series -> (F, S).  ``series`` layouts as in ``power_fft``."""
         be = self.be
-        s, T, S = self._series(series)
+        s, T, S, st = self._series_layout(series, series_major)
         f = _host(frequency_range, np.float64)
         nbytes = max(self.lib.size("dp_power_correlation_workspace_bytes", T, S, f.size, int(step)), 256)
         ws = be.empty((nbytes,), np.uint8)
         out = be.empty((f.size, S), np.float64)
-        self.lib.call("dp_power_correlation", be.ptr(s), T, S, S, float(dt), _hptr(f), f.size, int(step),
-                      int(integration_method), int(weight), float(scale), be.ptr(out), be.ptr(ws), nbytes, be.stream())
+        self.lib.call("dp_power_correlation_strided", be.ptr(s), T, S, st[0], st[1], st[2], st[3], float(dt), _hptr(f),
+                      f.size, int(step), int(integration_method), int(weight), float(scale), be.ptr(out), be.ptr(ws),
+                      nbytes, be.stream())
         return out
 
     def spectra_peaks(self, spectra, sets=None, want_average=True):

@@ -467,13 +467,17 @@ class MeshPipeline:
         return recv
 
     def spectra_series(self, blocks):
-        """(G, S_loc, Tb) time blocks of series-major series -> (F, S_loc) power spectra."""
-        if self.algorithm in (2, 3, 4, 5):
+        """(G, S_loc, Tb) time blocks of series-major series -> (F, S_loc) power spectra.  Every method reads the blocks
+        in place (``dp_power_{fft,mem,correlation}_strided``): no transposing copy of the series matrix."""
+        a = self.algorithm
+        if a in (2, 3, 4, 5):
             return self.ops.power_fft(blocks, self.dt, self.freq, series_major=True)
-        g, s_loc, tb = self.be.shape(blocks)
-        tm = blocks.permute(0, 2, 1).reshape(g * tb, s_loc) if hasattr(blocks, "permute") else \
-            np.ascontiguousarray(np.transpose(blocks, (0, 2, 1)).reshape(g * tb, s_loc))
-        return self.spectra(tm)
+        if a == 1:
+            return self.ops.power_mem(blocks, self.dt, self.freq, self.mem_coefficients, series_major=True)
+        if a == 0:
+            return self.ops.power_correlation(blocks, self.dt, self.freq, self.correlation_step, self.integration_method,
+                                              self.correlation_weight, series_major=True)
+        raise ValueError("Power spectrum algorithm number not found")
 
     def run(self, velocity_local, chunk_frames=4096):
         """Whole step on device-resident local frames; returns the (F, S_local) spectra of this rank."""

@@ -247,6 +247,12 @@ size_t dp_power_mem_workspace_bytes(int64_t T, int S, int F, int coefficients);
 int dp_power_mem(const double* series, int64_t T, int S, int64_t ld, double dt, const double* freq,
                  int F, int coefficients, double scale, int nan_to_num, double* out,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* Same for series stored with arbitrary strides / a blocked time axis (see dp_power_fft_strided): the series-major
+ * output of dp_project_phonon_series and the (source rank, chunk) time blocks of the multi-GPU exchange are read in
+ * place.  dp_power_mem is the case stride_s = 1, stride_t = ld. */
+int dp_power_mem_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t, int64_t tb_len,
+                         int64_t tb_stride, double dt, const double* freq, int F, int coefficients, double scale,
+                         int nan_to_num, double* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * A5  power spectrum, direct correlation method (selector key 0).
@@ -262,6 +268,12 @@ int dp_power_correlation(const double* series, int64_t T, int S, int64_t ld, dou
                          const double* freq, int F, int step, int integration_method,
                          int weight_mode, double scale, double* out, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* Same for strided series / a blocked time axis (see dp_power_fft_strided); dp_power_correlation is the case
+ * stride_s = 1, stride_t = ld. */
+int dp_power_correlation_strided(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                                 int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int step,
+                                 int integration_method, int weight_mode, double scale, double* out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Utility: batched complex FFT on device data with the library's own radix engine

@@ -554,6 +554,26 @@ def test_power_fft_series_rows_as_tensor_boxes(kops, nt, dt, res):
     assert np.array_equal(b.argmax(0), ref.argmax(0))
 
 
+def test_power_mem_and_correlation_series_major_and_time_blocks(kops):
+    """dp_power_mem_strided / dp_power_correlation_strided: series-major (S, T) input and the blocked time axis
+    (G, S, Tb) of the multi-GPU exchange give exactly the spectra of the reference's (T, S) layout."""
+    rng = np.random.default_rng(31)
+    nt, ns, dt = 1200, 5, 0.002
+    x = _series(rng, nt, ns, dt)
+    f = np.arange(0, 40.0, 2.0)
+    xt = np.ascontiguousarray(x.T)
+    blocks = np.ascontiguousarray(x.reshape(4, nt // 4, ns).transpose(0, 2, 1))       # (G, S, Tb)
+    a = to_np(kops.power_mem(x, dt, f, 40))
+    assert relerr(a, port.mem_spectra(x, dt, f, 40)) < TOL
+    assert np.array_equal(a, to_np(kops.power_mem(xt, dt, f, 40, series_major=True)))
+    assert np.array_equal(a, to_np(kops.power_mem(blocks, dt, f, 40, series_major=True)))
+    for method in (0, 1):
+        c = to_np(kops.power_correlation(x, dt, f, 10, method, 1))
+        assert relerr(c, port.correlation_spectra(x, dt, f, 10, method, "intended")) < TOL
+        assert np.array_equal(c, to_np(kops.power_correlation(xt, dt, f, 10, method, 1, series_major=True)))
+        assert np.array_equal(c, to_np(kops.power_correlation(blocks, dt, f, 10, method, 1, series_major=True)))
+
+
 def test_power_fft_incremental_windows(kops):
     """dp_power_fft_windows / dp_power_fft_finish: windows transformed in several calls (any split, even while
     later samples are still garbage) give exactly the one-shot spectrum."""
