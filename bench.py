@@ -299,7 +299,7 @@ def run_ours(args):
     assert pipe.fold_twiddle        # primitive cell: the projection twiddle rides on the eigenvectors
 
     # ---- device-resident inputs -------------------------------------------------------------------
-    CH = 4096                                        # frames per projection/contraction chunk (vc chunk: 2 GB)
+    CH = args.chunk                                  # frames per projection/contraction chunk (4096: vc chunk of 2 GB)
     # N > 1: chunk-cyclic time sharding (chunk j of the trajectory lives on rank j % N), so that the spectra of finished
     # windows overlap the rest of the exchange; --sharding blocks keeps one contiguous time block per rank
     # auto: cyclic where the exchange is the longer leg (measured: 8 GPUs 27.9 vs 32.3 ms, 4 GPUs equal, 2 GPUs 103.9 vs 99.6)
@@ -672,6 +672,7 @@ def main():
     ap.add_argument("--sharding", default="auto", choices=["auto", "cyclic", "blocks"],
                     help="N > 1: chunk-cyclic time sharding with overlapped spectra (default) or one time block per rank")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--chunk", type=int, default=4096, help="frames per projection / contraction / exchange chunk")
     ap.add_argument("--cpu-frames", type=int, default=4096, help="frames of the CPU projection sample (BASELINE.md section 3: 4096)")
     ap.add_argument("--write-golden", action="store_true",
                     help="N = 1: write the per-series spectrum sums of this run to gpurun_out/ (committed under tests/golden/ "

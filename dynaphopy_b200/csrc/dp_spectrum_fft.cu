@@ -324,6 +324,13 @@ int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* pi
 int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
                          int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
                          int n_windows, void* workspace, size_t workspace_bytes, void* stream) {
+    return dp_power_fft_windows_ex(series, T, S, stride_s, stride_t, tb_len, tb_stride, dt, freq, F, first_window, n_windows,
+                                   0, workspace, workspace_bytes, stream);
+}
+
+int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                            int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
+                            int n_windows, int max_ctas, void* workspace, size_t workspace_bytes, void* stream) {
     DP_REQUIRE(series && freq && workspace, DP_ERR_INVALID, "dp_power_fft: null pointer");
     DP_REQUIRE(S > 0 && stride_t != 0, DP_ERR_INVALID, "dp_power_fft: bad S=%d stride_t=%lld", S, (long long)stride_t);
     DP_REQUIRE(tb_len >= 0 && tb_len < (1LL << 31), DP_ERR_INVALID, "dp_power_fft: bad time-block length %lld", (long long)tb_len);
@@ -366,7 +373,8 @@ int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_
     if (rc) return rc;
     double* spec = (double*)(ws + lay.off_spec);
     const int64_t items = (int64_t)S * (pl.use_v2 ? (n_windows + 1) / 2 : n_windows);
-    const int grid = (int)dp::imin<int64_t>(items, lay.nslots);
+    int grid = (int)dp::imin<int64_t>(items, lay.nslots);
+    if (max_ctas > 0) grid = dp::imin(grid, max_ctas);          // leave SMs to work that runs concurrently on other streams
     if (pl.use_v2) {
         dp::S2Params p;
         p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;

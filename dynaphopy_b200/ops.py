@@ -304,15 +304,17 @@ class Ops:
                           self.be.stream())
         return self.be.empty((nbytes,), np.uint8)
 
-    def power_fft_windows(self, series, dt, frequency_range, first_window, n_windows, workspace, series_major=False):
+    def power_fft_windows(self, series, dt, frequency_range, first_window, n_windows, workspace, series_major=False,
+                          max_ctas=0):
         """Transform windows [first_window, first_window + n_windows) of every series into ``workspace``; reads
-        no sample outside those windows (the rest of ``series`` may still be in production)."""
+        no sample outside those windows (the rest of ``series`` may still be in production).  ``max_ctas``: SMs the
+        persistent kernel may occupy (0: all) -- leaves room for concurrent work of other streams."""
         be = self.be
         s, T, S, st = self._series_layout(series, series_major)
         f = _host(frequency_range, np.float64)
-        self.lib.call("dp_power_fft_windows", be.ptr(s), T, S, st[0], st[1], st[2], st[3], float(dt), _hptr(f), f.size,
-                      int(first_window), int(n_windows), be.ptr(workspace), int(workspace.numel() if hasattr(workspace, "numel")
-                                                                                else workspace.size), be.stream())
+        self.lib.call("dp_power_fft_windows_ex", be.ptr(s), T, S, st[0], st[1], st[2], st[3], float(dt), _hptr(f), f.size,
+                      int(first_window), int(n_windows), int(max_ctas), be.ptr(workspace),
+                      int(workspace.numel() if hasattr(workspace, "numel") else workspace.size), be.stream())
 
     def power_fft_finish(self, T, S, dt, frequency_range, workspace, scale=UNIT_CONVERSION):
         be = self.be

@@ -243,8 +243,10 @@ class MeshPipeline:
         pr["hdl"].barrier(channel=0)
         if "streams" not in pr:
             dev = self.be.device
-            nst = int(os.environ.get("DP_PEER_STREAMS", self.world - 1))       # one stream (copy engine) per destination
-            pr["streams"] = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(self.world - 1, nst)))]
+            # one stream (copy engine) per destination and per slice of a block (DP_PEER_SPLIT slices, default 1)
+            pr["split"] = max(1, int(os.environ.get("DP_PEER_SPLIT", 1)))
+            nst = int(os.environ.get("DP_PEER_STREAMS", (self.world - 1) * pr["split"]))
+            pr["streams"] = [torch.cuda.Stream(device=dev) for _ in range(max(1, min((self.world - 1) * pr["split"], nst)))]
             pr["slot_free"] = [None, None]
             nch, tc = pr["key"]
             s_loc = self.q_block * self.M
@@ -285,11 +287,15 @@ class MeshPipeline:
         evs = []
         for st in pr["streams"]:
             st.wait_event(done)
+        split = pr.get("split", 1)
+        n_ser = src.shape[1]
         for j in range(self.world - 1):
             dst = (self.rank + 1 + j) % self.world            # staggered: at any time every rank targets a different peer
-            st = pr["streams"][j % len(pr["streams"])]
-            with torch.cuda.stream(st):
-                views[dst][index[0], index[1]].copy_(src[dst], non_blocking=True)
+            for k in range(split):                            # slices of the block's series on separate copy engines
+                lo, hi = n_ser * k // split, n_ser * (k + 1) // split
+                st = pr["streams"][(j * split + k) % len(pr["streams"])]
+                with torch.cuda.stream(st):
+                    views[dst][index[0], index[1]][lo:hi].copy_(src[dst][lo:hi], non_blocking=True)
         for st in pr["streams"]:
             e = torch.cuda.Event()
             e.record(st)
@@ -370,6 +376,14 @@ class MeshPipeline:
             ws = self._cyc_ws[1]
         done = 0
 
+        # While later rounds are still being projected, contracted and pushed, the persistent spectrum kernel is kept
+        # to a share of the SMs: a full-grid launch owns every SM for milliseconds (one CTA needs a whole SM's shared
+        # memory) and the kernels that feed the exchange would wait behind it.  DP_SPEC_CTAS: that share (default 3/4).
+        sms = getattr(self, "_sms", None)
+        if sms is None:
+            sms = self._sms = int(self.ops.lib.cdll.dp_sm_count()) if hasattr(self.ops.lib, "cdll") else 0
+        share = int(os.environ.get("DP_SPEC_CTAS", max(1, sms * 3 // 4))) if (g > 1 and sms > 0) else 0
+
         def windows_after(frames_complete, blocks):
             nonlocal done
             complete = sum(1 for p in pieces if p[1] <= frames_complete)
@@ -379,7 +393,8 @@ class MeshPipeline:
             if complete < len(pieces) and not (done == 0 and nch <= len(pieces)):
                 ready = ready // 2 * 2
             if ready > 0:
-                self.ops.power_fft_windows(blocks, self.dt, self.freq, done, ready, ws, series_major=True)
+                self.ops.power_fft_windows(blocks, self.dt, self.freq, done, ready, ws, series_major=True,
+                                           max_ctas=share if complete < len(pieces) else 0)
                 done += ready
 
         if not peers:
@@ -401,58 +416,70 @@ class MeshPipeline:
                 return self.ops.power_fft_finish(T, s_loc, self.dt, self.freq, ws)
             return self.spectra_series(recv)
 
-        pr = self._peer
-        self.peer_begin()
-        if "cyc_views" not in pr:
-            pr["cyc_views"] = [pr["hdl"].get_buffer(r, (nch, g, s_loc, tc, 2), torch.float64) for r in range(g)]
-            pr["cyc_recv"] = torch.view_as_complex(pr["flat"].view(nch * g, s_loc, tc, 2))
-            pr["spec_stream"] = torch.cuda.Stream(device=be.device)
-        send = pr.get("send")
-        if send is None:
-            send = pr["send"] = be.empty((2, g, s_loc, tc), np.complex128)
-        recv, spec = pr["cyc_recv"], pr["spec_stream"]
-        main = torch.cuda.current_stream(be.device)
-        spec.wait_stream(main)
-        ev = []
-        for c in range(nch):
-            slot = c % 2
-            a, m, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            self.peer_wait_slot(slot)
-            a.record(main)
-            own = pr["ptrs"][self.rank] + ((c * g + self.rank) * s_loc * tc) * 16
-            self.series(velocity_local[c * tc:(c + 1) * tc], tc, t_total=tc, mark=lambda: m.record(main),
-                        block_ptrs=[own if dst == self.rank else int(send[slot][dst].data_ptr()) for dst in range(g)])
-            b.record(main)
-            self.peer_push(send[slot], c, slot, views=pr["cyc_views"], index=(c, self.rank))
-            with torch.cuda.stream(spec):
-                spec.wait_event(b)                                   # own block (written by the contraction kernel)
-                for e in pr["slot_free"][slot]:
-                    spec.wait_event(e)                               # own pushes of this round
-                pr["hdl"].barrier(channel=1)                         # ... and everybody else's
-                if fft:
-                    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s0.record(spec)
-                    windows_after((c + 1) * g * tc, recv)
-                    s1.record(spec)
-                    ev.append((a, m, b, s0, s1))
-                else:
-                    ev.append((a, m, b, None, None))
-        main.wait_stream(spec)
-        if fft:
-            ps = self.ops.power_fft_finish(T, s_loc, self.dt, self.freq, ws)
-        else:
-            ps = self.spectra_series(recv)
-        if record is not None:
-            torch.cuda.synchronize()
-            record["project"] = sum(a.elapsed_time(m) for a, m, _, _, _ in ev)
-            record["contract"] = sum(m.elapsed_time(b) for _, m, b, _, _ in ev)
+        # The projection / contraction / push of the rounds run on a HIGH-priority stream: whenever SMs free up, their
+        # CTAs are scheduled before those of the spectrum kernel (normal priority, second stream), so the exchange is fed
+        # as early as possible and the spectra fill in behind it.
+        outer = torch.cuda.current_stream(be.device)
+        if getattr(self, "_hp_stream", None) is None:
+            self._hp_stream = torch.cuda.Stream(device=be.device, priority=-1)
+        hp = self._hp_stream if not os.environ.get("DP_NO_HP_STREAM") else outer
+        hp.wait_stream(outer)
+        with torch.cuda.stream(hp):
+            pr = self._peer
+            self.peer_begin()
+            if "cyc_views" not in pr:
+                pr["cyc_views"] = [pr["hdl"].get_buffer(r, (nch, g, s_loc, tc, 2), torch.float64) for r in range(g)]
+                pr["cyc_recv"] = torch.view_as_complex(pr["flat"].view(nch * g, s_loc, tc, 2))
+                pr["spec_stream"] = torch.cuda.Stream(device=be.device)
+            send = pr.get("send")
+            if send is None:
+                send = pr["send"] = be.empty((2, g, s_loc, tc), np.complex128)
+            recv, spec = pr["cyc_recv"], pr["spec_stream"]
+            main = torch.cuda.current_stream(be.device)
+            spec.wait_stream(main)
+            ev = []
+            for c in range(nch):
+                slot = c % 2
+                a, m, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                self.peer_wait_slot(slot)
+                a.record(main)
+                own = pr["ptrs"][self.rank] + ((c * g + self.rank) * s_loc * tc) * 16
+                self.series(velocity_local[c * tc:(c + 1) * tc], tc, t_total=tc, mark=lambda: m.record(main),
+                            block_ptrs=[own if dst == self.rank else int(send[slot][dst].data_ptr()) for dst in range(g)])
+                b.record(main)
+                self.peer_push(send[slot], c, slot, views=pr["cyc_views"], index=(c, self.rank))
+                with torch.cuda.stream(spec):
+                    spec.wait_event(b)                                   # own block (written by the contraction kernel)
+                    for e in pr["slot_free"][slot]:
+                        spec.wait_event(e)                               # own pushes of this round
+                    pr["hdl"].barrier(channel=1)                         # ... and everybody else's
+                    if fft:
+                        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        s0.record(spec)
+                        windows_after((c + 1) * g * tc, recv)
+                        s1.record(spec)
+                        ev.append((a, m, b, s0, s1))
+                    else:
+                        ev.append((a, m, b, None, None))
+            main.wait_stream(spec)
             if fft:
-                record["spectra"] = sum(s0.elapsed_time(s1) for _, _, _, s0, s1 in ev)      # overlapped with later rounds
-                record["exchange"] = max(0.0, ev[-1][2].elapsed_time(ev[-1][3]))              # last round: contraction end -> landed everywhere
-                record["span"] = ev[0][0].elapsed_time(ev[-1][4])
-                if os.environ.get("DP_CYCLIC_TRACE") and self.rank == 0:      # development aid: per-round timeline (ms)
-                    t0 = ev[0][0]
-                    print("cyclic trace:", [tuple(round(t0.elapsed_time(x), 2) for x in e) for e in ev], flush=True)
+                ps = self.ops.power_fft_finish(T, s_loc, self.dt, self.freq, ws)
+            else:
+                ps = self.spectra_series(recv)
+            if record is not None:
+                torch.cuda.synchronize()
+                record["project"] = sum(a.elapsed_time(m) for a, m, _, _, _ in ev)
+                record["contract"] = sum(m.elapsed_time(b) for _, m, b, _, _ in ev)
+                if fft:
+                    record["spectra"] = sum(s0.elapsed_time(s1) for _, _, _, s0, s1 in ev)      # overlapped with later rounds
+                    record["exchange"] = max(0.0, ev[-1][2].elapsed_time(ev[-1][3]))              # last round: contraction end -> landed everywhere
+                    record["span"] = ev[0][0].elapsed_time(ev[-1][4])
+                    if os.environ.get("DP_CYCLIC_TRACE") and self.rank == 0:      # development aid: per-round timeline (ms)
+                        t0 = ev[0][0]
+                        print("cyclic trace:", [tuple(round(t0.elapsed_time(x), 2) for x in e) for e in ev], flush=True)
+        outer.wait_stream(hp)
+        if hasattr(ps, "record_stream"):
+            ps.record_stream(outer)
         return ps
 
     def exchange_series(self, send):

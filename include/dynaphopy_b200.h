@@ -231,6 +231,12 @@ int dp_power_fft_strided(const double* series, int64_t T, int S, int64_t stride_
 int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
                          int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
                          int n_windows, void* workspace, size_t workspace_bytes, void* stream);
+/* max_ctas > 0: the persistent kernel occupies at most that many SMs (it needs a whole SM per CTA), so that kernels of
+ * other streams -- the projection / contraction of the frames still to come, which feed the multi-GPU exchange -- keep
+ * running beside it; 0: all SMs. */
+int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                            int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
+                            int n_windows, int max_ctas, void* workspace, size_t workspace_bytes, void* stream);
 int dp_power_fft_finish(int64_t T, int S, double dt, const double* freq, int F, double scale, double* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* piece_len,
