@@ -48,6 +48,7 @@ void count_launch();
     (dp::count_launch(), dp_emul::launch((grid), (block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); }))
 #define DP_DYNSMEM(type, name) type* name = reinterpret_cast<type*>(dp_emul::tls_worker()->dyn_smem)
 #define DP_SET_SMEM(kfn, bytes) cudaSuccess
+#define DP_LAUNCH_PDL(kfn, grid, block, smem, stream, ...) (DP_LAUNCH(kfn, grid, block, smem, stream, __VA_ARGS__), cudaSuccess)
 #else
 #define DP_LAUNCH(kfn, grid, block, smem, stream, ...) \
     (dp::count_launch(), kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
@@ -56,7 +57,43 @@ void count_launch();
     type* name = reinterpret_cast<type*>(name##_raw_)
 #define DP_SET_SMEM(kfn, bytes) \
     cudaFuncSetAttribute((const void*)(kfn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+// Programmatic dependent launch: the grid may become resident while the tail of the previous kernel of the stream is
+// still running; the kernel calls pdl_wait() before it touches anything an earlier kernel wrote.
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, std::forward<Args>(args)...);
+}
+#define DP_LAUNCH_PDL(kfn, grid, block, smem, stream, ...) \
+    (dp::count_launch(), dp::launch_pdl(kfn, (grid), (block), (size_t)(smem), (stream), __VA_ARGS__))
 #endif
+
+// cudaFuncSetAttribute once per kernel and device instead of once per launch (flags: one static array per call site)
+#define DP_SET_SMEM_ONCE(kfn, bytes)                                                    \
+    do {                                                                                \
+        static bool dp_once_[64] = {};                                                  \
+        int dp_dev_ = 0;                                                                \
+        DP_CUDA_OK(cudaGetDevice(&dp_dev_));                                            \
+        if (dp_dev_ < 0 || dp_dev_ >= 64 || !dp_once_[dp_dev_]) {                       \
+            DP_CUDA_OK(DP_SET_SMEM(kfn, bytes));                                        \
+            if (dp_dev_ >= 0 && dp_dev_ < 64) dp_once_[dp_dev_] = true;                 \
+        }                                                                               \
+    } while (0)
+
+// Inside a kernel launched with DP_LAUNCH_PDL: wait until every earlier kernel of the stream has completed and its
+// writes are visible, then let the next kernel of the stream become resident (it waits in turn, so by induction a grid
+// never starts before the grid two launches earlier has completed).  No-ops under a plain launch.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // ---- small device helpers ---------------------------------------------------------------
 template <typename T> __host__ __device__ __forceinline__ T imin(T a, T b) { return a < b ? a : b; }

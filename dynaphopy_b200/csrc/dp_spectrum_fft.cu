@@ -20,6 +20,7 @@
 #include "dp_common.cuh"
 #include "dp_fft.cuh"
 #include "dp_spectrum_fft2.cuh"
+#include "dp_spectrum_fft3.cuh"
 
 namespace dp {
 
@@ -37,6 +38,8 @@ struct SpecHostPlan {
     std::vector<double> dx, den;
     bool use_v2 = false;              // register-codelet fast path (dp_spectrum_fft2.cuh)
     S2Plan s2;
+    bool use_v3 = false;              // long windows / wide bin ranges: three-factor batched passes (dp_spectrum_fft3.cuh)
+    S3Plan s3;
 };
 
 // _division_of_data (power_spectrum/__init__.py:33-51), same floating-point expressions.
@@ -119,6 +122,9 @@ static int make_spec_plan(int64_t T, double dt, const double* freq, int F, SpecH
     const char* force = dev_env("DP_SPECTRUM_ENGINE");      // "v1" forces the general engine (validation)
     pl->use_v2 = !(force && force[0] == 'v' && force[1] == '1') && make_s2_plan(L, pl->nkeep, &pl->s2);
     if (pl->use_v2) { pl->P = pl->s2.P; return DP_OK; }
+    const bool force_v1 = force && force[0] == 'v' && force[1] == '1';
+    pl->use_v3 = !force_v1 && make_s3_plan(L, pl->nkeep, &pl->s3);
+    if (pl->use_v3) { pl->P = pl->s3.P; return DP_OK; }
     if (!make_fft_split(L, &pl->sl)) {
         set_error("power_fft: window length %d has a prime factor > %d or no usable split", L, FFT_MAX_RADIX);
         return DP_ERR_UNSUPPORTED;
@@ -272,7 +278,8 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
     // v2: w256, wsub, fine, coarse (256 each), unused, w_L table
     int lens_v1[6] = {pl.sp.n1, pl.sp.n2, pl.P, pl.sl.n1, pl.sl.n2, pl.L};
     int lens_v2[6] = {6 * 256, 1, 1, 1, 1, pl.L};
-    const int* lens = pl.use_v2 ? lens_v2 : lens_v1;
+    int lens_v3[6] = {S3_TAB_BLOCKS * 256, 1, 1, 1, 1, pl.L};
+    const int* lens = pl.use_v2 ? lens_v2 : pl.use_v3 ? lens_v3 : lens_v1;
     for (int i = 0; i < 6; i++) { l.off_tw[i] = o; o += align_up((size_t)lens[i] * sizeof(cplx), 256); }
     l.off_starts = o; o += align_up(pl.starts.size() * sizeof(int), 256);
     l.off_idx0 = o;   o += align_up((size_t)F * sizeof(int), 256);
@@ -286,6 +293,13 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
         l.nslots = (int)imin<int64_t>(l.nslots, atoi(dev_env("DP_S2_GRID")));
     // v2: A[P] complex (+ Sr[P] real when |X_a|^2 of a window pair cannot be parked in the SM's 256 KB of tensor memory)
     l.slab_elems = pl.use_v2 ? (size_t)pl.P + (s2_parks_in_tmem(pl.s2) ? 0 : (size_t)pl.P / 2) : (size_t)pl.P + pl.L;
+    if (pl.use_v3) {
+        // a batch of series passes through the seven grid-wide passes together; its slabs (P complex per series) are
+        // sized to stay in L2 between the passes, the C arrays of pass 6 (L complex per series) follow them
+        int64_t batch = imax<int64_t>(1, (int64_t)(64u << 20) / ((int64_t)pl.P * (int64_t)sizeof(cplx)));
+        if (dev_env("DP_S3_BATCH") && atoi(dev_env("DP_S3_BATCH")) > 0) batch = atoi(dev_env("DP_S3_BATCH"));
+        l.nslots = (int)imin<int64_t>(S, batch);
+    }
     l.off_scratch = o; o += align_up((size_t)l.nslots * l.slab_elems * sizeof(cplx), 256);
     l.total = o;
     return l;
@@ -321,6 +335,14 @@ int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* pi
     return DP_OK;
 }
 
+int dp_power_fft_engine(int64_t T, double dt, const double* freq, int F) {
+    dp::SpecHostPlan pl;
+    if (!freq) return -DP_ERR_INVALID;
+    int rc = dp::make_spec_plan(T, dt, freq, F, &pl);
+    if (rc) return -rc;
+    return pl.use_v2 ? 2 : pl.use_v3 ? 3 : 1;
+}
+
 int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
                          int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
                          int n_windows, void* workspace, size_t workspace_bytes, void* stream) {
@@ -351,6 +373,34 @@ int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stri
     dp::cplx* tw[6];
     for (int i = 0; i < 6; i++) tw[i] = (dp::cplx*)(ws + lay.off_tw[i]);
     // tables and window starts are (re)written by every call: deterministic, and stream-ordered with the kernels
+    if (pl.use_v3) {
+        auto kt = dp::s3_tables_kernel;
+        DP_LAUNCH(kt, dim3(1), dim3(256), 0, st, tw[0], pl.s3.m1, pl.s3.m2, pl.s3.P);
+        DP_CUDA_OK(cudaGetLastError());
+        rc = dp::launch_twiddles(tw[5], pl.L, st);
+        if (rc) return rc;
+        dp::S3Params p;
+        p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;
+        p.tb_len = (int)tb_len; p.tb_stride = tb_stride;
+        p.tb_shift = -1;
+        if (tb_len > 0 && (tb_len & (tb_len - 1)) == 0) { p.tb_shift = 0; while ((1LL << p.tb_shift) < tb_len) p.tb_shift++; }
+        p.pl = pl.s3;
+        p.g_tab = tw[0]; p.g_twL = tw[5];
+        p.slab = (dp::cplx*)(ws + lay.off_scratch);
+        p.cbuf = p.slab + (size_t)lay.nslots * pl.P;
+        p.spec_stride = (int64_t)npieces * pl.nkeep;
+        p.lo = pl.lo; p.nkeep = pl.nkeep;
+        p.dt = dt; p.acf_scale = 1.0 / ((double)pl.P * (double)pl.L);
+        for (int s0 = 0; s0 < S; s0 += lay.nslots) {
+            p.s0 = s0; p.bs = dp::imin(lay.nslots, S - s0);
+            for (int w = first_window; w < first_window + n_windows; w++) {
+                p.t0 = pl.starts[w];
+                p.spec = (double*)(ws + lay.off_spec) + ((size_t)s0 * npieces + w) * pl.nkeep;
+                if ((rc = dp::s3_run_window(p, max_ctas, st))) return rc;
+            }
+        }
+        return DP_OK;
+    }
     if (pl.use_v2) {
         auto kt = dp::s2_tables_kernel;
         int a1, a2, b1, b2;

@@ -388,6 +388,14 @@ class Ops:
                       _hptr(starts), max_pieces)
         return L.value, [[int(s), int(s) + L.value] for s in starts[:n.value]]
 
+    def fft_engine(self, T, dt, frequency_range):
+        """Transform engine that serves this spectrum (dp_power_fft_engine: 1 general, 2 slab, 3 long-window)."""
+        f = _host(frequency_range, np.float64)
+        rc = self.lib.cdll.dp_power_fft_engine(int(T), float(dt), _hptr(f), f.size)
+        if rc < 0:
+            raise _lib.DpError(-rc, "dp_power_fft_engine")
+        return rc
+
     def fft_c2c(self, x, direction=-1):
         be = self.be
         x = be.asarray(x, np.complex128)

@@ -241,6 +241,11 @@ int dp_power_fft_finish(int64_t T, int S, double dt, const double* freq, int F, 
                         void* workspace, size_t workspace_bytes, void* stream);
 int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* piece_len,
                         int* n_pieces, int* starts, int max_pieces);
+/* Which transform engine serves this (T, dt, freq) (host query, for tests and benchmarks): 2 = one persistent CTA per
+ * series and window pair over an L2-resident slab (padded window length <= 65536), 3 = batched three-factor passes
+ * (longer windows, e.g. cfg 5-B's single 2^17-sample window, or wide kept-bin ranges), 1 = the general mixed-radix
+ * engine (window lengths without a usable factorisation); < 0: the error code dp_power_fft would return. */
+int dp_power_fft_engine(int64_t T, double dt, const double* freq, int F);
 
 /* ------------------------------------------------------------------------------------
  * A6  power spectrum, maximum-entropy (Burg) method (selector key 1).

@@ -364,6 +364,34 @@ def test_power_fft_long_windows(kops):
     assert np.array_equal(ps.argmax(0), ref.argmax(0))
 
 
+@pytest.mark.parametrize("nt,dt,res,nf", [(6000, 0.001, None, 2500),      # P = 16384 but 2500 kept bins: too wide for the v2 bin pass
+                                          (9000, 0.002, 0.125, 2400),     # L = 4000, three windows, wide bin range
+                                          (45000, 0.001, None, 300),      # P = 131072 = 32 x 64 x 64, n1' = 150 (15 x 10)
+                                          (100000, 0.001, 1.0 / 45.056, 700)])   # L = 45056 = 2^12 * 11 (n1' = 256), three windows
+def test_power_fft_long_window_engine(kops, nt, dt, res, nf):
+    """Windows with P > 65536 or wide kept-bin ranges: the three-factor batched engine (dp_spectrum_fft3.cuh)."""
+    rng = np.random.default_rng(nt + 1)
+    ns = 2 if not is_cuda(kops) else 19
+    x = _series(rng, nt, ns, dt)
+    if res is None:
+        res = 1.0 / (nt * dt)
+    f = np.arange(nf) * res
+    assert kops.fft_engine(nt, dt, f) == 3
+    ps = to_np(kops.power_fft(x, dt, f))
+    ref = port.fft_spectra(x, dt, f, use_fft_correlate=True)
+    assert ps.shape == ref.shape
+    assert relerr(ps, ref) < TOL
+    assert np.array_equal(ps.argmax(0), ref.argmax(0))
+    # series-major and blocked-time layouts (what the multi-GPU exchange delivers) give the same bits
+    xs = np.ascontiguousarray(x.T)
+    ps2 = to_np(kops.power_fft(xs, dt, f, series_major=True))
+    assert np.array_equal(ps, ps2)
+    if nt % 4 == 0:
+        xb = np.ascontiguousarray(xs.reshape(ns, 4, nt // 4).transpose(1, 0, 2))       # (G, S, Tb)
+        ps3 = to_np(kops.power_fft(xb, dt, f, series_major=True))
+        assert np.array_equal(ps, ps3)
+
+
 @pytest.mark.gpu
 def test_power_fft_cfg5b_single_window(cuda_ops):
     """cfg 5-B: resolution 2^-17/dt so that ONE window covers the whole 2^17-sample run

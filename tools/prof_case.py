@@ -1,6 +1,6 @@
 """One isolated call of a hot-path kernel at bench-relevant sizes, for `ncu --set full` captures.
 
-    python tools/prof_case.py fft5a|project|contract|mem|corr [reps]
+    python tools/prof_case.py fft5a|fft5b|project|contract|mem|corr [reps]
 """
 import itertools
 import os
@@ -24,6 +24,12 @@ if case == "fft5a":
     x = torch.randn((S, 131072), dtype=torch.complex128, device=dev)
     for _ in range(reps):
         out = ops.power_fft(x, 0.001, freq, series_major=True)
+elif case == "fft5b":
+    S = int(os.environ.get("PC_S", 64))
+    x = torch.randn((S, 131072), dtype=torch.complex128, device=dev)
+    f5b = np.arange(5244) * (1.0 / (131072 * 0.001))
+    for _ in range(reps):
+        out = ops.power_fft(x, 0.001, f5b, series_major=True)
 elif case in ("project", "contract"):
     dims = np.array([16, 16, 20]); nc = int(np.prod(dims)); T = int(os.environ.get("PC_T", 4096))
     cell = np.diag([4.0] * 3); unit_pos = np.array([[0, 0, 0], [2.0, 2, 2]])
