@@ -44,6 +44,7 @@ KB = 0.831446            # u A^2 / ps^2 / K  (reference's k_B, iofile/__init__.p
 TEMP = 400.0
 SEED = 20260101
 FREQ = np.arange(0, 40.05, 0.05)
+WORKLOAD = "cfg5-A"      # --workload cfg5-B: ONE window of the whole run (resolution 1/(T dt)), 5244 frequencies up to 40 THz
 CHUNK = 1024             # frames generated / copied per chunk
 
 
@@ -199,10 +200,12 @@ def run_reference(args):
 
 
 def config_dict(wl, frames, gpus):
-    return {"workload": "cfg5-A synthetic 2-atom cubic cell, 16x16x20 supercell (10240 atoms), "
+    spectra = ("801 frequencies, 7 windows of 20000" if WORKLOAD == "cfg5-A" else
+               f"{len(FREQ)} frequencies at the resolution 1/(T dt): one window of {frames} samples, padded transforms of "
+               f"{2 * frames} points")
+    return {"workload": f"{WORKLOAD} synthetic 2-atom cubic cell, 16x16x20 supercell (10240 atoms), "
                         f"{frames} frames, full commensurate q-mesh (5120 q x 6 modes), "
-                        "projection + eigenvector contraction + FFT power spectra (801 frequencies, "
-                        "7 windows of 20000)",
+                        f"projection + eigenvector contraction + FFT power spectra ({spectra})",
             "atoms": wl["n_atoms"], "frames": frames, "q_points": wl["Q"], "modes_per_q": wl["M"],
             "series": wl["Q"] * wl["M"], "frequencies": len(FREQ), "dt_ps": DT,
             "sharding": f"time-block x{gpus}" + (" (4096-frame blocks dealt cyclically to the ranks) + one exchange over NVLink "
@@ -450,10 +453,10 @@ def run_ours(args):
     series_peaks = series_peaks.cpu().numpy().astype(np.int64)
     parity = {"tolerance": 1e-10}
     gpath = os.path.join(ROOT, "tests", "golden", "bench_cfg5a_series_sums.npz")
-    if args.write_golden and world == 1 and rank == 0 and frames == 131072:
+    if args.write_golden and world == 1 and rank == 0 and frames == 131072 and WORKLOAD == "cfg5-A":
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.savez_compressed(os.path.join(ROOT, "gpurun_out", "bench_cfg5a_series_sums.npz"), sums=series_sums, peaks=series_peaks)
-    if os.path.exists(gpath) and frames == 131072:
+    if os.path.exists(gpath) and frames == 131072 and WORKLOAD == "cfg5-A":
         gold = np.load(gpath)
         parity["cross_n"] = {"reference": "single-GPU run of this bench (tests/golden/bench_cfg5a_series_sums.npz)",
                              "series": int(series_sums.size),
@@ -583,12 +586,14 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     mean = {k: (statistics.mean(x) if x else 0.0) for k, x in stage_ms.items()}
     # algorithmic bytes per launch on ONE rank
-    L, npieces = 20000, 7
+    L, pieces = ops.fft_pieces(frames, DT, FREQ)
+    npieces = len({tuple(pc) for pc in pieces})         # a window that spans the whole run is listed twice, read once
+    engine = ops.fft_engine(frames, DT, FREQ)
     s_loc = wl["Q"] * wl["M"] // world
     bytes_stage = {"project": (24.0 * wl["n_atoms"] + 16.0 * wl["M"] * wl["Q"]) * tl,
                    "contract": 2 * 16.0 * wl["M"] * wl["Q"] * tl,
                    "spectra": (16.0 * L * npieces + 8.0 * len(FREQ)) * s_loc}
-    kernels = {"project": "project_fft_kernel", "contract": "project_phonon_series_kernel", "spectra": "spectrum2_kernel"}
+    kernels = {"project": "project_fft_kernel", "contract": "project_phonon_series_kernel", "spectra": "spectrum2_kernel" if engine == 2 else "s3_col/s3_row/s3_bins kernels (long-window engine)" if engine == 3 else "spectrum_items_kernel"}
     stages = {}
     for k in ("project", "contract", "spectra"):
         ach = bytes_stage[k] / (mean[k] * 1e-3) / 1e9 if mean[k] > 0 else 0.0
@@ -610,11 +615,14 @@ def run_ours(args):
     # DRAM traffic of the dominant kernels: dram__bytes_read.sum + dram__bytes_write.sum of the newest `ncu --set full`
     # capture of each kernel listed in profiles/ncu_index.json (smaller launches of the same kernels: bytes per series /
     # per frame, scaled linearly to this launch)
-    ncu_traffic, ncu_src = ncu_traffic_from_profiles({"spectra": s_loc, "project": tl, "contract": tl})
+    ncu_units = {"spectra": s_loc, "project": tl, "contract": tl}
+    if engine != 2:
+        del ncu_units["spectra"]       # the committed capture is of spectrum2_kernel (cfg 5-A)
+    ncu_traffic, ncu_src = ncu_traffic_from_profiles(ncu_units)
     # fp64 view of the spectrum stage: 770.5 k warp-level fp64 instructions per series (7 windows, processed as
     # 3 pairs + 1 single; ncu instruction mix, profiles/r01_ncu_spectrum2.jsonl) against the measured
     # 64 lanes/clk/SM (tools/micro/fp64_rate.cu: 18.3 T lane-ops/s)
-    fp64_lane_ops = 770.5e3 * 32 * s_loc
+    fp64_lane_ops = 770.5e3 * 32 * s_loc if WORKLOAD == "cfg5-A" else 0.0
     fp64 = {"lane_ops": fp64_lane_ops, "achieved_Tops": fp64_lane_ops / (mean["spectra"] * 1e-3) / 1e12 if mean["spectra"] else 0.0,
             "peak_Tops": 18.3, "peak_source": "measured, tools/micro/fp64_rate.cu (DFMA/DADD/DMUL, 63.6 of 64 lanes/clk/SM)"}
     fp64["frac"] = fp64["achieved_Tops"] / fp64["peak_Tops"]
@@ -623,7 +631,7 @@ def run_ours(args):
                 "unit": "GB/s", "frac": stages[dom]["frac_of_hbm"], "traffic": ncu_traffic.get(dom),
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture of a smaller launch "
                                 "(%s), scaled linearly to this launch" % ncu_src.get(dom), "algorithmic_bytes": bytes_stage[dom],
-                "fp64": fp64 if dom == "spectra" else None, "peak_source": peak_src,
+                "fp64": fp64 if (dom == "spectra" and WORKLOAD == "cfg5-A") else None, "peak_source": peak_src,
                 "share_of_step": mean[dom] / max(sum(mean.values()), 1e-9),
                 "note": "algorithmic bytes per launch / CUDA-event duration of the stage on rank 0; "
                         "the FFT-spectrum kernel is fp64-FMA limited before it is HBM limited (DESIGN.md)"}
@@ -663,6 +671,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--workload", default="cfg5-A", choices=["cfg5-A", "cfg5-B"],
+                    help="cfg5-A (headline): 801 frequencies, 7 windows of 20000; cfg5-B: one window of the whole run, 5244 frequencies")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -680,6 +690,11 @@ def main():
     ap.add_argument("--cpu-q", type=int, default=4)
     ap.add_argument("--cpu-series", type=int, default=8)
     args = ap.parse_args()
+    if args.workload == "cfg5-B":
+        global FREQ, WORKLOAD
+        WORKLOAD = "cfg5-B"
+        FREQ = np.arange(5244) * (1.0 / (args.frames * DT))
+        args.skip_methods = True        # MEM / direct correlation do not depend on the window plan: reported by cfg5-A
     if args.impl == "reference":
         run_reference(args)
     else:

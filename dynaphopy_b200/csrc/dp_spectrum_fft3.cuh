@@ -28,11 +28,14 @@ constexpr int S3_WARPS = S3_THREADS / 32;
 constexpr int S3_TILE_COLS = S3_THREADS / 16;      // pass 6a: 16 threads per column
 constexpr int S3_CPITCH = S3_TILE_COLS + 1;        // odd pitch (16-byte elements)
 constexpr int S3_HGROUPS = S3_THREADS / 32;        // pass 6b: warp h owns the bins j = h (mod 8) of its 32 residues
-constexpr int S3_SLOTS = 4;                        // bins per thread and round in pass 6b
+constexpr int S3_BCOLS = 32;                       // pass 6b: columns per shared-memory stage (16 KB)
+constexpr int S3_BSTAGES = 4;                      // ring depth
+constexpr size_t S3_BINS_B_SMEM = (size_t)S3_BSTAGES * S3_BCOLS * 32 * sizeof(double2);
 
 typedef SubCfg<16, 1, 1> D16;
 typedef SubCfg<8, 4, 4> D32;
 typedef SubCfg<8, 8, 4> D64;
+typedef SubCfg<8, 8, 8> R64;         // row pass: 8 points per lane (the next tile is prefetched), 8 lanes = one 128-byte run
 typedef SubCfg<16, 8, 8> D128;
 typedef SubCfg<16, 16, 16> D256;
 
@@ -108,11 +111,12 @@ __global__ void __launch_bounds__(S3_THREADS, 2) s3_col_kernel(const __grid_cons
     const int tps = OUTER ? M / C::NS : n1 * (n3 / C::NS); // tiles per series
     const int64_t total = (int64_t)p.bs * tps;
     const double sc = p.acf_scale;
-    for (int64_t tile = (int64_t)blockIdx.x * S3_WARPS + warp; tile < total; tile += (int64_t)gridDim.x * S3_WARPS) {
-        const int b = (int)(tile / tps), tt = (int)(tile % tps);
-        cplx* __restrict__ A = p.slab + (size_t)b * P;
-        int col, k1 = 0, stride;
-        cplx* base;
+    // tile -> slab address of the warp's sub-transforms
+    auto decode = [&](int64_t tile, int& b, int& col, int& k1, cplx*& base, int& stride) {
+        b = (int)(tile / tps);
+        const int tt = (int)(tile % tps);
+        cplx* A = p.slab + (size_t)b * P;
+        k1 = 0;
         if (OUTER) { col = tt * C::NS + seq; base = A + col; stride = M; }
         else {
             const int tpb = n3 / C::NS;
@@ -121,10 +125,11 @@ __global__ void __launch_bounds__(S3_THREADS, 2) s3_col_kernel(const __grid_cons
             base = A + (size_t)k1 * M + col;
             stride = n3;
         }
-        cplx v[16];
+    };
+    const bool plain = p.tb_len == 0 && p.stride_t == 1;
+    auto load = [&](cplx* dst, int b, int col, const cplx* base, int stride) {
         if (PASS == 1) {
             const cplx* __restrict__ x = p.series + (int64_t)(p.s0 + b) * p.stride_s;
-            const bool plain = p.tb_len == 0 && p.stride_t == 1;
 #pragma unroll
             for (int i = 0; i < C::NB1; i++)
 #pragma unroll
@@ -132,13 +137,40 @@ __global__ void __launch_bounds__(S3_THREADS, 2) s3_col_kernel(const __grid_cons
                     const int idx = (a * C::R2 + g + C::TG * i) * M + col;
                     cplx val = make_double2(0.0, 0.0);
                     if (idx < L) val = plain ? __ldcs(x + p.t0 + idx) : __ldcs(x + s3_time_offset(p, p.t0 + idx));
-                    v[i * C::R1 + a] = val;
+                    dst[i * C::R1 + a] = val;
                 }
         } else {
 #pragma unroll
             for (int i = 0; i < C::NB1; i++)
 #pragma unroll
-                for (int a = 0; a < C::R1; a++) v[i * C::R1 + a] = __ldcg(base + (size_t)(a * C::R2 + g + C::TG * i) * stride);
+                for (int a = 0; a < C::R1; a++) dst[i * C::R1 + a] = __ldcg(base + (size_t)(a * C::R2 + g + C::TG * i) * stride);
+        }
+    };
+    // sub-transforms of <= 8 points per lane: the samples of the next tile are fetched while this one is transformed
+    constexpr int NV = C::NB1 * C::R1;
+    constexpr bool PRE = NV <= 8;
+    cplx nx[PRE ? NV : 1];
+    const int64_t tile0 = (int64_t)blockIdx.x * S3_WARPS + warp, tstep = (int64_t)gridDim.x * S3_WARPS;
+    if (PRE && tile0 < total) {
+        int b, col, k1, stride; cplx* base;
+        decode(tile0, b, col, k1, base, stride);
+        load(nx, b, col, base, stride);
+    }
+    for (int64_t tile = tile0; tile < total; tile += tstep) {
+        int b, col, k1, stride;
+        cplx* base;
+        decode(tile, b, col, k1, base, stride);
+        cplx v[16];
+        if (PRE) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) v[i] = nx[i];
+            if (tile + tstep < total) {
+                int b2, col2, k12, stride2; cplx* base2;
+                decode(tile + tstep, b2, col2, k12, base2, stride2);
+                load(nx, b2, col2, base2, stride2);
+            }
+        } else {
+            load(v, b, col, base, stride);
         }
         __syncwarp();                  // the exchange slab of the previous tile has been read by every lane
         sub_dit<C>(v, E, T, g);
@@ -186,20 +218,40 @@ __global__ void __launch_bounds__(S3_THREADS, 2) s3_row_kernel(const __grid_cons
     for (int k = tid; k < 768; k += S3_THREADS) fine[k] = p.g_tab[S3_TAB_FINE * 256 + k];
     __syncthreads();
     pdl_wait();
-    const int seq = lane % C::NS, g = lane / C::NS;
+    // rows are contiguous along the element index: group lane fastest, so a quarter-warp reads one 128-byte run
+    // (the column passes map the sequence index fastest for the same reason)
+    const int seq = lane / C::TG, g = lane % C::TG;
     cplx* E = smem + 1280 + (size_t)warp * SUBFFT_EWARP_MAX + seq * C::ESEQ;
     const int P = p.pl.P, n1 = p.pl.n1, n2 = p.pl.n2, n3 = p.pl.n3;
     const int tps = n1 * n2 / C::NS;
     const int64_t total = (int64_t)p.bs * tps;
-    for (int64_t tile = (int64_t)blockIdx.x * S3_WARPS + warp; tile < total; tile += (int64_t)gridDim.x * S3_WARPS) {
+    auto row_of = [&](int64_t tile, int& row) -> cplx* {
         const int b = (int)(tile / tps), tt = (int)(tile % tps);
-        const int row = tt * C::NS + seq;
-        cplx* __restrict__ Ar = p.slab + (size_t)b * P + (size_t)row * n3;
-        cplx v[16];
+        row = tt * C::NS + seq;
+        return p.slab + (size_t)b * P + (size_t)row * n3;
+    };
+    auto load = [&](cplx* dst, const cplx* Ar) {
 #pragma unroll
         for (int i = 0; i < C::NB1; i++)
 #pragma unroll
-            for (int a = 0; a < C::R1; a++) v[i * C::R1 + a] = __ldcg(Ar + a * C::R2 + g + C::TG * i);
+            for (int a = 0; a < C::R1; a++) dst[i * C::R1 + a] = __ldcg(Ar + a * C::R2 + g + C::TG * i);
+    };
+    constexpr int NV = C::NB1 * C::R1;
+    constexpr bool PRE = NV <= 8;                  // see s3_col_kernel
+    cplx nx[PRE ? NV : 1];
+    const int64_t tile0 = (int64_t)blockIdx.x * S3_WARPS + warp, tstep = (int64_t)gridDim.x * S3_WARPS;
+    if (PRE && tile0 < total) { int row; load(nx, row_of(tile0, row)); }
+    for (int64_t tile = tile0; tile < total; tile += tstep) {
+        int row;
+        cplx* __restrict__ Ar = row_of(tile, row);
+        cplx v[16];
+        if (PRE) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) v[i] = nx[i];
+            if (tile + tstep < total) { int row2; load(nx, row_of(tile + tstep, row2)); }
+        } else {
+            load(v, Ar);
+        }
         __syncwarp();
         sub_dit<C>(v, E, T, g);
 #pragma unroll
@@ -282,10 +334,31 @@ __global__ void __launch_bounds__(S3_THREADS) s3_bins_a_kernel(const __grid_cons
 
 // ---- pass 6b: the kept bins by Horner's rule -------------------------------------------------------------------
 // Kept bin e (sorted-frequency index lo + e) is FFT bin k = (k_lo + e) mod L of residue (k_lo + e) mod n1'.  A CTA owns
-// 32 consecutive residues of one series: lane = residue, warp h owns the bins e = r + n1' j with j = h (mod 8), so the
-// eight warps read the same 512-byte run of C per column (once from L2, then from L1) and every value feeds
-// S3_SLOTS bins of the thread.
+// 32 consecutive residues of one series: lane = residue, warp h owns the bins e = r + n1' j with j = h (mod 8).  The
+// columns C[j2][32 residues] (one 512-byte run each) stream from the highest j2 down through a ring of shared-memory
+// stages filled with cp.async, S3_BSTAGES - 1 stages ahead of the arithmetic: every value is fetched once per CTA and
+// feeds SLOTS bins of each of the eight warps.
+__device__ __forceinline__ void s3_cp16(cplx* dst_smem, const cplx* src) {
+#ifdef DP_EMUL
+    *dst_smem = *src;
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void s3_cp_commit() {
+#ifndef DP_EMUL
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int N> __device__ __forceinline__ void s3_cp_wait() {
+#ifndef DP_EMUL
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+#endif
+}
+
+template <int SLOTS>
 __global__ void __launch_bounds__(S3_THREADS) s3_bins_b_kernel(const __grid_constant__ S3Params p) {
+    DP_DYNSMEM(cplx, ring);            // [S3_BSTAGES][S3_BCOLS][32]
     const int L = p.pl.L, half = p.pl.half, NP = p.pl.np, n2L = p.pl.n2L;
     const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
     const int nrb = (NP + 31) / 32;
@@ -298,42 +371,66 @@ __global__ void __launch_bounds__(S3_THREADS) s3_bins_b_kernel(const __grid_cons
     double* __restrict__ spec = p.spec + (int64_t)b * p.spec_stride;
     const int nres = r < NP ? (p.nkeep - r + NP - 1) / NP : 0;        // kept bins of this residue: e = r + NP j, j < nres
     const int nres_max = (p.nkeep + NP - 1) / NP;
-    for (int j0 = 0; j0 < nres_max; j0 += S3_HGROUPS * S3_SLOTS) {     // rounds (uniform over the CTA)
-        cplx acc[S3_SLOTS], z[S3_SLOTS];
-        int nb = 0;
+    const int nchunks = (n2L + S3_BCOLS - 1) / S3_BCOLS;
+    auto issue = [&](int c) {          // chunk c = the columns n2L-1 - c*S3_BCOLS - i, i < S3_BCOLS; row i of its stage
+        if (c < nchunks) {
+            const int hi = n2L - 1 - c * S3_BCOLS;
+            cplx* dst = ring + (size_t)(c % S3_BSTAGES) * (S3_BCOLS * 32);
 #pragma unroll
-        for (int s = 0; s < S3_SLOTS; s++) {
+            for (int u = 0; u < S3_BCOLS / S3_HGROUPS; u++) {
+                const int i = h + S3_HGROUPS * u;
+                if (hi - i >= 0) s3_cp16(dst + i * 32 + lane, Cin + (size_t)(hi - i) * NP);
+            }
+        }
+        s3_cp_commit();                // one group per call, empty or not: the wait below counts groups
+    };
+    for (int j0 = 0; j0 < nres_max; j0 += S3_HGROUPS * SLOTS) {        // rounds (uniform over the CTA)
+        cplx acc[SLOTS], z[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) {
             const int j = j0 + h + S3_HGROUPS * s;
             acc[s] = make_double2(0.0, 0.0);
             z[s] = make_double2(0.0, 0.0);
-            if (j < nres) { z[s] = __ldg(p.g_twL + (k_lo + r + NP * j) % L); nb = s + 1; }
+            if (j < nres) z[s] = __ldg(p.g_twL + (k_lo + r + NP * j) % L);
         }
-        if (nb == 0) continue;
-        int j2 = n2L - 1;
-        for (; j2 >= 3; j2 -= 4) {
-            cplx cv[4];
+        const bool active = j0 + h < nres_max;                         // warp-uniform
+        __syncthreads();               // the previous round has left the ring
+        for (int c = 0; c < S3_BSTAGES - 1; c++) issue(c);
+        for (int c = 0; c < nchunks; c++) {
+            s3_cp_wait<S3_BSTAGES - 2>();                              // this thread's part of chunk c has landed
+            __syncthreads();           // ... everybody's has, and chunk c-1 has been consumed by every warp
+            issue(c + S3_BSTAGES - 1); // into the stage of chunk c-1
+            if (active) {
+                const cplx* st = ring + (size_t)(c % S3_BSTAGES) * (S3_BCOLS * 32) + lane;
+                const int cnt = imin(S3_BCOLS, n2L - c * S3_BCOLS);
+                int i = 0;
+                for (; i + 4 <= cnt; i += 4) {
+                    cplx cv[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) cv[u] = __ldg(Cin + (size_t)(j2 - u) * NP);
+                    for (int u = 0; u < 4; u++) cv[u] = st[(i + u) * 32];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+                    for (int u = 0; u < 4; u++)
 #pragma unroll
-                for (int s = 0; s < S3_SLOTS; s++) {
-                    const cplx a = acc[s];
-                    acc[s].x = fma(a.x, z[s].x, fma(-a.y, z[s].y, cv[u].x));
-                    acc[s].y = fma(a.x, z[s].y, fma(a.y, z[s].x, cv[u].y));
+                        for (int s = 0; s < SLOTS; s++) {
+                            const cplx a = acc[s];
+                            acc[s].x = fma(a.x, z[s].x, fma(-a.y, z[s].y, cv[u].x));
+                            acc[s].y = fma(a.x, z[s].y, fma(a.y, z[s].x, cv[u].y));
+                        }
                 }
-        }
-        for (; j2 >= 0; j2--) {
-            const cplx cv = __ldg(Cin + (size_t)j2 * NP);
+                for (; i < cnt; i++) {
+                    const cplx cv = st[i * 32];
 #pragma unroll
-            for (int s = 0; s < S3_SLOTS; s++) {
-                const cplx a = acc[s];
-                acc[s].x = fma(a.x, z[s].x, fma(-a.y, z[s].y, cv.x));
-                acc[s].y = fma(a.x, z[s].y, fma(a.y, z[s].x, cv.y));
+                    for (int s = 0; s < SLOTS; s++) {
+                        const cplx a = acc[s];
+                        acc[s].x = fma(a.x, z[s].x, fma(-a.y, z[s].y, cv.x));
+                        acc[s].y = fma(a.x, z[s].y, fma(a.y, z[s].x, cv.y));
+                    }
+                }
             }
         }
+        s3_cp_wait<0>();
 #pragma unroll
-        for (int s = 0; s < S3_SLOTS; s++) {
+        for (int s = 0; s < SLOTS; s++) {
             const int j = j0 + h + S3_HGROUPS * s;
             if (j < nres) spec[r + NP * j] = __dmul_rn(hypot(acc[s].x, acc[s].y), p.dt);
         }
@@ -412,7 +509,11 @@ template <int PASS> static int s3_launch_col(int n, int grid, cudaStream_t st, c
     switch (n) {
         case 16: DP_S3_COL(D16) break;
         case 32: DP_S3_COL(D32) break;
+#ifdef DP_S3_COL64_PRE
+        case 64: DP_S3_COL(R64) break;
+#else
         case 64: DP_S3_COL(D64) break;
+#endif
         case 128: DP_S3_COL(D128) break;
         default: DP_S3_COL(D256) break;
     }
@@ -431,7 +532,7 @@ static int s3_launch_row(int n, int grid, cudaStream_t st, const S3Params& p) {
     switch (n) {
         case 16: DP_S3_ROWK(D16) break;
         case 32: DP_S3_ROWK(D32) break;
-        case 64: DP_S3_ROWK(D64) break;
+        case 64: DP_S3_ROWK(R64) break;
         case 128: DP_S3_ROWK(D128) break;
         default: DP_S3_ROWK(D256) break;
     }
@@ -462,18 +563,37 @@ static int s3_run_window(const S3Params& p, int max_ctas, cudaStream_t st) {
     const S3Plan& pl = p.pl;
     const int cap = max_ctas > 0 ? max_ctas : 2 * imax(sm_count(), 1);
     auto grid_for = [&](int64_t warp_tiles) { return (int)imin<int64_t>((warp_tiles + S3_WARPS - 1) / S3_WARPS, cap); };
-    auto ns_of = [](int n) { return n == 16 ? 32 : (n == 32 || n == 64) ? 8 : n == 128 ? 4 : 2; };
+#ifdef DP_S3_COL64_PRE
+    auto ns_of = [](int n) { return n == 16 ? 32 : n == 32 ? 8 : (n == 64 || n == 128) ? 4 : 2; };
+#else
+    auto ns_of = [](int n) { return n == 16 ? 32 : (n == 32 || n == 64) ? 8 : n == 128 ? 4 : 2; };      // column passes
+#endif
+    auto ns_row = [](int n) { return n == 16 ? 32 : n == 32 ? 8 : (n == 64 || n == 128) ? 4 : 2; };       // row pass
     const int64_t bs = p.bs;
     int rc;
     if ((rc = s3_launch_col<1>(pl.n1, grid_for(bs * (pl.M / ns_of(pl.n1))), st, p))) return rc;
     if ((rc = s3_launch_col<2>(pl.n2, grid_for(bs * pl.n1 * (pl.n3 / ns_of(pl.n2))), st, p))) return rc;
-    if ((rc = s3_launch_row(pl.n3, grid_for(bs * (pl.n1 * pl.n2 / ns_of(pl.n3))), st, p))) return rc;
+    if ((rc = s3_launch_row(pl.n3, grid_for(bs * (pl.n1 * pl.n2 / ns_row(pl.n3))), st, p))) return rc;
     if ((rc = s3_launch_col<4>(pl.n2, grid_for(bs * pl.n1 * (pl.n3 / ns_of(pl.n2))), st, p))) return rc;
     if ((rc = s3_launch_col<5>(pl.n1, grid_for(bs * (pl.M / ns_of(pl.n1))), st, p))) return rc;
     const int64_t items_a = bs * ((pl.n2L + S3_TILE_COLS - 1) / S3_TILE_COLS);
     if ((rc = s3_launch_bins_a((int)imin<int64_t>(items_a, max_ctas > 0 ? max_ctas : 8 * imax(sm_count(), 1)), st, p))) return rc;
-    auto kb = s3_bins_b_kernel;
-    DP_CUDA_OK(DP_LAUNCH_PDL(kb, dim3((unsigned)(bs * ((pl.np + 31) / 32))), dim3(S3_THREADS), 0, st, p));
+    // bins per thread and round: the fewest slot-rounds, then the fewest passes over the columns
+    const int nres_max = (p.nkeep + pl.np - 1) / pl.np;
+    int slots = 4, best = 1 << 30;
+    for (int sl = 4; sl >= 2; sl--) {
+        const int cost = ((nres_max + S3_HGROUPS * sl - 1) / (S3_HGROUPS * sl)) * sl;
+        if (cost < best) { best = cost; slots = sl; }
+    }
+    const dim3 gb((unsigned)(bs * ((pl.np + 31) / 32)));
+#define DP_S3_BINS_B(SL)                                                                        \
+    {                                                                                           \
+        auto kb = s3_bins_b_kernel<SL>;                                                         \
+        DP_SET_SMEM_ONCE(kb, S3_BINS_B_SMEM);                                                   \
+        DP_CUDA_OK(DP_LAUNCH_PDL(kb, gb, dim3(S3_THREADS), S3_BINS_B_SMEM, st, p));             \
+    }
+    if (slots == 4) DP_S3_BINS_B(4) else if (slots == 3) DP_S3_BINS_B(3) else DP_S3_BINS_B(2)
+#undef DP_S3_BINS_B
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
 }
