@@ -245,7 +245,13 @@ __device__ __noinline__ void s2_pass2(const S2Params& p, cplx* __restrict__ A, d
     static_assert(!PARK || S2_WARPS % 4 == 0, "TMEM parking maps tile % 4 to the warp's lane quarter");
     S2_SMEM_HERE();
     const int n1 = p.pl.n1, n2 = p.pl.n2;
+    // rows are contiguous along the element index: group lane fastest, a quarter-warp reads one 128-byte run of its row
+    // (the column passes map the sequence index fastest for the same reason)
+#ifdef DP_S2_ROW_SEQFAST
     const int seq = lane % C::NS, g = lane / C::NS;
+#else
+    const int seq = lane / C::TG, g = lane % C::TG;
+#endif
     cplx* Ew = sm.E + (size_t)warp * SUBFFT_EWARP_MAX;
     cplx* E = Ew + seq * C::ESEQ;
     const int ntiles = n1 / C::NS;
