@@ -208,6 +208,7 @@ def config_dict(wl, frames, gpus):
                         f"projection + eigenvector contraction + FFT power spectra ({spectra})",
             "atoms": wl["n_atoms"], "frames": frames, "q_points": wl["Q"], "modes_per_q": wl["M"],
             "series": wl["Q"] * wl["M"], "frequencies": len(FREQ), "dt_ps": DT,
+            "intermediate": "pair-major bare lattice DFT; one wave vector per pair (q, -q) is projected and stored (2564 of 5120), both are contracted (--full-mesh: all 5120)",
             "sharding": f"time-block x{gpus}" + (" (4096-frame blocks dealt cyclically to the ranks) + one exchange over NVLink "
                                                    "peer memory (copy engines; NCCL all-to-all fallback)" if gpus > 1 else ""),
             "l2_policy": "inputs (32 GB velocities, 64 GB projected series) far exceed the 126 MB L2"}
@@ -298,7 +299,7 @@ def run_ours(args):
     plan = pipeline.CommensuratePlan(wl["cell"], DIMS, wl["pos"], wl["mass"], wl["typ"], wl["n_prim"], wl["q_cart"])
     assert plan.usable() and plan.commensurate.all()
     eig = random_unitary_eigenvectors(torch, dev, wl["Q"], wl["M"])
-    pipe = pipeline.MeshPipeline(plan, eig, FREQ, DT, ops=ops, algorithm=2)
+    pipe = pipeline.MeshPipeline(plan, eig, FREQ, DT, ops=ops, algorithm=2, use_mirror=not args.full_mesh)
     assert pipe.fold_twiddle        # primitive cell: the projection twiddle rides on the eigenvectors
 
     # ---- device-resident inputs -------------------------------------------------------------------
@@ -366,31 +367,26 @@ def run_ours(args):
         for ci, t0 in enumerate(range(0, tl, CH)):
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a.record()
-            vc = ops.project_commensurate(v[t0:t0 + CH], plan.dims, plan.unit_type, plan.n_prim, pipe.d_qbin, None,
-                                          pair_major=True)
+            vc = pipe.project_chunk(v[t0:t0 + CH])
             b.record()
             if world == 1:
-                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send, t_offset=t0, t_total=tl,
-                                          pair_major=True)
+                pipe.contract_chunk(vc, out=send, t_offset=t0, t_total=tl)
                 c.record()
             elif use_peers and peer_stores:              # the contraction kernel stores into the peers' receive buffers
                 off = ((rank * (tl // CH) + ci) * pipe.q_block * pipe.M * CH) * 16
-                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, t_total=CH, pair_major=True,
-                                          block_ptrs=[peer_ptrs[dst] + off for dst in range(world)])
+                pipe.contract_chunk(vc, t_total=CH, block_ptrs=[peer_ptrs[dst] + off for dst in range(world)])
                 c.record()
             elif use_peers:                              # local send slot, copy engines push the blocks over NVLink
                 slot = ci % 2
                 pipe.peer_wait_slot(slot)
-                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, t_total=CH, pair_major=True,
-                                          block_ptrs=pipe.peer_block_ptrs(send2[slot], ci))
+                pipe.contract_chunk(vc, t_total=CH, block_ptrs=pipe.peer_block_ptrs(send2[slot], ci))
                 c.record()
                 pipe.peer_push(send2[slot], ci, slot)
             else:
                 slot = ci % 2
                 if pending[slot] is not None:
                     pending[slot].wait()
-                ops.project_phonon_series(vc, pipe.d_eig_folded, q_block=pipe.q_block, out=send2[slot], t_total=CH,
-                                          pair_major=True)
+                pipe.contract_chunk(vc, out=send2[slot], t_total=CH)
                 c.record()
                 outs = [torch.view_as_real(recv[src, ci]) for src in range(world)]
                 ins = [torch.view_as_real(send2[slot, dst]) for dst in range(world)]
@@ -590,8 +586,10 @@ def run_ours(args):
     npieces = len({tuple(pc) for pc in pieces})         # a window that spans the whole run is listed twice, read once
     engine = ops.fft_engine(frames, DT, FREQ)
     s_loc = wl["Q"] * wl["M"] // world
-    bytes_stage = {"project": (24.0 * wl["n_atoms"] + 16.0 * wl["M"] * wl["Q"]) * tl,
-                   "contract": 2 * 16.0 * wl["M"] * wl["Q"] * tl,
+    # the intermediate holds one wave vector of every pair (q, -q) (real velocities: Hermitian lattice DFT)
+    q_stored = int(pipe.d_qmap.shape[0]) if getattr(pipe, "mirror", False) else wl["Q"]
+    bytes_stage = {"project": (24.0 * wl["n_atoms"] + 16.0 * wl["M"] * q_stored) * tl,
+                   "contract": 16.0 * wl["M"] * (q_stored + wl["Q"]) * tl,
                    "spectra": (16.0 * L * npieces + 8.0 * len(FREQ)) * s_loc}
     kernels = {"project": "project_fft_kernel", "contract": "project_phonon_series_kernel", "spectra": "spectrum2_kernel" if engine == 2 else "s3_col/s3_row/s3_bins kernels (long-window engine)" if engine == 3 else "spectrum_items_kernel"}
     stages = {}
@@ -678,6 +676,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=131072, help="total frames (default: the full 2^17 workload)")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--full-mesh", action="store_true",
+                    help="project and store every wave vector instead of one per pair (q, -q) (comparison run)")
     ap.add_argument("--skip-methods", action="store_true")
     ap.add_argument("--sharding", default="auto", choices=["auto", "cyclic", "blocks"],
                     help="N > 1: chunk-cyclic time sharding with overlapped spectra (default) or one time block per rank")

@@ -240,16 +240,23 @@ __device__ __forceinline__ void ps_cp_wait_all() {
 #endif
 }
 
-template <int MT>   // MT > 0: compile-time M (inputs kept in registers); 0: any M
+// MIRROR (velocities are real, so the lattice DFT is Hermitian: vc[t, -q, :] = conj(vc[t, q, :])): the intermediate holds
+// only one wave vector h of every pair (q, -q); the tile contracts it twice -- with the eigenvectors of qmap[h].x as it
+// is, and with the CONJUGATED eigenvectors of the partner qmap[h].y (second half of eig[h]) followed by a conjugation of
+// the result: vq[-q, s] = sum conj(e[-q,s,j]) conj(vc[q,j]) = conj(sum conj(conj e[-q,s,j]) vc[q,j]), bit for bit what
+// the unpaired contraction of the explicitly stored vc[-q] gives.  Q is then the number of stored wave vectors.
+template <int MT, bool MIRROR>   // MT > 0: compile-time M (inputs kept in registers); 0: any M
 __global__ void __launch_bounds__(256)
 project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict__ eig, int64_t T, int Q, int Mdyn,
                              int q_block, int qt, int vc_pairs, int64_t t_offset, int64_t T_total,
-                             cplx* __restrict__ out, const __grid_constant__ PsBlocks blocks) {
+                             cplx* __restrict__ out, const __grid_constant__ PsBlocks blocks,
+                             const int2* __restrict__ qmap) {
     DP_DYNSMEM(cplx, sm);
     const int M = MT > 0 ? MT : Mdyn;
     const int pitch = qt * M + 1;                   // odd: conflict-free column reads
+    constexpr int NE = MIRROR ? 2 : 1;                  // eigenvector sets per stored wave vector
     cplx* in = sm;                                      // [PS_TT][pitch]
-    cplx* es = sm + (size_t)PS_TT * pitch;              // [qt][M*M]
+    cplx* es = sm + (size_t)PS_TT * pitch;              // [qt][NE][M*M]
     const int64_t t0 = (int64_t)blockIdx.x * PS_TT;
     const int q0 = blockIdx.y * qt;
     const int nq = imin(qt, Q - q0);
@@ -280,42 +287,54 @@ project_phonon_series_kernel(const cplx* __restrict__ vc, const cplx* __restrict
             in[f * pitch + (w >> 1) * M + pr * 2 + (w & 1)] = val;
         }
     }
-    for (int e = tid; e < nq * M * M; e += nthreads) es[e] = __ldg(eig + (int64_t)q0 * M * M + e);
+    for (int e = tid; e < nq * NE * M * M; e += nthreads) es[e] = __ldg(eig + (int64_t)q0 * NE * M * M + e);
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int64_t t = t0 + lane;
     const int np = M / 3;
     for (int qq = warp; qq < nq; qq += nwarps) {
-        const int q = q0 + qq;
         const cplx* row = in + lane * pitch + qq * M;
-        const cplx* e = es + qq * M * M;
-        cplx* dst = (blocks.n > 0 ? blocks.p[q / q_block] : out + (int64_t)(q / q_block) * q_block * M * T_total) +
-                    (int64_t)(q % q_block) * M * T_total + t_offset + t;
+        cplx a[MT > 0 ? MT : 1];
         if (MT > 0) {
-            cplx a[MT > 0 ? MT : 1];
 #pragma unroll
             for (int j = 0; j < MT; j++) a[j] = row[j];
+        }
 #pragma unroll
-            for (int s = 0; s < MT; s++) {
-                cplx acc = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int p = 0; p < MT / 3; p++) {
-                    cplx part = make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int k = 0; k < 3; k++) part = cadd(part, cmulc(a[p * 3 + k], e[s * MT + p * 3 + k]));
-                    acc = cadd(acc, part);
-                }
-                if (t < T) __stcs(dst + (int64_t)s * T_total, acc);
+        for (int side = 0; side < NE; side++) {
+            int q = q0 + qq;
+            if (MIRROR) {
+                const int2 qm = __ldg(qmap + q);
+                q = side ? qm.y : qm.x;
+                if (q < 0) continue;                  // self-conjugate wave vector (or a partner outside the list)
             }
-        } else {
-            for (int s = 0; s < M; s++) {
-                cplx acc = make_double2(0.0, 0.0);
-                for (int p = 0; p < np; p++) {
-                    cplx part = make_double2(0.0, 0.0);
-                    for (int k = 0; k < 3; k++) part = cadd(part, cmulc(row[p * 3 + k], e[s * M + p * 3 + k]));
-                    acc = cadd(acc, part);
+            const cplx* e = es + (qq * NE + side) * M * M;
+            cplx* dst = (blocks.n > 0 ? blocks.p[q / q_block] : out + (int64_t)(q / q_block) * q_block * M * T_total) +
+                        (int64_t)(q % q_block) * M * T_total + t_offset + t;
+            if (MT > 0) {
+#pragma unroll
+                for (int s = 0; s < MT; s++) {
+                    cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int p = 0; p < MT / 3; p++) {
+                        cplx part = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int k = 0; k < 3; k++) part = cadd(part, cmulc(a[p * 3 + k], e[s * MT + p * 3 + k]));
+                        acc = cadd(acc, part);
+                    }
+                    if (MIRROR && side) acc.y = -acc.y;
+                    if (t < T) __stcs(dst + (int64_t)s * T_total, acc);
                 }
-                if (t < T) __stcs(dst + (int64_t)s * T_total, acc);
+            } else {
+                for (int s = 0; s < M; s++) {
+                    cplx acc = make_double2(0.0, 0.0);
+                    for (int p = 0; p < np; p++) {
+                        cplx part = make_double2(0.0, 0.0);
+                        for (int k = 0; k < 3; k++) part = cadd(part, cmulc(row[p * 3 + k], e[s * M + p * 3 + k]));
+                        acc = cadd(acc, part);
+                    }
+                    if (MIRROR && side) acc.y = -acc.y;
+                    if (t < T) __stcs(dst + (int64_t)s * T_total, acc);
+                }
             }
         }
     }
@@ -425,15 +444,21 @@ int dp_project_phonon_series(const double* vc, const double* eig, int64_t T, int
     return dp_project_phonon_series_ex(vc, DP_VC_ROWS, eig, T, Q, M, q_block, t_offset, T_total, out, stream);
 }
 
+// qmap != nullptr: mirror form -- vc / eig hold Q stored wave vectors, the outputs are addressed on the full mesh of
+// Q_full wave vectors (see project_phonon_series_kernel)
 static int project_phonon_series_impl(const double* vc, int vc_layout, const double* eig, int64_t T, int Q, int M,
                                       int q_block, int64_t t_offset, int64_t T_total, double* out,
-                                      double* const* block_out, int n_blocks, void* stream) {
+                                      double* const* block_out, int n_blocks, void* stream,
+                                      const int* qmap = nullptr, int Q_full = 0) {
+    if (!qmap) Q_full = Q;
+    DP_REQUIRE(!qmap || vc_layout == DP_VC_PAIRS, DP_ERR_INVALID, "dp_project_phonon_series_mirror: needs the pair-major layout");
+    DP_REQUIRE(Q_full >= Q, DP_ERR_INVALID, "dp_project_phonon_series_mirror: Q_full=%d < stored Q=%d", Q_full, Q);
     DP_REQUIRE(vc_layout == DP_VC_ROWS || (vc_layout == DP_VC_PAIRS && M % 2 == 0), DP_ERR_INVALID,
                "dp_project_phonon_series: bad vc_layout %d (the pair-major layout needs an even M)", vc_layout);
     const int vc_pairs = vc_layout == DP_VC_PAIRS;
     DP_REQUIRE((T == 0 || (vc && (out || block_out))) && eig, DP_ERR_INVALID, "dp_project_phonon_series: null pointer");
     DP_REQUIRE(vc != out, DP_ERR_INVALID, "dp_project_phonon_series: cannot run in place (the output is transposed)");
-    DP_REQUIRE(q_block > 0 && Q % q_block == 0, DP_ERR_INVALID, "dp_project_phonon_series: q_block=%d must divide Q=%d", q_block, Q);
+    DP_REQUIRE(q_block > 0 && Q_full % q_block == 0, DP_ERR_INVALID, "dp_project_phonon_series: q_block=%d must divide Q=%d", q_block, Q_full);
     DP_REQUIRE(T >= 0 && Q > 0 && M > 0 && M % 3 == 0, DP_ERR_INVALID, "dp_project_phonon_series: bad sizes (M must be 3*n_prim)");
     DP_REQUIRE(t_offset >= 0 && t_offset + T <= T_total, DP_ERR_INVALID, "dp_project_phonon_series: frames [%lld, %lld) outside the series length %lld",
                (long long)t_offset, (long long)(t_offset + T), (long long)T_total);
@@ -441,9 +466,9 @@ static int project_phonon_series_impl(const double* vc, int vc_layout, const dou
     blocks.n = 0;
     for (int g = 0; g < dp::PS_MAX_BLOCKS; g++) blocks.p[g] = nullptr;
     if (block_out) {
-        DP_REQUIRE(n_blocks == Q / q_block && n_blocks <= dp::PS_MAX_BLOCKS, DP_ERR_INVALID,
+        DP_REQUIRE(n_blocks == Q_full / q_block && n_blocks <= dp::PS_MAX_BLOCKS, DP_ERR_INVALID,
                    "dp_project_phonon_series_peers: %d block pointers for Q/q_block = %d blocks (at most %d)", n_blocks,
-                   Q / q_block, dp::PS_MAX_BLOCKS);
+                   Q_full / q_block, dp::PS_MAX_BLOCKS);
         for (int g = 0; g < n_blocks; g++) {
             DP_REQUIRE(block_out[g] != nullptr && (const double*)block_out[g] != vc, DP_ERR_INVALID,
                        "dp_project_phonon_series_peers: bad pointer for block %d", g);
@@ -452,24 +477,31 @@ static int project_phonon_series_impl(const double* vc, int vc_layout, const dou
         blocks.n = n_blocks;
     }
     if (T == 0) return DP_OK;
-    const size_t per_q = ((size_t)dp::PS_TT * M + (size_t)M * M) * sizeof(dp::cplx);
+    const int ne = qmap ? 2 : 1;
+    const size_t per_q = ((size_t)dp::PS_TT * M + (size_t)ne * M * M) * sizeof(dp::cplx);
     const int qt = (int)dp::imax<size_t>(1, dp::imin<size_t>(dp::PS_QT_MAX, (size_t)(72 * 1024) / per_q));
     const unsigned gy = (unsigned)((Q + qt - 1) / qt);
     DP_REQUIRE(gy <= 65535, DP_ERR_UNSUPPORTED, "dp_project_phonon_series: Q=%d too large for one launch", Q);
-    size_t smem = ((size_t)dp::PS_TT * (qt * M + 1) + (size_t)qt * M * M) * sizeof(dp::cplx);
+    size_t smem = ((size_t)dp::PS_TT * (qt * M + 1) + (size_t)qt * ne * M * M) * sizeof(dp::cplx);
     DP_REQUIRE(smem <= 200 * 1024, DP_ERR_UNSUPPORTED, "dp_project_phonon_series: M=%d too large", M);
     dim3 grid((unsigned)((T + dp::PS_TT - 1) / dp::PS_TT), gy);
     cudaStream_t st = (cudaStream_t)stream;
-#define DP_PS_LAUNCH(MT)                                                                                          \
+#define DP_PS_LAUNCH(MT, MIRROR)                                                                                  \
     do {                                                                                                          \
-        auto k = dp::project_phonon_series_kernel<MT>;                                                            \
+        auto k = dp::project_phonon_series_kernel<MT, MIRROR>;                                                    \
         DP_CUDA_OK(DP_SET_SMEM(k, smem));                                                                         \
         DP_LAUNCH(k, grid, dim3(256), smem, st, (const dp::cplx*)vc, (const dp::cplx*)eig, T, Q, M, q_block,     \
-                  qt, vc_pairs, t_offset, T_total, (dp::cplx*)out, blocks);                                       \
+                  qt, vc_pairs, t_offset, T_total, (dp::cplx*)out, blocks, (const int2*)qmap);                    \
     } while (0)
-    if (M == 6) DP_PS_LAUNCH(6);
-    else if (M == 12) DP_PS_LAUNCH(12);
-    else DP_PS_LAUNCH(0);
+    if (qmap) {
+        if (M == 6) DP_PS_LAUNCH(6, true);
+        else if (M == 12) DP_PS_LAUNCH(12, true);
+        else DP_PS_LAUNCH(0, true);
+    } else {
+        if (M == 6) DP_PS_LAUNCH(6, false);
+        else if (M == 12) DP_PS_LAUNCH(12, false);
+        else DP_PS_LAUNCH(0, false);
+    }
 #undef DP_PS_LAUNCH
     DP_CUDA_OK(cudaGetLastError());
     return DP_OK;
@@ -487,6 +519,13 @@ int dp_project_phonon_series_peers(const double* vc, int vc_layout, const double
     DP_REQUIRE(block_out, DP_ERR_INVALID, "dp_project_phonon_series_peers: null pointer");
     return project_phonon_series_impl(vc, vc_layout, eig, T, Q, M, q_block, t_offset, T_total, nullptr, block_out,
                                       n_blocks, stream);
+}
+int dp_project_phonon_series_mirror(const double* vc, const double* eig2, const int* qmap, int64_t T, int Q_stored,
+                                    int Q, int M, int q_block, int64_t t_offset, int64_t T_total, double* out,
+                                    double* const* block_out, int n_blocks, void* stream) {
+    DP_REQUIRE(qmap && (out || block_out), DP_ERR_INVALID, "dp_project_phonon_series_mirror: null pointer");
+    return project_phonon_series_impl(vc, DP_VC_PAIRS, eig2, T, Q_stored, M, q_block, t_offset, T_total, out,
+                                      block_out, block_out ? n_blocks : 0, stream, qmap, Q);
 }
 
 }  // extern "C"

@@ -239,6 +239,35 @@ class Ops:
                       int(t_offset), t_total, be.ptr(out), be.stream())
         return out
 
+    def project_phonon_series_mirror(self, vc, eig2, qmap, Q, q_block=None, out=None, t_offset=0, t_total=None,
+                                     block_ptrs=None):
+        """Half-mesh contraction (dp_project_phonon_series_mirror): ``vc`` (T, M/2, Qh, 2) is the pair-major bare lattice
+        DFT of one wave vector of every pair (q, -q); ``qmap`` (Qh, 2) int32 gives the indices of the stored q and of its
+        partner in the full list of ``Q`` wave vectors (< 0: none), ``eig2`` (Qh, 2, M, M) the eigenvectors of the first
+        and the conjugated eigenvectors of the second.  Output as ``project_phonon_series`` for all Q wave vectors."""
+        be = self.be
+        vc = be.asarray(vc, np.complex128)
+        T, half_m, Qh, _ = be.shape(vc)
+        M = 2 * half_m
+        e = be.asarray(eig2, np.complex128)
+        qm = be.asarray(qmap, np.int32)
+        assert be.shape(e) == (Qh, 2, M, M) and be.shape(qm) == (Qh, 2), "mirror tables do not match vc"
+        Q = int(Q)
+        qb = Q if q_block is None else int(q_block)
+        t_total = T if t_total is None else int(t_total)
+        if block_ptrs is not None:
+            ptrs = (ctypes.c_void_p * len(block_ptrs))(*[int(a) for a in block_ptrs])
+            self.lib.call("dp_project_phonon_series_mirror", be.ptr(vc), be.ptr(e), be.ptr(qm), T, Qh, Q, M, qb,
+                          int(t_offset), t_total, None, ptrs, len(block_ptrs), be.stream())
+            return None
+        if out is None:
+            out = be.empty((Q // qb, qb * M, t_total), np.complex128)
+        else:
+            assert be.shape(out) == (Q // qb, qb * M, t_total), "bad `out` buffer"
+        self.lib.call("dp_project_phonon_series_mirror", be.ptr(vc), be.ptr(e), be.ptr(qm), T, Qh, Q, M, qb,
+                      int(t_offset), t_total, be.ptr(out), None, 0, be.stream())
+        return out
+
     def launch_count(self):
         return int(self.lib.cdll.dp_launch_count())
 

@@ -85,12 +85,37 @@ def project_q_list(ops, velocity, sqrt_mass, plan, positions, atom_type, project
     return out
 
 
+def mirror_pairs(qbin, dims):
+    """Pair every wave vector of a commensurate list with its negative: rows (i, j) with bins[j] == -bins[i] (mod dims),
+    each index in exactly one row; j = -1 for self-conjugate wave vectors and for those whose negative is not listed."""
+    qbin = np.asarray(qbin, dtype=np.int64).reshape(-1, 3)
+    dims = np.asarray(dims, dtype=np.int64)
+    key = lambda m: (int(m[0]) * int(dims[1]) + int(m[1])) * int(dims[2]) + int(m[2])
+    first = {}
+    for i, m in enumerate(qbin):
+        first.setdefault(key(m), []).append(i)
+    used = np.zeros(len(qbin), dtype=bool)
+    rows = []
+    for i, m in enumerate(qbin):
+        if used[i]:
+            continue
+        used[i] = True
+        j = -1
+        for cand in first.get(key((-m) % dims), ()):
+            if not used[cand]:
+                j = cand
+                used[cand] = True
+                break
+        rows.append((i, j))
+    return np.asarray(rows, dtype=np.int32).reshape(-1, 2)
+
+
 class MeshPipeline:
     """All q of a mesh at once, optionally time-sharded over the ranks of a torch.distributed group."""
 
     def __init__(self, plan, eigenvectors, frequency_range, dt, ops=None, group=None, algorithm=2,
                  mem_coefficients=1000, correlation_step=10, integration_method=1, correlation_weight=0,
-                 project_on_atom=-1):
+                 project_on_atom=-1, use_mirror=True):
         self.ops = ops if ops is not None else _ops.default_ops()
         self.plan = plan
         self.be = self.ops.be
@@ -127,6 +152,22 @@ class MeshPipeline:
                            else eigenvectors, dtype=np.complex128).reshape(self.Q, self.M, plan.n_prim, 3)
             e = e * np.conj(plan.twiddle)[:, None, :, None]
             self.d_eig_folded = self.be.asarray(e.reshape(self.Q, self.M, self.M), np.complex128)
+        # Velocities are real, so the bare lattice DFT is Hermitian, vc[t, -q] = conj(vc[t, q]): only one wave vector of
+        # every pair (q, -q) of the list is projected and stored, the contraction produces both members
+        # (dp_project_phonon_series_mirror) -- half the intermediate, bit-identical series.
+        self.mirror = False
+        if self.fold_twiddle and self.M % 2 == 0 and use_mirror:
+            qmap = mirror_pairs(np.asarray(plan.qbin), np.asarray(plan.dims))
+            if len(qmap) < self.Q:
+                ef = e.reshape(self.Q, self.M, self.M)
+                eig2 = np.zeros((len(qmap), 2, self.M, self.M), dtype=np.complex128)
+                eig2[:, 0] = ef[qmap[:, 0]]
+                has = qmap[:, 1] >= 0
+                eig2[has, 1] = np.conj(ef[qmap[has, 1]])
+                self.mirror = True
+                self.d_qmap = self.be.asarray(qmap, np.int32)
+                self.d_qbin_half = self.be.asarray(np.asarray(plan.qbin)[qmap[:, 0]], np.int32)
+                self.d_eig2 = self.be.asarray(eig2, np.complex128)
 
     # -- stages -----------------------------------------------------------------------------------
     def project(self, velocity):
@@ -166,6 +207,28 @@ class MeshPipeline:
         raise ValueError("Power spectrum algorithm number not found")
 
     # -- series-major path (the one run() uses) ---------------------------------------------------------
+    def project_chunk(self, velocity_chunk):
+        """Frames (Tc, N, 3) -> the intermediate of the series-major path: the pair-major bare lattice DFT of one wave
+        vector per pair (q, -q) when the twiddle rides on the eigenvectors (``mirror``), of every q otherwise."""
+        if self.mirror:
+            return self.ops.project_commensurate(velocity_chunk, self.plan.dims, self.plan.unit_type, self.plan.n_prim,
+                                                 self.d_qbin_half, None, pair_major=True)
+        if self.fold_twiddle:
+            return self.ops.project_commensurate(velocity_chunk, self.plan.dims, self.plan.unit_type, self.plan.n_prim,
+                                                 self.d_qbin, None, pair_major=self.M % 2 == 0)
+        return self.project(velocity_chunk)
+
+    def contract_chunk(self, vc, out=None, t_offset=0, t_total=None, block_ptrs=None):
+        """Intermediate of ``project_chunk`` -> series-major contracted series (see ``series``)."""
+        if self.mirror:
+            return self.ops.project_phonon_series_mirror(vc, self.d_eig2, self.d_qmap, self.Q, q_block=self.q_block, out=out,
+                                                         t_offset=t_offset, t_total=t_total, block_ptrs=block_ptrs)
+        if self.fold_twiddle:
+            return self.ops.project_phonon_series(vc, self.d_eig_folded, q_block=self.q_block, out=out, t_offset=t_offset,
+                                                  t_total=t_total, pair_major=self.M % 2 == 0, block_ptrs=block_ptrs)
+        return self.ops.project_phonon_series(vc, self.d_eig, q_block=self.q_block, out=out, t_offset=t_offset,
+                                              t_total=t_total, block_ptrs=block_ptrs)
+
     def series(self, velocity_local, chunk_frames=4096, out=None, t_offset=0, t_total=None, block_ptrs=None, mark=None):
         """Local frames -> series-major contracted series ``(G, (Q/G)*M, Tl)``: block g is the contiguous
         message for rank g, every (q, s) series is contiguous in time.  Projection and contraction run chunk
@@ -177,19 +240,10 @@ class MeshPipeline:
             out = be.empty((self.world, self.q_block * self.M, t_total), np.complex128)
         for t0 in range(0, tl, chunk_frames):
             t1 = min(t0 + chunk_frames, tl)
-            if self.fold_twiddle:
-                pm = self.M % 2 == 0        # pair-major intermediate: every transform stores one contiguous run
-                vc = self.ops.project_commensurate(velocity_local[t0:t1], self.plan.dims, self.plan.unit_type,
-                                                   self.plan.n_prim, self.d_qbin, None, pair_major=pm)
-                eig = self.d_eig_folded
-            else:
-                pm = False
-                vc = self.project(velocity_local[t0:t1])
-                eig = self.d_eig
+            vc = self.project_chunk(velocity_local[t0:t1])
             if mark is not None:
                 mark()                                   # between projection and contraction (stage timing)
-            self.ops.project_phonon_series(vc, eig, q_block=self.q_block, out=out, t_offset=t_offset + t0,
-                                           t_total=t_total, pair_major=pm, block_ptrs=block_ptrs)
+            self.contract_chunk(vc, out=out, t_offset=t_offset + t0, t_total=t_total, block_ptrs=block_ptrs)
             del vc
         return out
 

@@ -198,6 +198,21 @@ int dp_project_phonon_series_peers(const double* vc, int vc_layout, const double
                                    int q_block, int64_t t_offset, int64_t T_total, double* const* block_out,
                                    int n_blocks, void* stream);
 
+/* Contraction of a HALF mesh (projection.py:43-54 on top of the Hermitian symmetry of projection.py:24-37 for real
+ * velocities: without the per-atom twiddle, vc[t, -q, :] = conj(vc[t, q, :])).  vc is the pair-major intermediate
+ * (DP_VC_PAIRS) of dp_project_commensurate_ex with twiddle == NULL for Q_stored wave vectors h, one of every pair
+ * (q, -q) of the full list of Q wave vectors:
+ *   qmap [dev] Q_stored x 2 ints: index (in the full list) of the stored wave vector and of its partner -q
+ *              (< 0: none -- a self-conjugate q, or -q is not in the list)
+ *   eig2 [dev] Q_stored x 2 x M x M complex128: the eigenvectors of qmap[h][0], then the CONJUGATED eigenvectors of
+ *              qmap[h][1] (anything when there is no partner)
+ * Output as dp_project_phonon_series_ex / _peers (out, or block_out != NULL with n_blocks = Q / q_block pointers), for
+ * all Q wave vectors, bit-identical to contracting an explicitly projected full mesh: the intermediate and the
+ * projection's stores are half the size. */
+int dp_project_phonon_series_mirror(const double* vc, const double* eig2, const int* qmap, int64_t T, int Q_stored,
+                                    int Q, int M, int q_block, int64_t t_offset, int64_t T_total, double* out,
+                                    double* const* block_out, int n_blocks, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A7  power spectrum, FFT method (selector keys 2 and 3).
  * Replaces: get_fft_numpy_spectra / _numpy_power / _division_of_data

@@ -245,6 +245,44 @@ def test_pair_major_intermediate_layout(kops):
                           raw_rows.reshape(raw_rows.shape[0], nq, -1))
 
 
+@pytest.mark.parametrize("dims,n_prim,nt,drop", [((4, 3, 5), 2, 70, 0), ((2, 2, 2), 2, 33, 0), ((3, 4, 2), 4, 45, 3),
+                                                 ((6, 5, 4), 2, 64, 7)])
+def test_half_mesh_contraction_is_bit_identical(kops, dims, n_prim, nt, drop):
+    """dp_project_phonon_series_mirror: one wave vector of every pair (q, -q) projected and stored, both contracted --
+    the same bits as projecting and contracting the whole list (real velocities: vc[-q] = conj(vc[q]); projection.py:24-54).
+    Lists with self-conjugate points, with partners missing (`drop` wave vectors removed) and with q blocks."""
+    from dynaphopy_b200.pipeline import mirror_pairs
+    rng = np.random.default_rng(sum(dims) + nt)
+    dims = np.array(dims, dtype=np.int32)
+    nc = int(np.prod(dims))
+    m = 3 * n_prim
+    unit_type = np.arange(n_prim, dtype=np.int32)
+    v = rng.normal(size=(nt, n_prim * nc, 3))
+    qb = np.array([[x, y, z] for z in range(dims[2]) for y in range(dims[1]) for x in range(dims[0])], dtype=np.int32)
+    if drop:
+        qb = np.delete(qb, rng.choice(len(qb), size=drop, replace=False), axis=0)
+    nq = len(qb)
+    eig = rng.normal(size=(nq, m, m)) + 1j * rng.normal(size=(nq, m, m))
+    raw = kops.project_commensurate(v, dims, unit_type, n_prim, qb, None, pair_major=True)
+    q_block = nq // 2 if nq % 2 == 0 else nq
+    ref = to_np(kops.project_phonon_series(raw, eig, q_block=q_block, pair_major=True))
+    qmap = mirror_pairs(qb, dims)
+    assert sorted(int(i) for i in qmap.ravel() if i >= 0) == list(range(nq))          # every q exactly once
+    assert len(qmap) < nq or tuple(dims) == (2, 2, 2)          # 2 x 2 x 2: every wave vector is its own negative
+    eig2 = np.zeros((len(qmap), 2, m, m), dtype=complex)
+    eig2[:, 0] = eig[qmap[:, 0]]
+    has = qmap[:, 1] >= 0
+    eig2[has, 1] = np.conj(eig[qmap[has, 1]])
+    half = kops.project_commensurate(v, dims, unit_type, n_prim, qb[qmap[:, 0]], None, pair_major=True)
+    out = to_np(kops.project_phonon_series_mirror(half, eig2, qmap, nq, q_block=q_block))
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref)
+    # chunked in time, as the pipeline calls it
+    out2 = kops.project_phonon_series_mirror(half[:20], eig2, qmap, nq, q_block=q_block, t_total=nt)
+    out2 = to_np(kops.project_phonon_series_mirror(half[20:], eig2, qmap, nq, q_block=q_block, out=out2, t_offset=20, t_total=nt))
+    assert np.array_equal(out2, ref)
+
+
 def test_project_phonon_wide(kops):
     """M = 12 and 30 modes (GaN / larger cells), ragged frame count."""
     rng = np.random.default_rng(5)

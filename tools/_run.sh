@@ -1,6 +1,9 @@
-mkdir -p gpurun_out/r3g
-python -m pytest tests -x -q -m gpu -k "fft" > gpurun_out/r3g/pytest_fft.log 2>&1; tail -1 gpurun_out/r3g/pytest_fft.log
-for i in 1 2; do
-KB_S=1480 python tools/kbench.py fft 2>&1 | grep "series-major T=131072" | sed 's/^/new /' | tee -a gpurun_out/r3g/kb.log
-KB_S=1480 DYNAPHOPY_B200_LIB=tools/_variants/libdp_dev.so python tools/kbench.py fft 2>&1 | grep "series-major T=131072" | sed 's/^/old /' | tee -a gpurun_out/r3g/kb.log
+mkdir -p gpurun_out/r3i
+for f in "" "--full-mesh"; do
+python bench.py --skip-methods --skip-e2e --skip-cpu $f > gpurun_out/r3i/bench$f.json 2> gpurun_out/r3i/bench$f.err
+tail -c 300 gpurun_out/r3i/bench$f.err; python - <<P
+import json
+d=json.load(open('gpurun_out/r3i/bench$f.json'))
+print("$f", d['ms_per_step'], {k:(round(v['ms'],2), round(v.get('frac_of_hbm',0),3)) for k,v in d['stages'].items()}, d['parity'].get('cross_n'))
+P
 done
