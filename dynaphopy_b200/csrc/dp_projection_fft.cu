@@ -29,6 +29,7 @@ namespace dp {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // pencil pc: base = (pc % A)*sa + (pc / A)*sb, elements at base + i*st
+// (measured: the in-place 16-point codelet of dp_fft_reg.cuh in this pass removes the spills but is slower: 24.7 vs 24.1 ms)
 // The last decimation-in-time stage is done here rather than inside PencilDft<N>::run: the R sub-transforms read
 // their inputs straight from shared memory and the final butterflies store straight back, so only the N intermediate
 // values are live (2N doubles instead of the 4N-6N of the out-of-place codelet, which spilled for N >= 16 under the
@@ -128,10 +129,11 @@ struct PfUnit {
     bool hasA, hasB;
 };
 
-__device__ __noinline__ void pf_load(const PfUnit& u, int Nc, int Nx, int Px, int tid, int nthreads) {
+// (the phases take their operands as scalars: a struct passed by reference to a __noinline__ function lives on the
+// local-memory stack and every field costs a local load at the top of the phase)
+__device__ __noinline__ void pf_load(const double* __restrict__ srcA, const double* __restrict__ srcB, int Nc, int Nx,
+                                     int Px, int tid, int nthreads) {
     DP_DYNSMEM(cplx, W);
-    const double* __restrict__ srcA = u.srcA;
-    const double* __restrict__ srcB = u.srcB;
     // two real sequences -> one complex array.  PF_LD cells (2 * PF_LD independent 8-byte loads) are in flight per
     // thread (measured on B200, loads alone, T = 4096: 4 cells 0.376 ms, 10 cells 0.418 ms, 20 cells 0.501 ms)
     for (int c0 = tid; c0 < Nc; c0 += PF_LD * nthreads) {
@@ -153,15 +155,13 @@ __device__ __noinline__ void pf_load(const PfUnit& u, int Nc, int Nx, int Px, in
 // epilogue: separate the two real sequences (A = (C + conj D)/2, B = (C - conj D)/(2i) with C, D the bins
 // m(q), -m(q)), twiddle, store.  ACC: add to what earlier unit atoms of the same type already stored.
 template <bool ACC, bool TW>
-__device__ __noinline__ void pf_epilogue(const PfUnit& u, int npad, int Q, int n_unit, int tid, int nthreads) {
+__device__ __noinline__ void pf_epilogue(cplx* __restrict__ outA, cplx* __restrict__ outB, const cplx* __restrict__ twA,
+                                         const cplx* __restrict__ twB, int qstride_i, int flags, int npad, int Q,
+                                         int n_unit, int tid, int nthreads) {
     DP_DYNSMEM(cplx, W);
     const unsigned* __restrict__ qo = reinterpret_cast<const unsigned*>(W + npad + 1);   // packed bin offsets (m, -m)
-    const bool hasA = u.hasA, hasB = u.hasB;
-    const cplx* __restrict__ twA = u.twA;
-    const cplx* __restrict__ twB = u.twB;
-    cplx* __restrict__ outA = u.outA;
-    cplx* __restrict__ outB = u.outB;
-    const int64_t qstride = u.qstride;
+    const bool hasA = flags & 1, hasB = flags & 2;
+    const int64_t qstride = qstride_i;
     if (!ACC && hasA && hasB && qstride == 2 && outB == outA + 1 && (nthreads & 31) == 0) {
         // Pair-major layout: (A, B) of 32 consecutive q are 1 KB contiguous.  A lane computes ONE of the two
         // sequences (even lanes A, odd lanes B) of wave vector 16h + lane/2 of its group, so consecutive lanes hold
@@ -276,7 +276,7 @@ project_fft_kernel(const __grid_constant__ PfParams p) {
             u.twA = p.tw + (u.hasA ? tm.uA : 0);
             u.twB = p.tw + (u.hasB ? tm.uB : 0);
             __syncthreads();
-            if (!(p.skip & 1)) pf_load(u, Nc, Nx, Px, tid, nthreads);
+            if (!(p.skip & 1)) pf_load(u.srcA, u.srcB, Nc, Nx, Px, tid, nthreads);
             __syncthreads();
             if (!(p.skip & 2)) {
                 axis_pass(Nx, Ny * Nz, Ny * Nz, Px, 0, 1, tid, nthreads);
@@ -287,12 +287,13 @@ project_fft_kernel(const __grid_constant__ PfParams p) {
                 __syncthreads();
             }
             if (!(p.skip & 4)) {
+                const int fl = (u.hasA ? 1 : 0) | (u.hasB ? 2 : 0), qs = (int)u.qstride;
                 if (p.tw) {
-                    if (term) pf_epilogue<true, true>(u, p.npad, Q, n_unit, tid, nthreads);
-                    else pf_epilogue<false, true>(u, p.npad, Q, n_unit, tid, nthreads);
+                    if (term) pf_epilogue<true, true>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
+                    else pf_epilogue<false, true>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
                 } else {
-                    if (term) pf_epilogue<true, false>(u, p.npad, Q, n_unit, tid, nthreads);
-                    else pf_epilogue<false, false>(u, p.npad, Q, n_unit, tid, nthreads);
+                    if (term) pf_epilogue<true, false>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
+                    else pf_epilogue<false, false>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
                 }
             }
         }

@@ -1,6 +1,6 @@
 """One isolated call of a hot-path kernel at bench-relevant sizes, for `ncu --set full` captures.
 
-    python tools/prof_case.py fft5a|fft5b|project|contract|mem|corr [reps]
+    python tools/prof_case.py fft5a|fft5b|project|contract|dense|mem|corr [reps]
 """
 import itertools
 import os
@@ -39,11 +39,34 @@ elif case in ("project", "contract"):
     qb = torch.as_tensor(mm, device=dev)
     v = torch.randn((T, 2 * nc, 3), dtype=torch.float64, device=dev)
     eig = torch.randn((len(mm), 6, 6), dtype=torch.complex128, device=dev)
+    # as the pipeline runs it: bare lattice DFT of one wave vector per pair (q, -q) in the pair-major intermediate
+    # layout, both contracted (PC_FULL=1: the whole mesh)
+    from dynaphopy_b200.pipeline import mirror_pairs
+    qmap = mirror_pairs(mm, dims)
+    e_np = eig.cpu().numpy()
+    eig2 = np.zeros((len(qmap), 2, 6, 6), dtype=complex)
+    eig2[:, 0] = e_np[qmap[:, 0]]
+    has = qmap[:, 1] >= 0
+    eig2[has, 1] = np.conj(e_np[qmap[has, 1]])
+    eig2 = torch.as_tensor(eig2, device=dev)
+    qmap_d = torch.as_tensor(qmap, device=dev)
+    qb_half = torch.as_tensor(mm[qmap[:, 0]], device=dev)
+    full = os.environ.get("PC_FULL") == "1"
     for _ in range(reps):
-        # bare lattice DFT in the pair-major intermediate layout, as the pipeline runs it
-        vc = ops.project_commensurate(v, dims, [0, 1], 2, qb, None, pair_major=True)
+        vc = ops.project_commensurate(v, dims, [0, 1], 2, qb if full else qb_half, None, pair_major=True)
         if case == "contract":
-            vq = ops.project_phonon_series(vc, eig, pair_major=True)
+            vq = ops.project_phonon_series(vc, eig, pair_major=True) if full else \
+                ops.project_phonon_series_mirror(vc, eig2, qmap_d, len(mm))
+elif case == "dense":
+    # arbitrary (non-commensurate) wave vectors: the DMMA GEMM form of projection.py:24-31
+    T, N, Q = int(os.environ.get("PC_T", 2048)), 10240, int(os.environ.get("PC_Q", 512))
+    rng = np.random.default_rng(1)
+    pos = torch.as_tensor(rng.random((N, 3)) * 64.0, device=dev)
+    typ = np.repeat(np.arange(2), N // 2).astype(np.int32)
+    v = torch.randn((T, N, 3), dtype=torch.float64, device=dev)
+    qc = rng.normal(size=(Q, 3))
+    for _ in range(reps):
+        vc = ops.project_wave_vector(v, None, pos, typ, 2, qc)
 elif case == "mem":
     T, S = (int(os.environ.get("PC_T", 2500)), int(os.environ.get("PC_S", 592)))
     x = torch.randn((T, S), dtype=torch.complex128, device=dev)
