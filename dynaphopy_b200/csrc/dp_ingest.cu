@@ -24,10 +24,10 @@ namespace dp {
 
 struct MappedFile {
     const char* p = nullptr;
-    size_t n = 0;
+    size_t n = 0, mapped = 0;
     int fd = -1;
     ~MappedFile() {
-        if (p && n) munmap((void*)p, n);
+        if (p && mapped) munmap((void*)p, mapped);
         if (fd >= 0) close(fd);
     }
     int open_ro(const char* path) {
@@ -37,9 +37,16 @@ struct MappedFile {
         DP_REQUIRE(fstat(fd, &st) == 0, DP_ERR_INVALID, "cannot stat %s", path);
         n = (size_t)st.st_size;
         if (n == 0) return DP_OK;
-        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
-        DP_REQUIRE(m != MAP_FAILED, DP_ERR_INVALID, "cannot map %s: %s", path, strerror(errno));
+        // strtod / strtol need a terminator: reserve n + 1 bytes (rounded to pages) of anonymous zero memory and map the
+        // file over its start, so the byte after the last one of the file is always a readable NUL -- also when the
+        // file size is a multiple of the page size and the file ends inside a number (no trailing newline)
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+        mapped = (n + 1 + page - 1) / page * page;
+        void* m = mmap(nullptr, mapped, PROT_READ, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        DP_REQUIRE(m != MAP_FAILED, DP_ERR_INVALID, "cannot reserve %zu bytes for %s: %s", mapped, path, strerror(errno));
         p = (const char*)m;
+        void* f = mmap(m, n, PROT_READ, MAP_PRIVATE | MAP_FIXED, fd, 0);
+        DP_REQUIRE(f == m, DP_ERR_INVALID, "cannot map %s: %s", path, strerror(errno));
         madvise(m, n, MADV_SEQUENTIAL);
         return DP_OK;
     }

@@ -274,6 +274,36 @@ def _write_dump(path, frames, steps, bounds_lines, labels, extra_cols=0, rng=Non
                 f.write("   " + "   ".join(cols) + " \n")
 
 
+def test_lammps_ingest_page_aligned_file_without_trailing_newline(tmp_path):
+    """A dump whose size is an exact multiple of the page size and whose last byte belongs to a number (no trailing
+    newline, e.g. a file still being written): strtod must find a terminator behind the mapping."""
+    import mmap as _mmap
+    from dynaphopy_b200 import iofile
+    from dynaphopy_b200.structure import Structure
+    rng = np.random.default_rng(7)
+    st = Structure(cell=np.eye(3) * 4.0, positions=np.array([[0.0, 0, 0], [2.0, 2.0, 2.0]]), masses=[28.0855, 69.723])
+    bounds = ["0.0 8.0", "0.0 8.0", "0.0 8.0"]
+    frames = [rng.normal(scale=3.0, size=(16, 3)) for _ in range(40)]
+    path = str(tmp_path / "aligned.lammpstrj")
+    with open(path, "w") as f:
+        for i, fr in enumerate(frames):
+            f.write("ITEM: TIMESTEP\n%d\nITEM: NUMBER OF ATOMS\n16\nITEM: BOX BOUNDS pp pp pp\n" % i + "\n".join(bounds) + "\nITEM: ATOMS x y z\n")
+            f.write("\n".join(" ".join("%.10f" % v for v in row) for row in fr))
+            if i + 1 < len(frames):
+                f.write("\n")
+    size = os.path.getsize(path)
+    pad = (-size) % _mmap.PAGESIZE
+    # lengthen the last number with digits that do not change its value class (more decimals) up to the page boundary
+    with open(path, "a") as f:
+        f.write("1" * pad)
+    assert os.path.getsize(path) % _mmap.PAGESIZE == 0
+    dyn = iofile.read_lammps_trajectory(path, st, time_step=0.001, pinned=False)
+    assert dyn.trajectory.shape == (40, 16, 3)
+    last = float(("%.10f" % frames[-1][-1, -1]) + "1" * pad)
+    assert dyn.trajectory[-1, -1, -1].real == last
+    assert np.array_equal(dyn.trajectory[:-1].real, np.array([[[float("%.10f" % v) for v in row] for row in fr] for fr in frames[:-1]]))
+
+
 def test_lammps_ingest_synthetic(tmp_path):
     """dp_lammps_scan / dp_lammps_read + the read_lammps_trajectory mirror on dumps written here: positions with a
     tilted box and extra columns, a velocity dump, frame ranges, atom template, and the reference's error paths;
