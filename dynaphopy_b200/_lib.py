@@ -30,6 +30,7 @@ SIGNATURES = {
     "dp_project_commensurate_workspace_bytes": (_Z, [_P, _I, _I, _I]),
     "dp_project_commensurate": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _I, _I, _P, _P, _Z, _P]),
     "dp_project_commensurate_ex": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    "dp_project_commensurate_blocks": (_I, [_P, _P, _I, _P, _I, _L, _P, _I, _I, _P, _I, _P, _Z, _P]),
     "dp_project_phonon_series_ex": (_I, [_P, _I, _P, _L, _I, _I, _I, _L, _L, _P, _P]),
     "dp_project_phonon_series_peers": (_I, [_P, _I, _P, _L, _I, _I, _I, _L, _L, _P, _I, _P]),
     "dp_project_phonon_series_mirror": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _L, _L, _P, _P, _I, _P]),

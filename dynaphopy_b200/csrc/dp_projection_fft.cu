@@ -85,6 +85,7 @@ __device__ __forceinline__ void axis_pass(int n, int npencil, int A, int sa, int
 #undef DP_AXIS_CASE
 
 // ---------------- kernel ------------------------------------------------------------------------
+constexpr int PF_MAX_BLOCKS = 16;
 struct PfJob { int pA, kA, pB, kB, term0, nterms; };      // pB < 0: single sequence
 struct PfTerm { int uA, uB; };                              // uB < 0: none
 
@@ -98,6 +99,10 @@ struct PfParams {
     const cplx* tw;          // [Q][n_unit], or nullptr: no twiddle (raw lattice DFT of every unit atom)
     cplx* out;               // [T][Q][n_prim][3]
     int pair_major;          // output layout: 0 = out[t][q][3*n_prim], 1 = out[t][slot pair][q][2]
+    // pair-major output split into blocks of q_block wave vectors with their own base pointer (one per destination rank
+    // of the multi-GPU exchange): blocks[q / q_block][t][slot pair][q % q_block][2]; n_blocks == 0: one array (out)
+    int q_block, n_blocks;
+    cplx* blocks[PF_MAX_BLOCKS];
     int skip;                // development aid (DP_PF_SKIP): 1 = no loads, 2 = no transforms, 4 = no epilogue
 };
 
@@ -157,11 +162,14 @@ __device__ __noinline__ void pf_load(const double* __restrict__ srcA, const doub
 template <bool ACC, bool TW>
 __device__ __noinline__ void pf_epilogue(cplx* __restrict__ outA, cplx* __restrict__ outB, const cplx* __restrict__ twA,
                                          const cplx* __restrict__ twB, int qstride_i, int flags, int npad, int Q,
-                                         int n_unit, int tid, int nthreads) {
+                                         int n_unit, int tid, int nthreads, cplx* const* blk, int q_block,
+                                         int64_t row_off) {
     DP_DYNSMEM(cplx, W);
     const unsigned* __restrict__ qo = reinterpret_cast<const unsigned*>(W + npad + 1);   // packed bin offsets (m, -m)
     const bool hasA = flags & 1, hasB = flags & 2;
     const int64_t qstride = qstride_i;
+    // blk != nullptr (pair-major only): row_off is the offset of this (frame, slot pair) row inside a block, in
+    // elements; wave vector q lives in block q / q_block at column q % q_block (outA / outB are not used for stores)
     if (!ACC && hasA && hasB && qstride == 2 && outB == outA + 1 && (nthreads & 31) == 0) {
         // Pair-major layout: (A, B) of 32 consecutive q are 1 KB contiguous.  A lane computes ONE of the two
         // sequences (even lanes A, odd lanes B) of wave vector 16h + lane/2 of its group, so consecutive lanes hold
@@ -195,7 +203,12 @@ __device__ __noinline__ void pf_epilogue(cplx* __restrict__ outA, cplx* __restri
                 const double a2 = par ? D[j].x : C[j].y, b2 = par ? C[j].x : D[j].y;
                 cplx r = make_double2(0.5 * (a1 + b1), 0.5 * (a2 - b2));
                 if (TW) r = cmul(r, w[j]);
-                if (q[j] < Q) __stcs(outA + (int64_t)(q[j] - sub) * 2 + lane, r);
+                if (q[j] < Q) {
+                    if (blk) {
+                        const int b = q[j] / q_block;
+                        __stcs(blk[b] + row_off + (int64_t)(q[j] - b * q_block) * 2 + (lane & 1), r);
+                    } else __stcs(outA + (int64_t)(q[j] - sub) * 2 + lane, r);
+                }
             }
         }
         return;
@@ -224,8 +237,15 @@ __device__ __noinline__ void pf_epilogue(cplx* __restrict__ outA, cplx* __restri
                     if (hasB) rb = cadd(outB[q * qstride], rb);
                 }
                 // paired slots are adjacent: the two 16-byte stores of a thread fill one 32-byte sector
-                if (hasA) __stcs(outA + q * qstride, ra);
-                if (hasB) __stcs(outB + q * qstride, rb);
+                if (blk) {
+                    const int b = q / q_block;
+                    cplx* d = blk[b] + row_off + (int64_t)(q - b * q_block) * 2;
+                    if (hasA) __stcs(d, ra);
+                    if (hasB) __stcs(d + 1, rb);
+                } else {
+                    if (hasA) __stcs(outA + q * qstride, ra);
+                    if (hasB) __stcs(outB + q * qstride, rb);
+                }
             }
         }
     }
@@ -244,6 +264,8 @@ project_fft_kernel(const __grid_constant__ PfParams p) {
     if (tid == 0) W[p.npad] = make_double2(nan(""), nan(""));
     PfJob* sjobs = reinterpret_cast<PfJob*>(qo + ((Q + 3) & ~3));
     PfTerm* sterms = reinterpret_cast<PfTerm*>(sjobs + p.njobs);
+    cplx** sblk = reinterpret_cast<cplx**>(sterms + ((p.nterms + 1) & ~1));      // 16-byte aligned
+    if (tid < p.n_blocks) sblk[tid] = p.blocks[tid];
     for (int q = tid; q < Q; q += nthreads) {
         const int2 o = p.qoff[q];
         qo[q] = o.x < 0 ? ((unsigned)p.npad | ((unsigned)p.npad << 16)) : ((unsigned)o.x | ((unsigned)o.y << 16));
@@ -257,9 +279,11 @@ project_fft_kernel(const __grid_constant__ PfParams p) {
         const PfJob job = sjobs[(int)(unit % p.njobs)];
         const double* __restrict__ vt = p.v + t * (int64_t)p.N * 3;
         PfUnit u;
+        int64_t row_off = 0;
         if (p.pair_major) {       // jobs are exactly the slot pairs (2j, 2j+1): [t][j][q][2], contiguous per job
             const int j = (job.pA * 3 + job.kA) >> 1;
-            u.outA = p.out + ((t * (3 * p.n_prim / 2) + j) * Q) * 2;
+            u.outA = p.n_blocks > 0 ? p.blocks[0] : p.out + ((t * (3 * p.n_prim / 2) + j) * Q) * 2;
+            row_off = ((t * (3 * p.n_prim / 2) + j) * p.q_block) * 2;
             u.outB = job.pB >= 0 ? u.outA + 1 : nullptr;
             u.qstride = 2;
         } else {
@@ -288,12 +312,13 @@ project_fft_kernel(const __grid_constant__ PfParams p) {
             }
             if (!(p.skip & 4)) {
                 const int fl = (u.hasA ? 1 : 0) | (u.hasB ? 2 : 0), qs = (int)u.qstride;
+                cplx* const* blk = p.n_blocks > 0 ? sblk : nullptr;
                 if (p.tw) {
-                    if (term) pf_epilogue<true, true>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
-                    else pf_epilogue<false, true>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
+                    if (term) pf_epilogue<true, true>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads, blk, p.q_block, row_off);
+                    else pf_epilogue<false, true>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads, blk, p.q_block, row_off);
                 } else {
-                    if (term) pf_epilogue<true, false>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
-                    else pf_epilogue<false, false>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads);
+                    if (term) pf_epilogue<true, false>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads, blk, p.q_block, row_off);
+                    else pf_epilogue<false, false>(u.outA, u.outB, u.twA, u.twB, qs, fl, p.npad, Q, n_unit, tid, nthreads, blk, p.q_block, row_off);
                 }
             }
         }
@@ -348,10 +373,35 @@ int dp_project_commensurate(const double* v, const int* dims, int n_unit, const 
                                       DP_VC_ROWS, out_vc, workspace, workspace_bytes, stream);
 }
 
+static int project_commensurate_impl(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
+                                     int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
+                                     int vc_layout, double* out_vc, void* workspace, size_t workspace_bytes,
+                                     void* stream, int q_block, double* const* block_out, int n_blocks);
+
 int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
                                int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
                                int vc_layout, double* out_vc, void* workspace, size_t workspace_bytes,
                                void* stream) {
+    return project_commensurate_impl(v, dims, n_unit, unit_type, n_prim, T, qbin, twiddle, Q, project_on_atom, vc_layout,
+                                     out_vc, workspace, workspace_bytes, stream, Q, nullptr, 0);
+}
+
+int dp_project_commensurate_blocks(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
+                                   int64_t T, const int* qbin, int Q, int q_block, double* const* block_out, int n_blocks,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    DP_REQUIRE(block_out && q_block > 0 && Q % q_block == 0 && n_blocks == Q / q_block && n_blocks <= dp::PF_MAX_BLOCKS,
+               DP_ERR_INVALID, "dp_project_commensurate_blocks: %d block pointers for Q=%d in blocks of %d (at most %d blocks)",
+               n_blocks, Q, q_block, dp::PF_MAX_BLOCKS);
+    for (int g = 0; g < n_blocks; g++)
+        DP_REQUIRE(block_out[g] != nullptr, DP_ERR_INVALID, "dp_project_commensurate_blocks: null pointer for block %d", g);
+    return project_commensurate_impl(v, dims, n_unit, unit_type, n_prim, T, qbin, nullptr, Q, -1, DP_VC_PAIRS,
+                                     block_out[0], workspace, workspace_bytes, stream, q_block, block_out, n_blocks);
+}
+
+static int project_commensurate_impl(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
+                                     int64_t T, const int* qbin, const double* twiddle, int Q, int project_on_atom,
+                                     int vc_layout, double* out_vc, void* workspace, size_t workspace_bytes,
+                                     void* stream, int q_block, double* const* block_out, int n_blocks) {
     DP_REQUIRE(vc_layout == DP_VC_ROWS || vc_layout == DP_VC_PAIRS, DP_ERR_INVALID, "dp_project_commensurate: bad vc_layout %d", vc_layout);
     DP_REQUIRE(vc_layout == DP_VC_ROWS || (n_unit == n_prim && project_on_atom < 0 && (3 * n_prim) % 2 == 0), DP_ERR_INVALID,
                "dp_project_commensurate: the pair-major layout needs one unit-cell atom per type, no atom filter and an even 3*n_prim");
@@ -369,7 +419,8 @@ int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, con
     const int64_t Nc64 = (int64_t)Nx * Ny * Nz;
     const size_t smem_w = (size_t)Nz * Ny * Px * sizeof(dp::cplx);
     const size_t smem = smem_w + sizeof(dp::cplx) + dp::align_up((size_t)Q * sizeof(unsigned), 16) +
-                        (size_t)(2 * n_prim + 2) * sizeof(dp::PfJob) + (size_t)(3 * n_unit + 4) * sizeof(dp::PfTerm);
+                        (size_t)(2 * n_prim + 2) * sizeof(dp::PfJob) + (size_t)(3 * n_unit + 4) * sizeof(dp::PfTerm) +
+                        (size_t)dp::PF_MAX_BLOCKS * sizeof(void*);
     DP_REQUIRE((int64_t)Nz * Ny * Px <= 65535, DP_ERR_UNSUPPORTED,
                "dp_project_commensurate: %lld cells exceed the 16-bit bin offsets (use dp_project_wave_vector)", (long long)Nc64);
     DP_REQUIRE(smem <= 220 * 1024, DP_ERR_UNSUPPORTED,
@@ -423,6 +474,7 @@ int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, con
     for (int p : types) if (units[p].empty()) need_zero = true;
     for (const auto& j : jobs)
         if (j.pB >= 0 && units[j.pA].size() != units[j.pB].size()) need_zero = true;
+    DP_REQUIRE(!(need_zero && block_out), DP_ERR_INVALID, "dp_project_commensurate_blocks: needs one unit-cell atom per type");
     if (need_zero) DP_CUDA_OK(cudaMemsetAsync(out_vc, 0, (size_t)T * Q * n_prim * 3 * sizeof(dp::cplx), st));
     if (jobs.empty()) return DP_OK;
 
@@ -447,6 +499,8 @@ int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, con
     p.v = v; p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Px = Px; p.Nc = Nc; p.N = n_unit * Nc;
     p.n_unit = n_unit; p.n_prim = n_prim; p.Q = Q; p.njobs = (int)jobs.size(); p.nterms = (int)terms.size();
     p.npad = Nz * Ny * Px; p.T = T; p.pair_major = (vc_layout == DP_VC_PAIRS);
+    p.q_block = q_block; p.n_blocks = block_out ? n_blocks : 0;
+    for (int g = 0; g < dp::PF_MAX_BLOCKS; g++) p.blocks[g] = (block_out && g < n_blocks) ? (dp::cplx*)block_out[g] : nullptr;
     p.skip = dp::dev_env("DP_PF_SKIP") ? atoi(dp::dev_env("DP_PF_SKIP")) : 0;
     p.jobs = d_jobs; p.terms = d_terms; p.qoff = d_qoff; p.tw = (const dp::cplx*)twiddle; p.out = (dp::cplx*)out_vc;
     int per_sm = (int)dp::imin<size_t>(2, dp::imax<size_t>(1, (size_t)(226 * 1024) / (smem + 1024)));

@@ -189,6 +189,40 @@ class Ops:
                       nbytes, be.stream())
         return out
 
+    def project_commensurate_blocks(self, velocity, dims, unit_type, n_prim, qbin, q_block, block_ptrs=None, out=None):
+        """Pair-major bare lattice DFT split into ``Q / q_block`` arrays of shape (T, 3*n_prim/2, q_block, 2), one per
+        block of consecutive wave vectors of ``qbin`` (dp_project_commensurate_blocks).  ``block_ptrs``: device address
+        of every block (send slots / peer receive buffers); otherwise the blocks are the leading axis of ``out``
+        ``(Q / q_block, T, 3*n_prim/2, q_block, 2)`` (allocated when None), which is returned."""
+        be = self.be
+        v = be.asarray(velocity, np.float64)
+        T, N, _ = be.shape(v)
+        dims_h = _host(dims, np.int32)
+        ut = _host(unit_type, np.int32)
+        n_unit = ut.shape[0]
+        assert N == n_unit * int(np.prod(dims_h)), "atom count does not match dims * n_unit"
+        qb = be.asarray(qbin, np.int32)
+        Q = be.shape(qb)[0]
+        q_block = int(q_block)
+        assert Q % q_block == 0
+        nb = Q // q_block
+        nbytes = self.lib.size("dp_project_commensurate_workspace_bytes", _hptr(dims_h), n_unit, int(n_prim), Q)
+        ws = be.empty((nbytes,), np.uint8)
+        if block_ptrs is None:
+            shape = (nb, T, 3 * int(n_prim) // 2, q_block, 2)
+            if out is None:
+                out = be.empty(shape, np.complex128)
+            else:
+                assert be.shape(out) == shape and out.is_contiguous(), "bad `out` buffer"
+            step = T * (3 * int(n_prim) // 2) * q_block * 2 * 16
+            base = be.ptr(out).value or be.ptr(ws).value          # (T == 0: nothing is written)
+            block_ptrs = [base + g * step for g in range(nb)]
+        assert len(block_ptrs) == nb
+        ptrs = (ctypes.c_void_p * nb)(*[int(a) for a in block_ptrs])
+        self.lib.call("dp_project_commensurate_blocks", be.ptr(v), _hptr(dims_h), n_unit, _hptr(ut), int(n_prim), T,
+                      be.ptr(qb), Q, q_block, ptrs, nb, be.ptr(ws), nbytes, be.stream())
+        return out
+
     def project_phonon(self, vc, eigenvectors, q_block=None, out=None, inplace=False):
         """vc (T,Q,n_p,3) or (T,Q,M); eigenvectors (Q,M,n_p,3) or (Q,M,M) -> vq (T,Q,M).
 

@@ -165,6 +165,7 @@ class MeshPipeline:
                 has = qmap[:, 1] >= 0
                 eig2[has, 1] = np.conj(ef[qmap[has, 1]])
                 self.mirror = True
+                self._qmap_host, self._ef_host = qmap, ef
                 self.d_qmap = self.be.asarray(qmap, np.int32)
                 self.d_qbin_half = self.be.asarray(np.asarray(plan.qbin)[qmap[:, 0]], np.int32)
                 self.d_eig2 = self.be.asarray(eig2, np.complex128)
@@ -396,6 +397,100 @@ class MeshPipeline:
         return self._peer["recv"].reshape(g * nch, s_loc, tc)
 
     # -- chunk-cyclic time sharding: the spectra of finished windows run underneath the rest of the exchange -------
+    # -- multi-GPU: exchange the INTERMEDIATE instead of the contracted series ---------------------------------------
+    def intermediate_exchange_plan(self):
+        """Exchange plan for sending the half-mesh intermediate (one wave vector per pair (q, -q), 16*M bytes per frame)
+        to the rank that owns the pair, instead of the contracted series of both members (2 x 16*M bytes per frame):
+        half the bytes over NVLink, the contraction runs on the destination.  Needs both members of a pair on the same
+        rank, so the Q/G wave vectors of a rank are chosen pair by pair (``local_q``: the global index of every local
+        wave vector); ``restore_natural_order`` puts the finished spectra back into blocks of consecutive q.
+        Returns None when the half-mesh form is off or the pairs cannot be dealt evenly."""
+        if getattr(self, "_vcx", False) is not False:
+            return self._vcx
+        self._vcx = None
+        g, qb = self.world, self.q_block
+        if not self.mirror or g == 1 or g > 16 or os.environ.get("DP_NO_VC_EXCHANGE"):
+            return None
+        qmap = self._qmap_host
+        selfs = [tuple(r) for r in qmap if r[1] < 0]
+        pairs = [tuple(r) for r in qmap if r[1] >= 0]
+        # rank r takes s_r unpaired wave vectors with s_r = Q/G (mod 2) and (Q/G - s_r) / 2 pairs
+        s_r = [qb % 2] * g
+        left = len(selfs) - sum(s_r)
+        if left < 0 or left % 2:
+            return None
+        i = 0
+        while left > 0:
+            if s_r[i % g] + 2 <= qb:
+                s_r[i % g] += 2
+                left -= 2
+            i += 1
+            if i > 4 * g + len(selfs):
+                return None
+        if sum((qb - x) // 2 for x in s_r) != len(pairs):
+            return None
+        rows, si, pi = [], 0, 0
+        for r in range(g):
+            npair = (qb - s_r[r]) // 2
+            rows.append(selfs[si:si + s_r[r]] + pairs[pi:pi + npair])
+            si += s_r[r]
+            pi += npair
+        hb = max(len(x) for x in rows)
+        qbin = np.asarray(self.plan.qbin)
+        qbin_all = np.zeros((g, hb, 3), dtype=np.int32)            # padding rows project bin (0, 0, 0) and are ignored
+        local_q = []
+        qmap_loc = np.full((g, hb, 2), -1, dtype=np.int32)
+        for r in range(g):
+            lq = []
+            for k, (qa, qb_) in enumerate(rows[r]):
+                qbin_all[r, k] = qbin[qa]
+                qmap_loc[r, k, 0] = len(lq)
+                lq.append(qa)
+                if qb_ >= 0:
+                    qmap_loc[r, k, 1] = len(lq)
+                    lq.append(qb_)
+            assert len(lq) == qb
+            local_q.append(np.asarray(lq, dtype=np.int64))
+        mine = rows[self.rank]
+        eig2 = np.zeros((hb, 2, self.M, self.M), dtype=np.complex128)
+        for k, (qa, qb_) in enumerate(mine):
+            eig2[k, 0] = self._ef_host[qa]
+            if qb_ >= 0:
+                eig2[k, 1] = np.conj(self._ef_host[qb_])
+        self._vcx = {"hb": hb, "local_q": local_q,
+                     "d_qbin_all": self.be.asarray(qbin_all.reshape(g * hb, 3), np.int32),
+                     "d_qmap_loc": self.be.asarray(qmap_loc[self.rank], np.int32),
+                     "d_eig2_loc": self.be.asarray(eig2, np.complex128)}
+        return self._vcx
+
+    def restore_natural_order(self, ps_local):
+        """(F, (Q/G)*M) spectra of this rank's ``local_q`` wave vectors -> the spectra of the wave vectors
+        [rank*Q/G, (rank+1)*Q/G) in their natural order: one small all-to-all (8*F*M bytes per wave vector)."""
+        import torch
+        import torch.distributed as dist
+        vcx, g, qb, m = self._vcx, self.world, self.q_block, self.M
+        as_t = (lambda x: x) if torch.is_tensor(ps_local) else torch.from_numpy
+        pt = as_t(ps_local)
+        nf = pt.shape[0]
+        if "order" not in vcx:
+            lq = vcx["local_q"]
+            mine = lq[self.rank]
+            order = np.lexsort((mine, mine // qb))                                  # by destination, then by q
+            send_counts = [int(np.sum(mine // qb == d)) for d in range(g)]
+            recv_counts = [int(np.sum(lq[src] // qb == self.rank)) for src in range(g)]
+            nat = np.concatenate([np.sort(lq[src][lq[src] // qb == self.rank]) for src in range(g)]) - self.rank * qb
+            vcx["order"] = torch.as_tensor(order, device=pt.device)
+            vcx["nat"] = torch.as_tensor(nat, device=pt.device)
+            vcx["send_counts"], vcx["recv_counts"] = send_counts, recv_counts
+        rows = pt.t().reshape(qb, m * nf).index_select(0, vcx["order"]).contiguous()       # (q, s, f), grouped by destination
+        got = torch.empty_like(rows)
+        dist.all_to_all_single(got, rows, output_split_sizes=vcx["recv_counts"], input_split_sizes=vcx["send_counts"],
+                               group=self.group)
+        out = torch.empty_like(got)
+        out.index_copy_(0, vcx["nat"], got)
+        out = out.reshape(qb * m, nf).t().contiguous()
+        return out if torch.is_tensor(ps_local) else out.numpy()
+
     def cyclic_chunks(self, total_frames, chunk_frames):
         """Global frame ranges owned by this rank under chunk-cyclic sharding, in local order: chunk j of the
         trajectory belongs to rank j % G.  After round c (every rank has pushed its c-th chunk) the frames
@@ -406,11 +501,15 @@ class MeshPipeline:
         assert nch * g * chunk_frames == total_frames, "frames must be a multiple of ranks * chunk"
         return [((c * g + self.rank) * chunk_frames, (c * g + self.rank + 1) * chunk_frames) for c in range(nch)]
 
-    def run_cyclic(self, velocity_local, chunk_frames=4096, record=None):
+    def run_cyclic(self, velocity_local, chunk_frames=4096, record=None, natural_order=True):
         """Whole step on device-resident frames held chunk-cyclically (``cyclic_chunks``): per round project ->
         contract -> push (copy engines, peer memory); on a second stream, as soon as a round has landed on every rank
         (device barrier), the FFT spectra of the windows it completed.  Returns the (F, S_local) spectra.
-        ``record``: optional dict that receives CUDA-event stage times in ms."""
+        ``record``: optional dict that receives CUDA-event stage times in ms.
+        ``natural_order=False``: when the ranks exchange the intermediate (``intermediate_exchange_plan``), return the
+        spectra of this rank's wave vectors in ITS order (column j*M + s belongs to wave vector
+        ``intermediate_exchange_plan()["local_q"][rank][j]``) and skip the closing all-to-all that would sort them into
+        blocks of consecutive q -- for consumers that treat every mode on its own (peak fitting) the order is irrelevant."""
         import torch
         import torch.distributed as dist
         be = self.be
@@ -432,11 +531,11 @@ class MeshPipeline:
 
         # While later rounds are still being projected, contracted and pushed, the persistent spectrum kernel is kept
         # to a share of the SMs: a full-grid launch owns every SM for milliseconds (one CTA needs a whole SM's shared
-        # memory) and the kernels that feed the exchange would wait behind it.  DP_SPEC_CTAS: that share (default 3/4).
+        # memory) and the kernels that feed the exchange would wait behind it.  DP_SPEC_CTAS: that share (default 7/8; measured on 4 B200: 111 / 128 / 148 SMs -> 43.5 / 42.3 / 46.3 ms per step).
         sms = getattr(self, "_sms", None)
         if sms is None:
             sms = self._sms = int(self.ops.lib.cdll.dp_sm_count()) if hasattr(self.ops.lib, "cdll") else 0
-        share = int(os.environ.get("DP_SPEC_CTAS", max(1, sms * 3 // 4))) if (g > 1 and sms > 0) else 0
+        share = int(os.environ.get("DP_SPEC_CTAS", max(1, sms * 7 // 8))) if (g > 1 and sms > 0) else 0
 
         def windows_after(frames_complete, blocks):
             nonlocal done
@@ -451,6 +550,10 @@ class MeshPipeline:
                                            max_ctas=share if complete < len(pieces) else 0)
                 done += ready
 
+        vcx = self.intermediate_exchange_plan() if g > 1 else None
+        if vcx is not None:
+            return self._run_cyclic_intermediate(velocity_local, tc, nch, vcx, peers, fft, ws if fft else None,
+                                                 pieces if fft else None, share, record, natural_order)
         if not peers:
             # single rank, CPU test back-end, or no symmetric memory: one all-to-all per round, same data movement
             recv = be.empty((nch * g, s_loc, tc), np.complex128)
@@ -531,6 +634,150 @@ class MeshPipeline:
                     if os.environ.get("DP_CYCLIC_TRACE") and self.rank == 0:      # development aid: per-round timeline (ms)
                         t0 = ev[0][0]
                         print("cyclic trace:", [tuple(round(t0.elapsed_time(x), 2) for x in e) for e in ev], flush=True)
+        outer.wait_stream(hp)
+        if hasattr(ps, "record_stream"):
+            ps.record_stream(outer)
+        return ps
+
+    def _run_cyclic_intermediate(self, velocity_local, tc, nch, vcx, peers, fft, ws, pieces, share, record,
+                                 natural_order=True):
+        """``run_cyclic`` with the intermediate exchanged (``intermediate_exchange_plan``): per round the projection
+        writes one block of the half-mesh intermediate per destination rank (dp_project_commensurate_blocks: its own
+        straight into its receive buffer, the others into a send slot that copy engines push over NVLink); once a round
+        has landed everywhere the destination contracts the G received blocks into its series matrix (S_loc, T), plain
+        series-major, and the spectra of the windows that round completed follow on the same stream."""
+        import torch
+        import torch.distributed as dist
+        be = self.be
+        g, s_loc, hb, np2 = self.world, self.q_block * self.M, vcx["hb"], self.M // 2
+        T = tc * nch * g
+        blk_shape = (tc, np2, hb, 2)
+        nblk = int(np.prod(blk_shape))
+        if getattr(self, "_vcx_series", None) is None or tuple(self._vcx_series.shape) != (1, s_loc, T):
+            self._vcx_series = be.empty((1, s_loc, T), np.complex128)
+        series = self._vcx_series
+        done = 0
+
+        # The spectrum kernel is persistent (one CTA per SM for the whole launch): while rounds are in flight it is limited
+        # to `share` SMs, so that the projections, pushes and contractions of later rounds (high-priority streams) never
+        # wait for a whole launch.  DP_SPEC_SPLIT=n > 1 (experiment, measured slower on 4 B200: 43.5 / 44.6 / 47.4 ms for
+        # n = 6 / 3 / 12 against 42.3 ms): full-width launches over n sub-ranges of the series instead.
+        nsub = max(1, int(os.environ.get("DP_SPEC_SPLIT", 1))) if (fft and peers) else 1
+        if fft and nsub > 1:
+            bounds = [s_loc * i // nsub for i in range(nsub + 1)]
+            key = (T, s_loc, nsub)
+            if getattr(self, "_vcx_ws", None) is None or self._vcx_ws[0] != key:
+                self._vcx_ws = (key, [self.ops.power_fft_begin(T, bounds[i + 1] - bounds[i], self.dt, self.freq) for i in range(nsub)])
+            sub_ws = self._vcx_ws[1]
+
+        def windows_after(frames_complete):
+            nonlocal done
+            complete = sum(1 for p in pieces if p[1] <= frames_complete)
+            ready = complete - done
+            if complete < len(pieces) and not (done == 0 and nch <= len(pieces)):
+                ready = ready // 2 * 2
+            if ready > 0:
+                if nsub > 1:
+                    for i in range(nsub):
+                        self.ops.power_fft_windows(series[:, bounds[i]:bounds[i + 1], :], self.dt, self.freq, done, ready,
+                                                   sub_ws[i], series_major=True)
+                else:
+                    self.ops.power_fft_windows(series, self.dt, self.freq, done, ready, ws, series_major=True,
+                                               max_ctas=share if complete < len(pieces) else 0)
+                done += ready
+
+        def contract_round(c, blocks_of):
+            for src in range(g):
+                self.ops.project_phonon_series_mirror(blocks_of(src), vcx["d_eig2_loc"], vcx["d_qmap_loc"], self.q_block,
+                                                      q_block=self.q_block, out=series, t_offset=(c * g + src) * tc, t_total=T)
+
+        def project_round(c, ptrs):
+            self.ops.project_commensurate_blocks(velocity_local[c * tc:(c + 1) * tc], self.plan.dims, self.plan.unit_type,
+                                                 self.plan.n_prim, vcx["d_qbin_all"], hb, block_ptrs=ptrs)
+
+        def finish():
+            if fft and nsub > 1:
+                ps = torch.cat([self.ops.power_fft_finish(T, bounds[i + 1] - bounds[i], self.dt, self.freq, sub_ws[i])
+                                for i in range(nsub)], dim=1)
+            else:
+                ps = self.ops.power_fft_finish(T, s_loc, self.dt, self.freq, ws) if fft else self.spectra_series(series)
+            return self.restore_natural_order(ps) if natural_order else ps
+
+        if not peers:
+            # CPU test back-end or no symmetric memory: one all-to-all of the intermediate per round
+            send = be.empty((g,) + blk_shape, np.complex128)
+            recv = be.empty((g,) + blk_shape, np.complex128)
+            as_t = (lambda x: x) if torch.is_tensor(send) else torch.from_numpy
+            for c in range(nch):
+                project_round(c, [be.ptr(send).value + d * nblk * 16 for d in range(g)])
+                dist.all_to_all_single(torch.view_as_real(as_t(recv)), torch.view_as_real(as_t(send)), group=self.group)
+                contract_round(c, lambda src: recv[src])
+                if fft:
+                    windows_after((c + 1) * g * tc)
+            return finish()
+
+        outer = torch.cuda.current_stream(be.device)
+        if getattr(self, "_hp_stream", None) is None:
+            self._hp_stream = torch.cuda.Stream(device=be.device, priority=-1)
+        hp = self._hp_stream if not os.environ.get("DP_NO_HP_STREAM") else outer
+        hp.wait_stream(outer)
+        with torch.cuda.stream(hp):
+            pr = self._peer
+            self.peer_begin()
+            need = nch * g * nblk * 2
+            assert pr["flat"].numel() >= need, "receive buffer too small for the intermediate"
+            if "vcx_views" not in pr:
+                pr["vcx_views"] = [pr["hdl"].get_buffer(r, (nch, g) + blk_shape + (2,), torch.float64) for r in range(g)]
+                pr["vcx_recv"] = torch.view_as_complex(pr["flat"][:need].view(nch, g, *blk_shape, 2))
+                pr["vcx_send"] = be.empty((2, g) + blk_shape, np.complex128)
+                if "spec_stream" not in pr:
+                    pr["spec_stream"] = torch.cuda.Stream(device=be.device)
+            if "land_stream" not in pr:
+                pr["land_stream"] = torch.cuda.Stream(device=be.device, priority=-1)
+            send, recv, spec, land = pr["vcx_send"], pr["vcx_recv"], pr["spec_stream"], pr["land_stream"]
+            main = torch.cuda.current_stream(be.device)
+            spec.wait_stream(main)
+            land.wait_stream(main)
+            ev = []
+            for c in range(nch):
+                slot = c % 2
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.peer_wait_slot(slot)
+                a.record(main)
+                own = pr["ptrs"][self.rank] + ((c * g + self.rank) * nblk) * 16
+                project_round(c, [own if dst == self.rank else int(send[slot][dst].data_ptr()) for dst in range(g)])
+                b.record(main)
+                self.peer_push(send[slot], c, slot, views=pr["vcx_views"], index=(c, self.rank))
+                c0, c1, s1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                # the contraction of a landed round runs on its own high-priority stream: it is not queued behind the
+                # (long) spectrum kernels of earlier rounds, and its CTAs are placed before theirs
+                with torch.cuda.stream(land):
+                    land.wait_event(b)                                   # own block (written by the projection kernel)
+                    for e in pr["slot_free"][slot]:
+                        land.wait_event(e)                               # own pushes of this round
+                    pr["hdl"].barrier(channel=1)                         # ... and everybody else's
+                    c0.record(land)
+                    contract_round(c, lambda src: recv[c, src])
+                    c1.record(land)
+                with torch.cuda.stream(spec):
+                    spec.wait_event(c1)
+                    if fft:
+                        windows_after((c + 1) * g * tc)
+                    s1.record(spec)
+                    ev.append((a, b, c0, c1, s1))
+            main.wait_stream(land)
+            main.wait_stream(spec)
+            ps = finish()
+            if record is not None:
+                torch.cuda.synchronize()
+                record["project"] = sum(a.elapsed_time(b) for a, b, _, _, _ in ev)
+                record["contract"] = sum(c0.elapsed_time(c1) for _, _, c0, c1, _ in ev)
+                record["spectra"] = sum(c1.elapsed_time(s1) for _, _, _, c1, s1 in ev)          # overlapped with later rounds
+                record["exchange"] = max(0.0, ev[-1][1].elapsed_time(ev[-1][2]))                 # last round: projection end -> landed everywhere
+                record["span"] = ev[0][0].elapsed_time(ev[-1][4])
+                if os.environ.get("DP_CYCLIC_TRACE") and self.rank == 0:      # development aid: per-round timeline (ms)
+                    t0 = ev[0][0]
+                    print("cyclic trace:", [tuple(round(t0.elapsed_time(x), 2) for x in e) for e in ev], flush=True)
         outer.wait_stream(hp)
         if hasattr(ps, "record_stream"):
             ps.record_stream(outer)

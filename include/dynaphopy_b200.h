@@ -158,6 +158,14 @@ int dp_project_commensurate_ex(const double* v, const int* dims, int n_unit, con
                                int n_prim, int64_t T, const int* qbin, const double* twiddle, int Q,
                                int project_on_atom, int vc_layout, double* out_vc, void* workspace,
                                size_t workspace_bytes, void* stream);
+/* The pair-major bare lattice DFT (twiddle == NULL, DP_VC_PAIRS) written as n_blocks = Q / q_block separate arrays, one
+ * per block of q_block consecutive wave vectors of the list: block_out[g][((t * (3 n_prim / 2) + j) * q_block + qq) * 2 + c]
+ * for q = g * q_block + qq.  block_out is a HOST array of device pointers (<= 16), e.g. the send slots / the receive
+ * buffer of the multi-GPU exchange: each destination rank receives the intermediate of ITS wave vectors and contracts
+ * it there (half the exchange volume of the contracted series when the list holds one q per pair (q, -q)). */
+int dp_project_commensurate_blocks(const double* v, const int* dims, int n_unit, const int* unit_type, int n_prim,
+                                   int64_t T, const int* qbin, int Q, int q_block, double* const* block_out, int n_blocks,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * A3  eigenvector contraction, batched over q.

@@ -74,6 +74,21 @@ def main():
                     check("run_cyclic %s step %d" % (mode, step), pipe.run_cyclic(v_cyc, tc))
             for step in range(2):
                 check("run_from_host %s step %d" % (mode, step), pipe.run_from_host(v_host, chunk_frames=tc))
+        if alg == 2:
+            # run_cyclic above exchanged the half-mesh intermediate (when the pairs (q, -q) deal evenly over the ranks);
+            # the same step with the contracted series exchanged, and the intermediate through NCCL instead of peer memory
+            used = pipe.intermediate_exchange_plan() is not None
+            if rank == 0:
+                print("run_cyclic exchanged the %s" % ("half-mesh intermediate" if used else "contracted series"), flush=True)
+            os.environ["DP_NO_VC_EXCHANGE"] = "1"
+            p2 = pipeline.MeshPipeline(plan, eig, freq, dt, ops=ops, algorithm=alg)
+            for step in range(2):
+                check("run_cyclic series exchange %d" % step, p2.run_cyclic(v_cyc, tc))
+            del os.environ["DP_NO_VC_EXCHANGE"]
+            os.environ["DP_NO_PEER_EXCHANGE"] = "1"
+            p3 = pipeline.MeshPipeline(plan, eig, freq, dt, ops=ops, algorithm=alg)
+            check("run_cyclic intermediate, nccl", p3.run_cyclic(v_cyc, tc))
+            del os.environ["DP_NO_PEER_EXCHANGE"]
         os.environ["DP_NO_PEER_EXCHANGE"] = "1"                    # the NCCL all-to-all fallback
         fb = pipeline.MeshPipeline(plan, eig, freq, dt, ops=ops, algorithm=alg, mem_coefficients=40, correlation_weight=1)
         check("run nccl all_to_all", fb.run(v_blocks, tc))

@@ -277,6 +277,13 @@ def test_half_mesh_contraction_is_bit_identical(kops, dims, n_prim, nt, drop):
     out = to_np(kops.project_phonon_series_mirror(half, eig2, qmap, nq, q_block=q_block))
     assert out.shape == ref.shape
     assert np.array_equal(out, ref)
+    # the same intermediate written as per-destination blocks (dp_project_commensurate_blocks): block g holds the
+    # columns [g*hb, (g+1)*hb) of every (frame, slot pair) row
+    nh = len(qmap)
+    for hb in [d for d in range(1, nh + 1) if nh % d == 0 and nh // d <= 16]:
+        blocks = to_np(kops.project_commensurate_blocks(v, dims, unit_type, n_prim, qb[qmap[:, 0]], hb))
+        assert blocks.shape == (nh // hb, nt, m // 2, hb, 2)
+        assert np.array_equal(np.concatenate(list(blocks), axis=2), to_np(half))
     # chunked in time, as the pipeline calls it
     out2 = kops.project_phonon_series_mirror(half[:20], eig2, qmap, nq, q_block=q_block, t_total=nt)
     out2 = to_np(kops.project_phonon_series_mirror(half[20:], eig2, qmap, nq, q_block=q_block, out=out2, t_offset=20, t_total=nt))

@@ -160,17 +160,26 @@ def _rank_cyclic(rank, world, port_no, out_dir):
     assert chunks[0] == (rank * 96, rank * 96 + 96) and len(chunks) == 768 // (world * 96)
     v_local = np.concatenate([c["v"][a:b] for a, b in chunks])
     ps = pipe.run_cyclic(v_local, chunk_frames=96)
+    assert pipe.intermediate_exchange_plan() is not None and sorted(np.concatenate(pipe._vcx["local_q"])) == list(range(24))
     np.save(os.path.join(out_dir, f"psc{rank}.npy"), np.asarray(ps))
+    # the series-exchange form of the same step (DP_NO_VC_EXCHANGE) gives the same spectra
+    os.environ["DP_NO_VC_EXCHANGE"] = "1"
+    pipe2 = pipeline.MeshPipeline(c["plan"], c["eig"], c["freq"], c["dt"], ops=emul_ops(), algorithm=2)
+    ps2 = pipe2.run_cyclic(v_local, chunk_frames=96)
+    assert pipe2.intermediate_exchange_plan() is None
+    assert np.abs(np.asarray(ps2) - np.asarray(ps)).max() <= 1e-13 * np.abs(np.asarray(ps)).max()
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_chunk_cyclic_sharding_gloo(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_chunk_cyclic_sharding_gloo(tmp_path, world):
     """Chunk-cyclic time sharding (round c completes frames [0, (c+1)*G*chunk) on every rank; the spectra of finished
-    windows are launched round by round): 2 ranks, 4 rounds, 4 overlapping windows of 250 samples == oracle."""
+    windows are launched round by round): 2 ranks x 4 rounds / 4 ranks x 2 rounds, 4 overlapping windows of 250 samples
+    == oracle.  The ranks exchange the half-mesh INTERMEDIATE (MeshPipeline.intermediate_exchange_plan: every pair
+    (q, -q) lives on one rank, which contracts both members) and restore the natural q order with one small all-to-all."""
     import torch.multiprocessing as mp
-    world = 2
-    port_no = 29900 + os.getpid() % 90
+    port_no = 29900 + os.getpid() % 90 + world
     mp.spawn(_rank_cyclic, args=(world, port_no, str(tmp_path)), nprocs=world, join=True)
     c = make_case(nt=768, seed=7)
     assert len(set(map(tuple, port.division_of_data(c["freq"][1] - c["freq"][0], 768, c["dt"])))) == 4
