@@ -20,6 +20,11 @@ KEYS = {
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
     "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active": "dmma_inst_pct",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed": "tensor_cycles_active_pct",
+    "SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg": "dmma_cycles_active_avg",
+    "smsp__cycles_active.avg": "smsp_cycles_active_avg",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "fp64_inst_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "launch__registers_per_thread": "registers",
