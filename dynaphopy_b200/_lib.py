@@ -42,6 +42,7 @@ SIGNATURES = {
     "dp_power_fft_strided": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _D, _P, _P, _Z, _P]),
     "dp_power_fft_windows": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _I, _I, _P, _Z, _P]),
     "dp_power_fft_windows_ex": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "dp_power_fft_windows_preemptible": (_I, [_P, _L, _I, _L, _L, _L, _L, _D, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "dp_power_fft_finish": (_I, [_L, _I, _D, _P, _I, _D, _P, _P, _Z, _P]),
     "dp_power_fft_pieces": (_I, [_L, _D, _P, _I, _P, _P, _P, _I]),
     "dp_power_fft_engine": (_I, [_L, _D, _P, _I]),

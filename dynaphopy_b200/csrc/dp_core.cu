@@ -123,6 +123,7 @@ const char* dp_last_error(void) { return dp::g_err; }
 
 long long dp_launch_count(void) { return dp::launches(); }
 
+
 int dp_sm_count(void) {
     int n = dp::sm_count();
     if (n <= 0) {

@@ -289,7 +289,7 @@ spectrum_finalize_kernel(const double* __restrict__ spec, int S, int npieces, in
 }
 
 struct SpecLayout {
-    size_t off_tw[6], off_starts, off_idx0, off_mode, off_dx, off_den, off_spec, off_scratch, total;
+    size_t off_tw[6], off_starts, off_idx0, off_mode, off_dx, off_den, off_spec, off_scratch, off_claim, total;
     size_t slab_elems;
     int nslots;
 };
@@ -323,6 +323,7 @@ static SpecLayout spec_layout(const SpecHostPlan& pl, int S, int F) {
         l.nslots = (int)imin<int64_t>(S, batch);
     }
     l.off_scratch = o; o += align_up((size_t)l.nslots * l.slab_elems * sizeof(cplx), 256);
+    l.off_claim = o; o += align_up((size_t)imax(l.nslots, 1) * sizeof(int), 256);      // slab free list (preemptible form)
     l.total = o;
     return l;
 }
@@ -372,9 +373,30 @@ int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_
                                    0, workspace, workspace_bytes, stream);
 }
 
+static int power_fft_windows_impl(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                                  int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
+                                  int n_windows, int max_ctas, void* workspace, size_t workspace_bytes, void* stream,
+                                  bool preemptible);
+
 int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
                             int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
                             int n_windows, int max_ctas, void* workspace, size_t workspace_bytes, void* stream) {
+    return power_fft_windows_impl(series, T, S, stride_s, stride_t, tb_len, tb_stride, dt, freq, F, first_window, n_windows,
+                                  max_ctas, workspace, workspace_bytes, stream, false);
+}
+
+int dp_power_fft_windows_preemptible(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                                     int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F,
+                                     int first_window, int n_windows, int max_ctas, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    return power_fft_windows_impl(series, T, S, stride_s, stride_t, tb_len, tb_stride, dt, freq, F, first_window, n_windows,
+                                  max_ctas, workspace, workspace_bytes, stream, true);
+}
+
+static int power_fft_windows_impl(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                                  int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
+                                  int n_windows, int max_ctas, void* workspace, size_t workspace_bytes, void* stream,
+                                  bool preemptible) {
     DP_REQUIRE(series && freq && workspace, DP_ERR_INVALID, "dp_power_fft: null pointer");
     DP_REQUIRE(S > 0 && stride_t != 0, DP_ERR_INVALID, "dp_power_fft: bad S=%d stride_t=%lld", S, (long long)stride_t);
     DP_REQUIRE(tb_len >= 0 && tb_len < (1LL << 31), DP_ERR_INVALID, "dp_power_fft: bad time-block length %lld", (long long)tb_len);
@@ -446,7 +468,11 @@ int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stri
     double* spec = (double*)(ws + lay.off_spec);
     const int64_t items = (int64_t)S * (pl.use_v2 ? (n_windows + 1) / 2 : n_windows);
     int grid = (int)dp::imin<int64_t>(items, lay.nslots);
-    if (max_ctas > 0) grid = dp::imin(grid, max_ctas);          // leave SMs to work that runs concurrently on other streams
+    // leave SMs to work that runs concurrently on other streams: a fixed share of the grid, or (slab engine, preemptible
+    // form) one short-lived CTA per item, which lets the block scheduler honour stream priorities between items
+    const bool oneshot = preemptible && pl.use_v2 && items <= 0x7fffffff;
+    if (max_ctas > 0 && !oneshot) grid = dp::imin(grid, max_ctas);
+    const int n_slabs = grid;                                   // slabs (and rows of the tensor maps) behind the launch
     if (pl.use_v2) {
         dp::S2Params p;
         p.series = (const dp::cplx*)series; p.stride_s = stride_s; p.stride_t = stride_t;
@@ -468,7 +494,7 @@ int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stri
             p.slab_rows = (int)(lay.slab_elems / (size_t)n2);
             p.r_lo = dp::imin(n1, pl.s2.half / n2 + 1);
             p.r_hi = dp::imax(p.r_lo, (pl.s2.P - pl.s2.half) / n2);
-            const uint64_t rows = (uint64_t)grid * (uint64_t)p.slab_rows;
+            const uint64_t rows = (uint64_t)n_slabs * (uint64_t)p.slab_rows;
             const uint64_t pitch = (uint64_t)n2 * sizeof(dp::cplx);
             rc = dp::make_tensor_map_2d(&p.tm_col, p.scratch, 2ull * n2, rows, pitch, 2u * ns, (uint32_t)n1);
             if (rc) return rc;
@@ -483,6 +509,12 @@ int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stri
         while (p.park_cols < pl.s2.P / 64) p.park_cols *= 2;       // P doubles over 128 lanes: P / 128 * 2 columns
         p.skip_mask = dp::dev_env("DP_S2_SKIP") ? atoi(dp::dev_env("DP_S2_SKIP")) : 0;
         p.pair = (n_windows >= 2 && !(dp::dev_env("DP_S2_PAIR") && atoi(dp::dev_env("DP_S2_PAIR")) == 0)) ? 1 : 0;
+        p.slab_busy = nullptr; p.n_slabs = n_slabs;
+        if (oneshot) {
+            p.slab_busy = (int*)(ws + lay.off_claim);
+            DP_CUDA_OK(cudaMemsetAsync(p.slab_busy, 0, (size_t)n_slabs * sizeof(int), st));
+            grid = (int)items;
+        }
         auto k = dp::spectrum2_kernel;
         DP_CUDA_OK(DP_SET_SMEM(k, dp::S2_SMEM_BYTES));
         DP_LAUNCH(k, dim3(grid), dim3(dp::S2_THREADS), dp::S2_SMEM_BYTES, st, p);

@@ -72,6 +72,14 @@ struct S2Params {
     int slab_rows, r_lo, r_hi;
     TensorMap2D tm_col, tm_lo, tm_hi;
     int park, park_cols;           // |X_a|^2 parked in tensor memory (park_cols columns allocated) instead of the slab
+    // Preemptible form (dp_power_fft_windows_preemptible): ONE (series, window pair) item per CTA, grid = number of
+    // items, so the block scheduler can place CTAs of higher-priority streams whenever an item ends (~0.15 ms) instead of
+    // waiting for a persistent launch to finish.  A CTA then borrows one of `n_slabs` slabs for its lifetime: slab_busy
+    // [dev, n_slabs ints, zero when the launch starts] is the free list (one CTA per SM is resident at a time -- the
+    // kernel's shared memory fills an SM -- so n_slabs = number of SMs always leaves a free one).  slab_busy == nullptr:
+    // persistent form, CTA b owns slab b.
+    int* slab_busy;
+    int n_slabs;
 };
 
 struct S2Smem {
@@ -222,7 +230,7 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
         }
         s2_stage_publish();
         if (lane == 0) {
-            tma_store_2d(&p.tm_col, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows), Ew);
+            tma_store_2d(&p.tm_col, 2 * tile * C::NS, (int)((A - p.scratch) / n2), Ew);        // first row of this slab
             bulk_commit();
         }
         tile = s2_claim_get(next_raw);
@@ -379,8 +387,8 @@ __device__ __noinline__ void s2_pass3(const S2Params& p, cplx* __restrict__ A, S
             }
         s2_stage_publish();
         if (lane == 0) {
-            tma_store_2d(&p.tm_lo, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows), Ew);
-            if (PAIRED) tma_store_2d(&p.tm_hi, 2 * tile * C::NS, (int)(blockIdx.x * p.slab_rows) + r_hi, Ew + (size_t)r_hi * C::NS);
+            tma_store_2d(&p.tm_lo, 2 * tile * C::NS, (int)((A - p.scratch) / n2), Ew);
+            if (PAIRED) tma_store_2d(&p.tm_hi, 2 * tile * C::NS, (int)((A - p.scratch) / n2) + r_hi, Ew + (size_t)r_hi * C::NS);
             bulk_commit();
         }
         tile = s2_claim_get(next_raw);
@@ -557,7 +565,17 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
     S2Tiles ts;
     ts.counter = &s2_tile_counter;
     ts.base = 0;
-    cplx* A = p.scratch + (size_t)blockIdx.x * p.slab_elems;
+    __shared__ int s2_slab;
+    if (p.slab_busy) {
+        if (tid == 0) {
+            int slot = (int)(blockIdx.x % (unsigned)p.n_slabs);
+            while (atomicCAS(p.slab_busy + slot, 0, 1) != 0) slot = slot + 1 == p.n_slabs ? 0 : slot + 1;
+            s2_slab = slot;
+        }
+        __syncthreads();
+    }
+    const int slab = p.slab_busy ? s2_slab : (int)blockIdx.x;
+    cplx* A = p.scratch + (size_t)slab * p.slab_elems;
     double* Sr = reinterpret_cast<double*>(A + p.pl.P);            // [P] real: |X_a|^2 of a pair's first window
     const int layout = p.stride_t != 1 ? 2 : (p.tb_len == 0 ? 0 : (p.tb_shift >= 0 ? 1 : 2));
     const int npairs = p.pair ? (p.w_count + 1) / 2 : p.w_count;
@@ -606,6 +624,9 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
         __syncthreads();
     }
     if (p.park && warp == 0) tmem_free(tmem_base, (uint32_t)p.park_cols);      // every TMEM access precedes the barrier above
+    // the slab goes back to the free list: every access of this CTA to it (the bulk stores were drained at the end of
+    // their passes) precedes the barrier that closes the item
+    if (p.slab_busy && tid == 0) { __threadfence(); atomicExch(p.slab_busy + slab, 0); }
 }
 #undef DP_S2_PASS1
 #undef DP_S2_PASS1_L

@@ -368,13 +368,19 @@ class Ops:
         return self.be.empty((nbytes,), np.uint8)
 
     def power_fft_windows(self, series, dt, frequency_range, first_window, n_windows, workspace, series_major=False,
-                          max_ctas=0):
+                          max_ctas=0, preemptible=False):
         """Transform windows [first_window, first_window + n_windows) of every series into ``workspace``; reads
         no sample outside those windows (the rest of ``series`` may still be in production).  ``max_ctas``: SMs the
-        persistent kernel may occupy (0: all) -- leaves room for concurrent work of other streams."""
+        persistent kernel may occupy (0: all) -- leaves room for concurrent work of other streams.  ``preemptible``:
+        one short-lived CTA per item instead (dp_power_fft_windows_preemptible), for callers that rely on stream priorities."""
         be = self.be
         s, T, S, st = self._series_layout(series, series_major)
         f = _host(frequency_range, np.float64)
+        if preemptible:
+            self.lib.call("dp_power_fft_windows_preemptible", be.ptr(s), T, S, st[0], st[1], st[2], st[3], float(dt), _hptr(f),
+                          f.size, int(first_window), int(n_windows), int(max_ctas), be.ptr(workspace),
+                          int(workspace.numel() if hasattr(workspace, "numel") else workspace.size), be.stream())
+            return
         self.lib.call("dp_power_fft_windows_ex", be.ptr(s), T, S, st[0], st[1], st[2], st[3], float(dt), _hptr(f), f.size,
                       int(first_window), int(n_windows), int(max_ctas), be.ptr(workspace),
                       int(workspace.numel() if hasattr(workspace, "numel") else workspace.size), be.stream())

@@ -663,6 +663,10 @@ class MeshPipeline:
         # wait for a whole launch.  DP_SPEC_SPLIT=n > 1 (experiment, measured slower on 4 B200: 43.5 / 44.6 / 47.4 ms for
         # n = 6 / 3 / 12 against 42.3 ms): full-width launches over n sub-ranges of the series instead.
         nsub = max(1, int(os.environ.get("DP_SPEC_SPLIT", 1))) if (fft and peers) else 1
+        # default on the GPU: the PREEMPTIBLE form of the spectrum kernel (one short-lived CTA per item): the block
+        # scheduler places the high-priority projection / contraction CTAs between items and the spectra take every SM
+        # the rest of the time (DP_SPEC_PERSISTENT=1: persistent launches limited to `share` SMs, the older scheme)
+        preempt = bool(peers) and not os.environ.get("DP_SPEC_PERSISTENT")
         if fft and nsub > 1:
             bounds = [s_loc * i // nsub for i in range(nsub + 1)]
             key = (T, s_loc, nsub)
@@ -681,6 +685,8 @@ class MeshPipeline:
                     for i in range(nsub):
                         self.ops.power_fft_windows(series[:, bounds[i]:bounds[i + 1], :], self.dt, self.freq, done, ready,
                                                    sub_ws[i], series_major=True)
+                elif preempt:
+                    self.ops.power_fft_windows(series, self.dt, self.freq, done, ready, ws, series_major=True, preemptible=True)
                 else:
                     self.ops.power_fft_windows(series, self.dt, self.freq, done, ready, ws, series_major=True,
                                                max_ctas=share if complete < len(pieces) else 0)
@@ -729,18 +735,25 @@ class MeshPipeline:
             if "vcx_views" not in pr:
                 pr["vcx_views"] = [pr["hdl"].get_buffer(r, (nch, g) + blk_shape + (2,), torch.float64) for r in range(g)]
                 pr["vcx_recv"] = torch.view_as_complex(pr["flat"][:need].view(nch, g, *blk_shape, 2))
-                pr["vcx_send"] = be.empty((2, g) + blk_shape, np.complex128)
+                # one send slot per round while they fit in ~1/8 of the device memory (else a ring): the projections of
+                # all rounds then run back to back at the start of the step, never waiting for a slot to drain, and the
+                # copy engines work through the rounds at link speed
+                cap = int(torch.cuda.get_device_properties(be.device).total_memory // 8 // (g * nblk * 16))
+                nslots = max(2, min(nch, cap, int(os.environ.get("DP_VCX_SLOTS", nch))))
+                pr["vcx_send"] = be.empty((nslots, g) + blk_shape, np.complex128)
                 if "spec_stream" not in pr:
                     pr["spec_stream"] = torch.cuda.Stream(device=be.device)
             if "land_stream" not in pr:
                 pr["land_stream"] = torch.cuda.Stream(device=be.device, priority=-1)
             send, recv, spec, land = pr["vcx_send"], pr["vcx_recv"], pr["spec_stream"], pr["land_stream"]
+            nslots = send.shape[0]
+            pr["slot_free"] = [None] * nslots
             main = torch.cuda.current_stream(be.device)
             spec.wait_stream(main)
             land.wait_stream(main)
             ev = []
             for c in range(nch):
-                slot = c % 2
+                slot = c % nslots
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 self.peer_wait_slot(slot)
                 a.record(main)

@@ -260,6 +260,16 @@ int dp_power_fft_windows(const double* series, int64_t T, int S, int64_t stride_
 int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
                             int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F, int first_window,
                             int n_windows, int max_ctas, void* workspace, size_t workspace_bytes, void* stream);
+/* As dp_power_fft_windows_ex, PREEMPTIBLE form for pipelines that run urgent kernels on higher-priority streams (the
+ * multi-GPU pipeline: the projection / contraction kernels that feed and drain the exchange): the slab engine launches
+ * one short-lived CTA per (series, window pair) item instead of one persistent CTA per SM, so the block scheduler places
+ * the waiting high-priority CTAs whenever an item ends (~0.15 ms) and the spectrum CTAs take every SM back afterwards.
+ * Each CTA borrows one of the workspace's slabs through a free list in the workspace.  Same results; ~1 % more work per
+ * item (table loads, tensor-memory allocation).  Other engines: identical to dp_power_fft_windows_ex. */
+int dp_power_fft_windows_preemptible(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
+                                     int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F,
+                                     int first_window, int n_windows, int max_ctas, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 int dp_power_fft_finish(int64_t T, int S, double dt, const double* freq, int F, double scale, double* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 int dp_power_fft_pieces(int64_t T, double dt, const double* freq, int F, int* piece_len,

@@ -647,6 +647,24 @@ def test_power_mem_and_correlation_series_major_and_time_blocks(kops):
         assert np.array_equal(c, to_np(kops.power_correlation(blocks, dt, f, 10, method, 1, series_major=True)))
 
 
+def test_power_fft_preemptible_form_is_bit_identical(kops):
+    """dp_power_fft_windows_preemptible (one short-lived CTA per (series, window pair), slabs from a free list) gives the
+    bits of the persistent form, for pairs, a trailing single window and an incremental window range."""
+    rng = np.random.default_rng(77)
+    nt, dt, ns = 2600, 0.002, 21
+    x = np.ascontiguousarray(_series(rng, nt, ns, dt).T)                       # (S, T) series-major
+    f = np.arange(0, 30.0, 0.5)
+    L, pieces = kops.fft_pieces(nt, dt, f)
+    npieces = len({tuple(pc) for pc in pieces})
+    assert kops.fft_engine(nt, dt, f) == 2 and npieces >= 3
+    ref = to_np(kops.power_fft(x, dt, f, series_major=True))
+    ws = kops.power_fft_begin(nt, ns, dt, f)
+    kops.power_fft_windows(x, dt, f, 0, 2, ws, series_major=True, preemptible=True)
+    kops.power_fft_windows(x, dt, f, 2, npieces - 2, ws, series_major=True, preemptible=True, max_ctas=3)
+    out = to_np(kops.power_fft_finish(nt, ns, dt, f, ws))
+    assert np.array_equal(out, ref)
+
+
 def test_power_fft_incremental_windows(kops):
     """dp_power_fft_windows / dp_power_fft_finish: windows transformed in several calls (any split, even while
     later samples are still garbage) give exactly the one-shot spectrum."""
