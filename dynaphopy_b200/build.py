@@ -3,7 +3,7 @@
 nvcc cross-compiles for sm_100a without a GPU.  The built ``.so`` is git-ignored but travels
 to the GPU box with the gpurun snapshot.  ``build_emulator`` compiles the same sources for the
 host with ``-DDP_EMUL`` into ``tests/_emul_build/`` -- TEST INFRASTRUCTURE only (see
-``csrc/dp_emul.h``); the package never loads it.
+``tests/emul_include/dp_emul.h``); the package never loads it.
 """
 import glob
 import os
@@ -28,7 +28,7 @@ def _sources():
 
 def _deps():
     return _sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
-        glob.glob(os.path.join(ROOT, "include", "*.h"))
+        glob.glob(os.path.join(ROOT, "include", "*.h")) + glob.glob(os.path.join(ROOT, "tests", "emul_include", "*.h"))
 
 
 def _stale(target):
@@ -90,7 +90,7 @@ def build_emulator(force=False):
     for src in _sources():
         obj = os.path.join(EMUL_DIR, os.path.basename(src) + ".o")
         cmd = [gxx, "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-DDP_EMUL", "-ffp-contract=off", "-w",
-               "-c", src, "-o", obj]
+               "-I", os.path.join(ROOT, "tests", "emul_include"), "-c", src, "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
     subprocess.check_call([gxx, "-shared", "-o", EMUL_LIB] + objs + ["-lpthread"])

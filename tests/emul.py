@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE -- drive the kernels' host emulation build from numpy.
 
 ``emul_ops()`` returns a ``dynaphopy_b200.ops.Ops`` bound to tests/_emul_build/libdp_emul.so (the
-SAME .cu sources compiled with -DDP_EMUL, see dynaphopy_b200/csrc/dp_emul.h) and a numpy
+SAME .cu sources compiled with -DDP_EMUL, see tests/emul_include/dp_emul.h) and a numpy
 back-end, so that the CPU test-suite exercises the real kernel code paths (index algebra,
 barriers, shuffles) without a GPU.  Nothing in the dynaphopy_b200 package refers to this.
 """
