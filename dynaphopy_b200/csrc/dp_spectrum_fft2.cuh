@@ -118,6 +118,19 @@ __device__ __forceinline__ int64_t s2_time_offset(const S2Params& p, int t) {
     return (int64_t)b * p.tb_stride + (int64_t)(t - b * p.tb_len) * p.stride_t;
 }
 
+// streaming load of a window sample (evict-first); DP_S2_LD128 (experiment): with the 128-byte L2 prefetch size, so that
+// the 64-byte piece of the neighbouring column tile (same 128-byte line, fetched by another warp a moment later) is an
+// L2 hit -- measured neutral (4.83-4.85 ms per 1480 series either way), left off
+__device__ __forceinline__ cplx s2_ld_window(const cplx* ptr) {
+#if defined(DP_S2_LD128) && !defined(DP_EMUL)
+    cplx v;
+    asm volatile("ld.global.cs.L2::128B.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
+    return v;
+#else
+    return __ldcs(ptr);
+#endif
+}
+
 __device__ __forceinline__ void s2_prefetch_l2(const void* ptr) {
 #ifndef DP_EMUL
     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
@@ -204,11 +217,11 @@ __device__ __noinline__ void s2_pass1(const S2Params& p, const cplx* __restrict_
                 const int idx = (a * C::R2 + g + C::TG * i) * n2 + col;
                 cplx val = make_double2(0.0, 0.0);
                 if (idx < L) {
-                    if (LAYOUT == 0) val = __ldcs(x + t0 + idx);
+                    if (LAYOUT == 0) val = s2_ld_window(x + t0 + idx);
                     else if (LAYOUT == 1) {
                         const int t = t0 + idx, b = t >> tb_shift;
-                        val = __ldcs(x + (int64_t)b * tb_stride + (t - (b << tb_shift)));
-                    } else val = __ldcs(x + s2_time_offset(p, t0 + idx));
+                        val = s2_ld_window(x + (int64_t)b * tb_stride + (t - (b << tb_shift)));
+                    } else val = s2_ld_window(x + s2_time_offset(p, t0 + idx));
                 }
                 v[i * C::R1 + a] = val;
             }
