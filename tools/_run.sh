@@ -1,6 +1,10 @@
-mkdir -p gpurun_out/r4b
-for i in 1 2; do
-KB_S=1480 python tools/kbench.py fft 2>&1 | grep "series-major T=131072" | sed 's/^/base /' | cut -c1-120 | tee -a gpurun_out/r4b/kb.log
-KB_S=1480 DYNAPHOPY_B200_LIB=tools/_variants/libdp_dev.so python tools/kbench.py fft 2>&1 | grep "series-major T=131072" | sed 's/^/ld128 /' | cut -c1-120 | tee -a gpurun_out/r4b/kb.log
-done
-DYNAPHOPY_B200_LIB=tools/_variants/libdp_dev.so python -m pytest tests/test_parity.py -x -q -m gpu -k fft 2>&1 | tail -1
+mkdir -p gpurun_out/r4c
+O=gpurun_out/r4c
+python __graft_entry__.py --smoke > $O/smoke.log 2>&1; tail -2 $O/smoke.log
+python bench.py > $O/bench_g1.json 2> $O/bench_g1.err
+tail -c 300 $O/bench_g1.err
+python - <<P
+import json
+d=json.load(open('$O/bench_g1.json'))
+print(d['ms_per_step'], {k:(round(v['ms'],2), round(v.get('frac_of_hbm',0),3)) for k,v in d['stages'].items()}, 'e2e', d['e2e']['ms_per_step'], d['parity']['ok'], d['roofline']['frac'], d['roofline']['fp64']['frac'], d['clocks'])
+P
