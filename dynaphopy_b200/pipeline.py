@@ -301,7 +301,11 @@ class MeshPipeline:
             # one stream (copy engine) per destination and per slice of a block (DP_PEER_SPLIT slices, default 1)
             pr["split"] = max(1, int(os.environ.get("DP_PEER_SPLIT", 1)))
             nst = int(os.environ.get("DP_PEER_STREAMS", (self.world - 1) * pr["split"]))
-            pr["streams"] = [torch.cuda.Stream(device=dev) for _ in range(max(1, min((self.world - 1) * pr["split"], nst)))]
+            # (high priority: should a push be carried out by a copy kernel rather than a copy engine, its CTAs must not
+            # queue behind the persistent projection / spectrum grids)
+            prio = int(os.environ.get("DP_PUSH_PRIORITY", -1))
+            pr["streams"] = [torch.cuda.Stream(device=dev, priority=prio)
+                             for _ in range(max(1, min((self.world - 1) * pr["split"], nst)))]
             pr["slot_free"] = [None, None]
             nch, tc = pr["key"]
             s_loc = self.q_block * self.M
