@@ -52,6 +52,8 @@ def main():
     path = os.path.join(tempfile.gettempdir(), "dp_cfg3_vel.lammpstrj")
     t_write = write_dump(path, frames, n_atoms, np.diag(np.diag(dims) @ cell), rng)
     size = os.path.getsize(path)
+    torch.zeros(1, device="cuda")                            # CUDA context and the pinned allocator exist before the clock starts
+    torch.empty(1 << 20, dtype=torch.uint8).pin_memory()
     t0 = time.perf_counter()
     dyn = iofile.read_lammps_trajectory(path, st, time_step=0.001, pinned=True)
     t_read = time.perf_counter() - t0
