@@ -513,7 +513,12 @@ static int power_fft_windows_impl(const double* series, int64_t T, int S, int64_
         if (oneshot) {
             p.slab_busy = (int*)(ws + lay.off_claim);
             DP_CUDA_OK(cudaMemsetAsync(p.slab_busy, 0, (size_t)n_slabs * sizeof(int), st));
-            grid = (int)items;
+            // a CTA works on S2_PREEMPT_ITEMS items (stride = grid) before it leaves its SM.  Measured on an idle B200
+            // (tools/preempt_overhead.py, 1480 series x 7 windows; persistent form 4.74 ms): 1 item per CTA 4.87 ms, 4 items
+            // 4.89 ms -- with the slab chosen by SM number; with slabs handed out by block index (an SM keeps changing
+            // slabs, i.e. L2 lines) 5.07 / 5.11-5.21 ms.
+            grid = (int)dp::imax<int64_t>(n_slabs, (items + dp::S2_PREEMPT_ITEMS - 1) / dp::S2_PREEMPT_ITEMS);
+            grid = (int)dp::imin<int64_t>(grid, items);
         }
         auto k = dp::spectrum2_kernel;
         DP_CUDA_OK(DP_SET_SMEM(k, dp::S2_SMEM_BYTES));

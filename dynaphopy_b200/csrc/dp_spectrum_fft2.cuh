@@ -26,6 +26,10 @@ namespace dp {
 #endif
 constexpr int S2_THREADS = DP_S2_THREADS;          // 12 warps x <= 168 registers (measured best of 8 / 12 / 16 warps)
 constexpr int S2_WARPS = S2_THREADS / 32;
+#ifndef DP_S2_PREEMPT_ITEMS
+#define DP_S2_PREEMPT_ITEMS 1
+#endif
+constexpr int S2_PREEMPT_ITEMS = DP_S2_PREEMPT_ITEMS;   // items per CTA in the preemptible form (dp_power_fft_windows_preemptible)
 constexpr int S2_BINSLOTS = 8;                    // bins per residue thread in pass 4
 constexpr int S2_TILE_COLS = S2_THREADS / 16;     // pass-4 column tile: 16 threads per column
 constexpr int S2_NP_MAX = 192;                    // largest n1' of the menu
@@ -72,9 +76,9 @@ struct S2Params {
     int slab_rows, r_lo, r_hi;
     TensorMap2D tm_col, tm_lo, tm_hi;
     int park, park_cols;           // |X_a|^2 parked in tensor memory (park_cols columns allocated) instead of the slab
-    // Preemptible form (dp_power_fft_windows_preemptible): ONE (series, window pair) item per CTA, grid = number of
-    // items, so the block scheduler can place CTAs of higher-priority streams whenever an item ends (~0.15 ms) instead of
-    // waiting for a persistent launch to finish.  A CTA then borrows one of `n_slabs` slabs for its lifetime: slab_busy
+    // Preemptible form (dp_power_fft_windows_preemptible): S2_PREEMPT_ITEMS (series, window pair) items per CTA (one),
+    // grid = items / that, so the block scheduler can place CTAs of higher-priority streams whenever a CTA ends (~0.15 ms)
+    // instead of waiting for a persistent launch to finish.  A CTA then borrows one of `n_slabs` slabs for its lifetime: slab_busy
     // [dev, n_slabs ints, zero when the launch starts] is the free list (one CTA per SM is resident at a time -- the
     // kernel's shared memory fills an SM -- so n_slabs = number of SMs always leaves a free one).  slab_busy == nullptr:
     // persistent form, CTA b owns slab b.
@@ -583,7 +587,13 @@ spectrum2_kernel(const __grid_constant__ S2Params p) {
     __shared__ int s2_slab;
     if (p.slab_busy) {
         if (tid == 0) {
-            int slot = (int)(blockIdx.x % (unsigned)p.n_slabs);
+            // start the search at the SM's own number: an SM keeps re-using the same slab (and so the same L2 lines),
+            // as a persistent CTA does; with n_slabs = number of SMs the first try succeeds
+            unsigned smid = blockIdx.x;
+#ifndef DP_EMUL
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+#endif
+            int slot = (int)(smid % (unsigned)p.n_slabs);
             while (atomicCAS(p.slab_busy + slot, 0, 1) != 0) slot = slot + 1 == p.n_slabs ? 0 : slot + 1;
             s2_slab = slot;
         }

@@ -264,8 +264,8 @@ int dp_power_fft_windows_ex(const double* series, int64_t T, int S, int64_t stri
  * multi-GPU pipeline: the projection / contraction kernels that feed and drain the exchange): the slab engine launches
  * one short-lived CTA per (series, window pair) item instead of one persistent CTA per SM, so the block scheduler places
  * the waiting high-priority CTAs whenever an item ends (~0.15 ms) and the spectrum CTAs take every SM back afterwards.
- * Each CTA borrows one of the workspace's slabs through a free list in the workspace.  Same results; ~1 % more work per
- * item (table loads, tensor-memory allocation).  Other engines: identical to dp_power_fft_windows_ex. */
+ * Each CTA borrows the slab of the SM it runs on (free list in the workspace).  Same results; 3 % slower than the
+ * persistent form on an otherwise idle GPU (tools/preempt_overhead.py).  Other engines: as dp_power_fft_windows_ex. */
 int dp_power_fft_windows_preemptible(const double* series, int64_t T, int S, int64_t stride_s, int64_t stride_t,
                                      int64_t tb_len, int64_t tb_stride, double dt, const double* freq, int F,
                                      int first_window, int n_windows, int max_ctas, void* workspace,
