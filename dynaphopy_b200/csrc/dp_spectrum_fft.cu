@@ -470,7 +470,9 @@ static int power_fft_windows_impl(const double* series, int64_t T, int S, int64_
     int grid = (int)dp::imin<int64_t>(items, lay.nslots);
     // leave SMs to work that runs concurrently on other streams: a fixed share of the grid, or (slab engine, preemptible
     // form) one short-lived CTA per item, which lets the block scheduler honour stream priorities between items
-    const bool oneshot = preemptible && pl.use_v2 && items <= 0x7fffffff;
+    // (only when every CTA that can be resident at once finds a slab: one CTA fits an SM, so min(items, SMs) slabs)
+    const bool oneshot = preemptible && pl.use_v2 && items <= 0x7fffffff &&
+                         (int64_t)lay.nslots >= dp::imin<int64_t>(items, (int64_t)dp::imax(dp::sm_count(), 1));
     if (max_ctas > 0 && !oneshot) grid = dp::imin(grid, max_ctas);
     const int n_slabs = grid;                                   // slabs (and rows of the tensor maps) behind the launch
     if (pl.use_v2) {
