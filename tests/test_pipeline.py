@@ -146,6 +146,67 @@ def test_time_sharded_all_to_all_gloo(tmp_path, world):
         assert relerr(ps, c["ref_ps"][:, r * qb * 6:(r + 1) * qb * 6]) < 1e-10
 
 
+@pytest.mark.parametrize("dims,world", [((4, 2, 3), 2), ((4, 2, 3), 3), ((4, 2, 3), 4), ((4, 2, 3), 8), ((3, 3, 3), 3),
+                                        ((3, 3, 3), 9), ((5, 4, 3), 4), ((2, 2, 2), 2), ((6, 5, 4), 8)])
+def test_intermediate_exchange_plan_deals_pairs_evenly(dims, world):
+    """MeshPipeline.intermediate_exchange_plan (host logic of the multi-GPU intermediate exchange): every rank gets
+    exactly Q/G wave vectors, both members of a pair (q, -q) on the same rank, every q exactly once, the local tables
+    consistent with the global pairing -- or None when the pairs cannot be dealt evenly (the series exchange is used)."""
+    from emul import emul_ops
+    from dynaphopy_b200 import pipeline
+    dims = np.array(dims)
+    nc = int(np.prod(dims))
+    cell = np.diag([4.0, 4.1, 3.9])
+    unit = np.array([[0, 0, 0], [0.5, 0.5, 0.5]]) @ cell
+    grid = np.array([[x, y, z] for z in range(dims[2]) for y in range(dims[1]) for x in range(dims[0])], float) @ cell
+    pos = (unit[:, None, :] + grid[None]).reshape(-1, 3)
+    typ = np.repeat(np.arange(2), nc).astype(np.int32)
+    mass = np.repeat([28.0855, 69.723], nc)
+    m = np.array([[x, y, z] for z in range(dims[2]) for y in range(dims[1]) for x in range(dims[0])])
+    q_cart = (m / dims) @ (2.0 * np.pi * np.linalg.inv(cell).T)
+    rng = np.random.default_rng(int(dims.sum()) + world)
+    eig = rng.normal(size=(nc, 6, 6)) + 1j * rng.normal(size=(nc, 6, 6))
+    plan = pipeline.CommensuratePlan(cell, dims, pos, mass, typ, 2, q_cart)
+    pipe = pipeline.MeshPipeline(plan, eig, np.arange(0, 10.0, 0.5), 0.002, ops=emul_ops(), algorithm=2)
+    if nc % world:
+        return
+    qmap = pipeline.mirror_pairs(plan.qbin, plan.dims)
+    partner = {int(a): int(b) for a, b in qmap if b >= 0}
+    partner.update({b: a for a, b in list(partner.items())})
+    n_self = int((qmap[:, 1] < 0).sum())
+    seen = []
+    for rank in range(world):
+        pipe.world, pipe.rank, pipe.q_block, pipe._vcx = world, rank, nc // world, False
+        vcx = pipe.intermediate_exchange_plan()
+        qb = nc // world
+        feasible = pipe.mirror and world <= 16 and (n_self - world * (qb % 2)) >= 0 and (n_self - world * (qb % 2)) % 2 == 0
+        if not feasible:
+            assert vcx is None
+            return
+        assert vcx is not None
+        lq = vcx["local_q"][rank]
+        assert len(lq) == qb and len(set(lq.tolist())) == qb
+        for q in lq.tolist():                                  # both members of a pair on this rank
+            assert q not in partner or partner[q] in lq.tolist()
+        qm = np.asarray(vcx["d_qmap_loc"])
+        e2 = np.asarray(vcx["d_eig2_loc"])
+        ef = pipe._ef_host
+        bins = np.asarray(vcx["d_qbin_all"]).reshape(world, vcx["hb"], 3)[rank]
+        for k in range(vcx["hb"]):
+            a, b = int(qm[k, 0]), int(qm[k, 1])
+            if a < 0:
+                assert b < 0                                   # padding row
+                continue
+            assert np.array_equal(bins[k], np.asarray(plan.qbin)[lq[a]])
+            assert np.array_equal(e2[k, 0], ef[lq[a]])
+            if b >= 0:
+                assert partner[int(lq[a])] == int(lq[b]) and np.array_equal(e2[k, 1], np.conj(ef[lq[b]]))
+            else:
+                assert int(lq[a]) not in partner
+        seen += lq.tolist()
+    assert sorted(seen) == list(range(nc))
+
+
 def _rank_cyclic(rank, world, port_no, out_dir):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
